@@ -1,0 +1,166 @@
+/*
+ * p2w.h -- C ABI of libp2w.so, the sm_100a replacement for the neighbourhood-search and
+ * message-passing ops on PointsToWood's inference hot path.
+ *
+ * The reference reaches this path through Python wrappers around the dispatcher ops of
+ * torch_cluster / torch_scatter / torch_geometric (un-vendored; call sites below are in
+ * /root/reference/pointstowood).  Each entry point names the interface it replaces.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - row-major contiguous arrays, FP32 coordinates [N,3], int64 CSR `ptr` arrays
+ *     (ptr[b]..ptr[b+1] = rows of example/tile b; the `batch` vector must be sorted);
+ *   - no allocation and no host synchronisation inside: the caller passes outputs and
+ *     workspaces; work is enqueued on `stream` (a cudaStream_t) and is graph-capturable;
+ *   - returns 0, or a negative P2W_E* code with the text available from p2w_last_error().
+ */
+#ifndef P2W_H_
+#define P2W_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *p2w_stream_t; /* cudaStream_t */
+
+#define P2W_OK 0
+#define P2W_EINVAL (-1)   /* bad argument (the upstream TORCH_CHECK / AT_ASSERTM cases) */
+#define P2W_ECUDA (-2)    /* CUDA runtime error at launch */
+#define P2W_ENOGPU (-3)   /* no sm_100 device */
+
+#define P2W_MAX_K 128     /* upstream knn asserts k <= 100 */
+
+int p2w_version(void);
+const char *p2w_last_error(void);
+/* Number of SMs / compute capability of the current device (host query). */
+int p2w_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+
+/* ---- K1: exact k nearest neighbours -------------------------------------------------
+ * Replaces torch_cluster::knn (src/model.py:120 SA2/SA3 k=32; :149 knn_interpolate k=2).
+ * nbr[q*k+e] = global x index of the e-th nearest source of query q inside its own tile,
+ * ascending by (FP32 squared distance, index); -1 where the tile has fewer than k
+ * sources.  d2 (optional, may be NULL) receives the matching squared distances (1e10 pad). */
+int p2w_knn(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
+            int32_t num_tiles, int64_t nx, int64_t ny, int32_t k,
+            int32_t *nbr, float *d2, p2w_stream_t stream);
+
+/* ---- K2: radius search --------------------------------------------------------------
+ * Replaces torch_cluster::radius, CUDA semantics (src/model.py:118, r=0.08, max 32):
+ * the first max_nbr sources in ascending index order with d2 < (float)(r*r).
+ * nbr [ny,max_nbr] -1 padded, cnt [ny]. */
+int p2w_radius(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
+               int32_t num_tiles, int64_t nx, int64_t ny, double r, int32_t max_nbr,
+               int32_t *nbr, int32_t *cnt, p2w_stream_t stream);
+
+/* Compaction of a -1 padded [ny,k] table into upstream's [2,E] int64 edge list
+ * (row 0 = query index, row 1 = source index, query-major).  edge_offset [ny+1] is a
+ * caller workspace that receives the exclusive prefix sum of the per-query counts;
+ * E = edge_offset[ny].  Two calls: p2w_table_count fills edge_offset, then the caller
+ * reads E, allocates `edges` [2,E] and calls p2w_table_to_edges. */
+int p2w_table_count(const int32_t *nbr, int64_t ny, int32_t k, int64_t *edge_offset,
+                    p2w_stream_t stream);
+int p2w_table_to_edges(const int32_t *nbr, int64_t ny, int32_t k, const int64_t *edge_offset,
+                       int64_t num_edges, int64_t *edges, p2w_stream_t stream);
+
+/* ---- K3: farthest point sampling ----------------------------------------------------
+ * Replaces torch_cluster::fps (not called by the reference; BASELINE config 3).
+ * out_ptr [num_tiles+1] (device) = cumulative ceil(ratio * n_b), computed by the caller;
+ * start = first point of each tile (random_start=False); ties -> lowest index. */
+int p2w_fps(const float *src, const int64_t *ptr, const int64_t *out_ptr, int32_t num_tiles,
+            int64_t n, float *dist_ws /* [n] */, int64_t *out, p2w_stream_t stream);
+
+/* ---- K4: voxel grid ids and voxel representatives ----------------------------------
+ * p2w_colminmax: per-column min / max of pos [n,dim] (the start/end defaults of
+ * torch_cluster::grid).  mn/mx [dim].
+ * p2w_grid replaces torch_cluster::grid (src/model.py:104, src/preprocessing.py:33,58):
+ *   id = sum_d (int64)((pos[d]-start[d])/size[d]) * prod_{d'<d}((int64)((end-start)/size)+1).
+ * If batch != NULL an extra trailing column (float)batch[i] with size 1, start
+ * batch_start and end batch_end is appended (torch_geometric.nn.voxel_grid);
+ * start/end then hold dim+1 entries. */
+int p2w_colminmax(const float *pos, int64_t n, int32_t dim, int32_t ld, float *mn, float *mx,
+                  p2w_stream_t stream);
+int p2w_grid(const float *pos, int64_t n, int32_t dim, int32_t ld, const int64_t *batch,
+             const float *size, const float *start, const float *end, int64_t *ids,
+             p2w_stream_t stream);
+
+/* Stable LSD radix sort of (key, value) pairs on key bits [0, key_bits).
+ * ws: p2w_sort_ws_bytes(n) bytes.  Results land in keys_out / vals_out. */
+size_t p2w_sort_ws_bytes(int64_t n);
+int p2w_sort_pairs(const uint64_t *keys_in, const int32_t *vals_in, uint64_t *keys_out,
+                   int32_t *vals_out, int64_t n, int32_t key_bits, void *ws, p2w_stream_t stream);
+
+size_t p2w_unique_ws_bytes(int64_t n);
+/* torch_geometric consecutive_cluster (src/model.py:105) on SORTED keys with their
+ * original indices (ascending inside equal keys, as the stable sort leaves them):
+ * perm[u] = highest original index of the u-th distinct key, inverse[orig] = u (may be NULL),
+ * *num_unique (device int64) = number of distinct keys.  ws: p2w_unique_ws_bytes(n). */
+int p2w_unique_last(const uint64_t *sorted_keys, const int32_t *sorted_idx, int64_t n,
+                    int64_t *perm, int64_t *inverse, int64_t *num_unique, void *ws,
+                    p2w_stream_t stream);
+
+/* ---- K5: fused PointNetConv: gather -> per-edge MLP -> max --------------------------
+ * Replaces MessagePassing.propagate(aggr='max') around PointNetConv.message
+ * (src/pointnet.py:108,116-132) for local_nn = Lin(C+4,H) ReLU Lin(H,Co) ReLU BN(Co):
+ *   rel = pos_src[j,:3] - pos_tgt[i,:3];  m_i = max_j |rel|;
+ *   msg = [x[j], rel/(m_i+1e-8), pos_src[j,3]];  out[i] = max_j BN(ReLU(W2 ReLU(W1 msg+b1)+b2))
+ * over the valid entries j = nbr[i, :]; targets without neighbours get 0.
+ * x [n_src,C] fp32; pos_src [n_src,4], pos_tgt [n_tgt,4] (xyz already divided by sf,
+ * reflectance in column 3); w1 [H,C+4], w2 [Co,H] row-major (torch Linear layout);
+ * bn_scale/bn_shift [Co] = folded eval-mode BatchNorm; out [n_tgt,Co] fp32.
+ * mode: 0 = FP32 SIMT (parity mode, 1e-3), 1 = BF16 operands on tcgen05 tensor cores with
+ * FP32 accumulation in TMEM (1e-2).  The E x C' edge tensor is never written to HBM. */
+#define P2W_CONV_FP32 0
+#define P2W_CONV_BF16_TC 1
+int p2w_pointnet_conv_max(const float *x, const float *pos_src, const float *pos_tgt,
+                          const int32_t *nbr, int64_t n_src, int64_t n_tgt, int32_t k,
+                          int32_t c_in, int32_t hidden, int32_t c_out,
+                          const float *w1, const float *b1, const float *w2, const float *b2,
+                          const float *bn_scale, const float *bn_shift, float *out,
+                          int32_t mode, void *ws, size_t ws_bytes, p2w_stream_t stream);
+size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, int32_t mode);
+
+/* ---- knn_interpolate (src/model.py:149, torch_geometric.nn.knn_interpolate) ---------
+ * out[q,:] = sum_e w_e x[nbr[q,e],:] / sum_e w_e,  w_e = 1/max(|pos_x[nbr]-pos_y[q]|^2, 1e-16). */
+int p2w_knn_interpolate(const float *x, const float *pos_x, const float *pos_y,
+                        const int32_t *nbr, int64_t ny, int32_t k, int32_t c, int32_t ld_out,
+                        float *out, p2w_stream_t stream);
+
+/* ---- segment / scatter reductions ---------------------------------------------------
+ * p2w_segment_max: torch_geometric global_max_pool (src/model.py:136) for a sorted batch
+ * given as ptr: out[b,:] = max over rows ptr[b]..ptr[b+1] (0 for empty segments).
+ * p2w_scatter_minmax: torch_scatter::scatter_max / scatter_min along dim 0
+ * (src/pointnet.py:122, src/preprocessing.py:49): out [dim_size,c] (0 for empty slots),
+ * arg [dim_size,c] int64 (n for empty slots; lowest row on ties).  is_max: 1 max, 0 min. */
+int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_segments, int32_t c,
+                    float *out, p2w_stream_t stream);
+int p2w_scatter_minmax(const float *src, const int64_t *index, int64_t n, int32_t c,
+                       int64_t dim_size, int32_t is_max, float *out, int64_t *arg,
+                       p2w_stream_t stream);
+
+/* ---- K7 / K8 and SA glue ------------------------------------------------------------
+ * p2w_sa_prepare (src/model.py:109,122,124): pos4[i] = (pos[i]/sf[tile], refl[i]) and
+ * pos_back[i] = (pos[i]/sf[tile])*sf[tile] (the reference's in-place round trip, which
+ * perturbs coordinates by an ulp and feeds the next level).  tile id from ptr.
+ * p2w_pack (src/predicter.py:78-94 + PyG collate): gathers rows `index` of cloud [n,ld]
+ * (x,y,z,reflectance in columns 0..3) tile by tile, subtracts the per-tile mean
+ * (local_shift [B,3]) and returns sf[b] = max |pos|; pos [m,3], refl [m], batch [m].
+ * p2w_writeback (src/predicter.py:199-214): prob = sigmoid(nan_to_num(logit)),
+ * pred = prob >= is_wood, xyz = pos + local_shift[tile]; rows (x,y,z,pred,prob) as
+ * float64 [m,5] (out64) and/or compact prob [m] / pred [m]. */
+int p2w_sa_prepare(const float *pos, int32_t ld_pos, const float *refl, const int64_t *ptr,
+                   const float *sf, int32_t num_tiles, int64_t n, float *pos4, float *pos_back,
+                   p2w_stream_t stream);
+int p2w_pack(const float *cloud, int32_t ld, const int64_t *index, const int64_t *ptr,
+             int32_t num_tiles, int64_t m, float *pos, float *refl, int64_t *batch,
+             float *local_shift, float *sf, p2w_stream_t stream);
+int p2w_writeback(const float *logits, const float *pos, const int64_t *ptr,
+                  const float *local_shift, int32_t num_tiles, int64_t m, float is_wood,
+                  double *out64, float *prob, uint8_t *pred, p2w_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2W_H_ */

@@ -1,0 +1,299 @@
+// conv_simt.cu -- K5 in FP32: fused gather -> per-edge MLP -> max (the 1e-3 parity mode).
+//
+// Replaces MessagePassing.propagate(aggr='max') around PointNetConv.message
+// (src/pointnet.py:108,116-132).  One 128-thread CTA owns one target and its <= 32 edges:
+// lane = edge.  The gathered message tile [32, C+4] and the hidden tile [32, H] live in
+// shared memory (odd row strides: conflict-free column reads); the weights are read as
+// warp-uniform 128-bit loads from L1/L2 in a [K][N] layout, 8 output channels per lane in
+// registers.  BatchNorm is applied per edge BEFORE the max (its scale may be negative),
+// padded / missing edges are replaced by a duplicate of a valid one, so the [E, C'] edge
+// tensor never exists in HBM.
+#include "common.cuh"
+
+namespace p2w {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CONV_WARPS = 4;
+
+__global__ void transpose_kernel(const float *__restrict__ w, int rows, int cols, float *__restrict__ wt) {
+    // w [rows, cols] -> wt [cols, rows]
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<int64_t>(rows) * cols) return;
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+    wt[static_cast<int64_t>(c) * rows + r] = w[i];
+}
+
+// acc[8] += a * wt[k][n0..n0+8) for k in [0, K)
+__device__ __forceinline__ void dot8(const float *__restrict__ tile_row, int K, const float *__restrict__ wt, int N,
+                                     int n0, float acc[8]) {
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        const float a = tile_row[k];
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wt + static_cast<int64_t>(k) * N + n0));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(wt + static_cast<int64_t>(k) * N + n0 + 4));
+        acc[0] = fmaf(a, w0.x, acc[0]);
+        acc[1] = fmaf(a, w0.y, acc[1]);
+        acc[2] = fmaf(a, w0.z, acc[2]);
+        acc[3] = fmaf(a, w0.w, acc[3]);
+        acc[4] = fmaf(a, w1.x, acc[4]);
+        acc[5] = fmaf(a, w1.y, acc[5]);
+        acc[6] = fmaf(a, w1.z, acc[6]);
+        acc[7] = fmaf(a, w1.w, acc[7]);
+    }
+}
+
+__global__ void __launch_bounds__(CONV_WARPS * 32)
+    conv_simt_kernel(const float *__restrict__ x, const float *__restrict__ pos_src, const float *__restrict__ pos_tgt,
+                     const int32_t *__restrict__ nbr, int64_t n_tgt, int K, int C, int H, int Co,
+                     const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2t,
+                     const float *__restrict__ b2, const float *__restrict__ bn_scale,
+                     const float *__restrict__ bn_shift, float *__restrict__ out) {
+    extern __shared__ float smem[];
+    const int K1 = C + 4;
+    const int ldm = K1 | 1, ldh = H | 1;
+    float *msg = smem;                 // [32][ldm]
+    float *hid = smem + 32 * ldm;      // [32][ldh]
+    __shared__ int s_j[32];
+    __shared__ int s_any;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int64_t t = blockIdx.x; t < n_tgt; t += gridDim.x) {
+        // ---- edges of this target; padded slots duplicate the first valid neighbour
+        if (warp == 0) {
+            int j = (lane < K) ? nbr[t * K + lane] : -1;
+            const unsigned m = __ballot_sync(FULL, j >= 0);
+            if (m) {
+                const int jf = __shfl_sync(FULL, j, __ffs(m) - 1);
+                if (j < 0) j = jf;
+                const float dx = pos_src[static_cast<int64_t>(j) * 4 + 0] - pos_tgt[t * 4 + 0];
+                const float dy = pos_src[static_cast<int64_t>(j) * 4 + 1] - pos_tgt[t * 4 + 1];
+                const float dz = pos_src[static_cast<int64_t>(j) * 4 + 2] - pos_tgt[t * 4 + 2];
+                float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+                for (int o = 16; o; o >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(FULL, nrm, o));
+                const float den = nrm + 1e-8f;
+                msg[lane * ldm + C + 0] = dx / den;
+                msg[lane * ldm + C + 1] = dy / den;
+                msg[lane * ldm + C + 2] = dz / den;
+                msg[lane * ldm + C + 3] = pos_src[static_cast<int64_t>(j) * 4 + 3];
+            }
+            s_j[lane] = j;
+            if (lane == 0) s_any = m ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_any) {   // no edge: PyG's max aggregation leaves 0
+            for (int c = threadIdx.x; c < Co; c += CONV_WARPS * 32) out[t * Co + c] = 0.f;
+            __syncthreads();
+            continue;
+        }
+        // ---- gather x_j rows (coalesced along channels)
+        for (int e = warp; e < 32; e += CONV_WARPS) {
+            const float *row = x + static_cast<int64_t>(s_j[e]) * C;
+            for (int c = lane; c < C; c += 32) msg[e * ldm + c] = row[c];
+        }
+        __syncthreads();
+        // ---- layer 1: hid = relu(msg W1^T + b1)
+        for (int blk = warp; blk < H / 8; blk += CONV_WARPS) {
+            const int n0 = blk * 8;
+            float acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc[u] = b1[n0 + u];
+            dot8(msg + lane * ldm, K1, w1t, H, n0, acc);
+#pragma unroll
+            for (int u = 0; u < 8; u++) hid[lane * ldh + n0 + u] = fmaxf(acc[u], 0.f);
+        }
+        __syncthreads();
+        // ---- layer 2 + ReLU + BN, then max over the 32 edges
+        for (int blk = warp; blk < Co / 8; blk += CONV_WARPS) {
+            const int n0 = blk * 8;
+            float acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc[u] = b2[n0 + u];
+            dot8(hid + lane * ldh, H, w2t, Co, n0, acc);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                float v = fmaf(fmaxf(acc[u], 0.f), bn_scale[n0 + u], bn_shift[n0 + u]);
+                for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+                acc[u] = v;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (lane == u) out[t * Co + n0 + u] = acc[u];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ knn_interpolate
+// warp per query; lanes over channels.  w = 1 / max(|p_x - p_y|^2, 1e-16)
+__global__ void __launch_bounds__(256) interp_kernel(const float *__restrict__ x, const float *__restrict__ pos_x,
+                                                     const float *__restrict__ pos_y, const int32_t *__restrict__ nbr,
+                                                     int64_t ny, int k, int c, int ld_out, float *__restrict__ out) {
+    const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= ny) return;
+    int j = -1;
+    float w = 0.f;
+    if (lane < k) {
+        j = nbr[q * k + lane];
+        if (j >= 0) {
+            const float dx = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 0], pos_y[q * 3 + 0]);
+            const float dy = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 1], pos_y[q * 3 + 1]);
+            const float dz = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 2], pos_y[q * 3 + 2]);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            w = __fdiv_rn(1.0f, fmaxf(d2, 1e-16f));
+        }
+    }
+    float den = 0.f;
+    for (int e = 0; e < k; e++) den = __fadd_rn(den, __shfl_sync(FULL, w, e));
+    for (int c0 = 0; c0 < c; c0 += 32) {
+        const int ch = c0 + lane;
+        float num = 0.f;
+        for (int e = 0; e < k; e++) {
+            const int je = __shfl_sync(FULL, j, e);
+            const float we = __shfl_sync(FULL, w, e);
+            if (je >= 0 && ch < c) num = __fadd_rn(num, __fmul_rn(x[static_cast<int64_t>(je) * c + ch], we));
+        }
+        if (ch < c) out[q * ld_out + ch] = __fdiv_rn(num, den);
+    }
+}
+
+// ------------------------------------------------------------------ segment max (global_max_pool)
+__global__ void __launch_bounds__(128) segment_max_kernel(const float *__restrict__ x, const int64_t *__restrict__ ptr,
+                                                          int c, float *__restrict__ out) {
+    const int b = blockIdx.x;
+    const int ch = blockIdx.y * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    const int64_t r0 = ptr[b], r1 = ptr[b + 1];
+    float m = __int_as_float(0xff800000);
+    for (int64_t r = r0; r < r1; r++) m = fmaxf(m, x[r * c + ch]);
+    out[static_cast<int64_t>(b) * c + ch] = (r1 > r0) ? m : 0.f;
+}
+
+// ------------------------------------------------------------------ scatter max / min with arg
+__device__ __forceinline__ void atomic_max_f(float *a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_f(float *a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+
+__global__ void scatter_init_kernel(float *out, int64_t *arg, int64_t total, int is_max, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    out[i] = __int_as_float(is_max ? 0xff800000 : 0x7f800000);
+    if (arg) arg[i] = n;
+}
+__global__ void scatter_reduce_kernel(const float *__restrict__ src, const int64_t *__restrict__ index, int64_t n,
+                                      int c, int is_max, float *__restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    const int64_t r = i / c;
+    const int ch = static_cast<int>(i % c);
+    float *dst = out + index[r] * c + ch;
+    if (is_max) atomic_max_f(dst, src[i]); else atomic_min_f(dst, src[i]);
+}
+__global__ void scatter_arg_kernel(const float *__restrict__ src, const int64_t *__restrict__ index, int64_t n, int c,
+                                   const float *__restrict__ out, int64_t *__restrict__ arg) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    const int64_t r = i / c;
+    const int ch = static_cast<int>(i % c);
+    const int64_t o = index[r] * c + ch;
+    if (src[i] == out[o]) atomicMin(reinterpret_cast<long long *>(arg + o), static_cast<long long>(r));
+}
+__global__ void scatter_final_kernel(float *out, const int64_t *arg, int64_t total, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float v = out[i];
+    if (isinf(v) && (arg ? arg[i] == n : true)) out[i] = 0.f;
+}
+
+}  // namespace
+}  // namespace p2w
+
+using namespace p2w;
+
+int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
+                       int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out, const float *w1,
+                       const float *b1, const float *w2, const float *b2, const float *bn_scale,
+                       const float *bn_shift, float *out, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out);
+
+extern "C" size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, int32_t mode) {
+    if (mode == P2W_CONV_BF16_TC) return p2w_conv_tc_ws_bytes(c_in, hidden, c_out);
+    return sizeof(float) * (static_cast<size_t>(c_in + 4) * hidden + static_cast<size_t>(hidden) * c_out) + 256;
+}
+
+extern "C" int p2w_pointnet_conv_max(const float *x, const float *pos_src, const float *pos_tgt, const int32_t *nbr,
+                                     int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden,
+                                     int32_t c_out, const float *w1, const float *b1, const float *w2, const float *b2,
+                                     const float *bn_scale, const float *bn_shift, float *out, int32_t mode, void *ws,
+                                     size_t ws_bytes, p2w_stream_t stream) {
+    P2W_REQUIRE(k >= 1 && k <= 32, "p2w_pointnet_conv_max: k=%d outside [1,32]", k);
+    P2W_REQUIRE(c_in >= 1 && hidden % 8 == 0 && c_out % 8 == 0 && hidden > 0 && c_out > 0,
+                "p2w_pointnet_conv_max: hidden=%d and c_out=%d must be positive multiples of 8", hidden, c_out);
+    P2W_REQUIRE(mode == P2W_CONV_FP32 || mode == P2W_CONV_BF16_TC, "p2w_pointnet_conv_max: unknown mode %d", mode);
+    P2W_REQUIRE(ws_bytes >= p2w_pointnet_conv_ws_bytes(c_in, hidden, c_out, mode),
+                "p2w_pointnet_conv_max: workspace too small");
+    if (n_tgt == 0) return P2W_OK;
+    cudaStream_t st = as_stream(stream);
+    if (mode == P2W_CONV_BF16_TC)
+        return p2w_conv_tc_launch(x, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out, w1, b1, w2, b2,
+                                  bn_scale, bn_shift, out, ws, ws_bytes, st);
+    const int K1 = c_in + 4;
+    float *w1t = static_cast<float *>(ws);
+    float *w2t = w1t + static_cast<size_t>(K1) * hidden;
+    // 16-byte alignment of the second panel for the float4 loads
+    w2t = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(w2t) + 15) & ~uintptr_t(15));
+    transpose_kernel<<<(K1 * hidden + 255) / 256, 256, 0, st>>>(w1, hidden, K1, w1t);
+    transpose_kernel<<<(hidden * c_out + 255) / 256, 256, 0, st>>>(w2, c_out, hidden, w2t);
+    const size_t smem = sizeof(float) * 32 * ((K1 | 1) + (hidden | 1));
+    P2W_REQUIRE(smem <= 200 * 1024, "p2w_pointnet_conv_max: layer too wide for the FP32 kernel");
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(conv_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set = smem;
+    }
+    int64_t grid = n_tgt < 148 * 16 ? n_tgt : 148 * 16;
+    conv_simt_kernel<<<(unsigned)grid, CONV_WARPS * 32, smem, st>>>(x, pos_src, pos_tgt, nbr, n_tgt, k, c_in, hidden,
+                                                                    c_out, w1t, b1, w2t, b2, bn_scale, bn_shift, out);
+    return check_launch("p2w_pointnet_conv_max");
+}
+
+extern "C" int p2w_knn_interpolate(const float *x, const float *pos_x, const float *pos_y, const int32_t *nbr,
+                                   int64_t ny, int32_t k, int32_t c, int32_t ld_out, float *out,
+                                   p2w_stream_t stream) {
+    P2W_REQUIRE(k >= 1 && k <= 32, "p2w_knn_interpolate: k=%d outside [1,32]", k);
+    P2W_REQUIRE(c >= 1 && ld_out >= c, "p2w_knn_interpolate: bad channel count / stride");
+    if (ny == 0) return P2W_OK;
+    interp_kernel<<<(unsigned)((ny * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(x, pos_x, pos_y, nbr, ny, k, c,
+                                                                                    ld_out, out);
+    return check_launch("p2w_knn_interpolate");
+}
+
+extern "C" int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_segments, int32_t c, float *out,
+                               p2w_stream_t stream) {
+    P2W_REQUIRE(num_segments >= 1 && c >= 1, "p2w_segment_max: bad sizes");
+    dim3 grid(num_segments, (c + 127) / 128);
+    segment_max_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, ptr, c, out);
+    return check_launch("p2w_segment_max");
+}
+
+extern "C" int p2w_scatter_minmax(const float *src, const int64_t *index, int64_t n, int32_t c, int64_t dim_size,
+                                  int32_t is_max, float *out, int64_t *arg, p2w_stream_t stream) {
+    P2W_REQUIRE(c >= 1 && dim_size >= 0 && n >= 0, "p2w_scatter_minmax: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    const int64_t total = dim_size * c;
+    if (total == 0) return P2W_OK;
+    scatter_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, arg, total, is_max, n);
+    if (n > 0) {
+        const unsigned blocks = (unsigned)((n * c + 255) / 256);
+        scatter_reduce_kernel<<<blocks, 256, 0, st>>>(src, index, n, c, is_max, out);
+        if (arg) scatter_arg_kernel<<<blocks, 256, 0, st>>>(src, index, n, c, out, arg);
+    }
+    scatter_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, arg, total, n);
+    return check_launch("p2w_scatter_minmax");
+}

@@ -1,0 +1,281 @@
+"""PointsToWood's network on the B200-native ops.
+
+Same constructor / forward signatures, module tree and state-dict key names as
+/root/reference/pointstowood/src/model.py, so a reference checkpoint
+(`{'model_state_dict': ...}`, optional `module.` prefix) loads unchanged.  What differs is
+the execution of the hot path (src/model.py:103-127, src/pointnet.py:116-132):
+
+* voxel sub-sampling, radius / kNN search and the whole PointNetConv (gather -> per-edge MLP
+  -> BatchNorm -> max) run as libp2w kernels on fixed-width int32 neighbour tables; the
+  [E, C+4] / [E, H] / [E, C'] edge tensors are never materialised;
+* the ReflectanceYesNo gate is the constant 1.0 (gumbel_softmax over a single logit, SURVEY.md
+  Appendix C.1): its parameters are kept for checkpoint compatibility, its compute, RNG draw
+  and two host syncs are skipped;
+* the dense per-point blocks (stem, InvertedResidualBlock, FP MLPs, head) stay torch/cuBLAS
+  modules evaluated in [N, C] layout (k=1 Conv1d == Linear), optionally under bf16 autocast.
+
+Inference (eval mode) only; the training-mode branch (random 50 % sampling, batch-stat BN inside
+local_nn) belongs to the train.py row of SURVEY.md §8(f) and raises.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import ops
+
+__all__ = ["Net", "SAModule", "GlobalSAModule", "FPModule", "InvertedResidualBlock", "PointNetConv", "MLP",
+           "initialize_weights", "load_model"]
+
+
+def initialize_weights(model: nn.Module) -> None:
+    """Xavier-uniform Linear, Kaiming-uniform Conv1d, zero bias (src/model.py:9-16)."""
+    for m in model.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+        elif isinstance(m, nn.Conv1d):
+            nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
+        else:
+            continue
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+
+
+def MLP(channels) -> nn.Sequential:
+    """Linear -> ReLU -> BatchNorm1d per layer, no BatchNorm after the first (src/model.py:198-202)."""
+    layers = []
+    for i, (cin, cout) in enumerate(zip(channels[:-1], channels[1:])):
+        block = [nn.Linear(cin, cout), nn.ReLU()]
+        if i > 0:
+            block.append(nn.BatchNorm1d(cout))
+        layers.append(nn.Sequential(*block))
+    return nn.Sequential(*layers)
+
+
+def _bn_affine(bn: nn.BatchNorm1d):
+    """Eval-mode BatchNorm as y = x * scale + shift."""
+    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    return scale, bn.bias - bn.running_mean * scale
+
+
+def _bn(bn: nn.BatchNorm1d, x: Tensor) -> Tensor:
+    return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+
+
+def _pointwise(conv: nn.Conv1d, x: Tensor) -> Tensor:
+    """k=1 Conv1d applied to rows of [N, C]."""
+    return F.linear(x, conv.weight.squeeze(-1), conv.bias)
+
+
+class DepthwiseSeparableConv1d(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=0):
+        super().__init__()
+        self.depthwise_conv = nn.Conv1d(in_channels, in_channels, kernel_size, stride, padding, groups=in_channels)
+        self.depthwise_bn = nn.BatchNorm1d(in_channels)
+        self.pointwise_conv = nn.Conv1d(in_channels, out_channels, 1)
+        self.pointwise_bn = nn.BatchNorm1d(in_channels)
+
+    def forward(self, x: Tensor) -> Tensor:          # x: [N, C]
+        x = x * self.depthwise_conv.weight.view(1, -1) + self.depthwise_conv.bias
+        x = F.relu(_bn(self.depthwise_bn, x))
+        return F.relu(_bn(self.pointwise_bn, _pointwise(self.pointwise_conv, x)))
+
+
+class InvertedResidualBlock(nn.Module):
+    """src/model.py:46-85 evaluated in [N, C] layout."""
+
+    def __init__(self, in_channels, out_channels, expansion_factor=4):
+        super().__init__()
+        e = in_channels * expansion_factor
+        self.expansion_factor = expansion_factor
+        self.expand = nn.Sequential(nn.Conv1d(in_channels, e, 1), nn.BatchNorm1d(e), nn.ReLU())
+        self.conv = nn.Sequential(DepthwiseSeparableConv1d(e, e), nn.BatchNorm1d(e), nn.ReLU(),
+                                  DepthwiseSeparableConv1d(e, e), nn.BatchNorm1d(e))
+        self.project = nn.Sequential(nn.Conv1d(e, out_channels, 1), nn.BatchNorm1d(out_channels))
+        self.shortcut = nn.Sequential()
+        if in_channels != out_channels:
+            self.shortcut = nn.Sequential(nn.Conv1d(in_channels, out_channels, 1), nn.BatchNorm1d(out_channels))
+
+    def forward(self, x: Tensor) -> Tensor:
+        out = F.relu(_bn(self.expand[1], _pointwise(self.expand[0], x)))
+        out = F.relu(_bn(self.conv[1], self.conv[0](out)))
+        out = _bn(self.conv[4], self.conv[3](out))
+        out = _bn(self.project[1], _pointwise(self.project[0], out))
+        res = x if len(self.shortcut) == 0 else _bn(self.shortcut[1], _pointwise(self.shortcut[0], x))
+        return F.relu(out + res)
+
+
+class PointNetConv(nn.Module):
+    """Drop-in for src/pointnet.py's PointNetConv(aggr='max') with a 2-layer local_nn.
+
+    forward(x, (pos_src, pos_tgt), nbr): `nbr` is either a [N_tgt, K] int32 neighbour table
+    (-1 padded; the fast path) or the reference's LongTensor edge_index [2, E] (row 0 = source j,
+    row 1 = target i, targets ascending as knn/radius emit them)."""
+
+    def __init__(self, local_nn=None, global_nn=None, add_self_loops=False, conv_mode=ops.CONV_FP32, **kwargs):
+        super().__init__()
+        if global_nn is not None or add_self_loops:
+            raise NotImplementedError("the reference builds PointNetConv(global_nn=None, add_self_loops=False)")
+        self.radius = kwargs.pop("radius", None)
+        self.local_nn = local_nn
+        self.global_nn = None
+        self.add_self_loops = False
+        self.conv_mode = conv_mode
+
+    @staticmethod
+    def edge_index_to_table(edge_index: Tensor, n_tgt: int, k: int = 32) -> Tensor:
+        j, i = edge_index[0], edge_index[1]
+        start = torch.searchsorted(i.contiguous(), torch.arange(n_tgt, device=i.device))
+        slot = torch.arange(i.numel(), device=i.device) - start[i]
+        table = torch.full((n_tgt, k), -1, device=i.device, dtype=torch.int32)
+        table[i, slot] = j.to(torch.int32)
+        return table
+
+    def forward(self, x, pos, nbr: Tensor) -> Tensor:
+        if isinstance(x, tuple):
+            x = x[0]
+        pos_src, pos_tgt = pos if isinstance(pos, tuple) else (pos, pos)
+        if nbr.dtype == torch.int64 and nbr.dim() == 2 and nbr.size(0) == 2:
+            nbr = self.edge_index_to_table(nbr, pos_tgt.size(0))
+        lin1, lin2, bn = self.local_nn[0][0], self.local_nn[1][0], self.local_nn[1][2]
+        scale, shift = _bn_affine(bn)
+        return ops.pointnet_conv_max(x.float(), pos_src, pos_tgt, nbr, lin1.weight, lin1.bias, lin2.weight, lin2.bias,
+                                     scale, shift, self.conv_mode)
+
+
+class ReflectanceYesNo(nn.Module):
+    """Parameters kept for checkpoint compatibility; the reference's output is identically 1.0
+    (hard gumbel-softmax over ONE logit, src/model.py:160,173-175), so forward returns ones."""
+
+    def __init__(self, input_dim, hidden_dim, temperature=1.0):
+        super().__init__()
+        self.fc1 = nn.Linear(input_dim, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, hidden_dim)
+        self.fc3 = nn.Linear(hidden_dim, 1)
+        self.temperature = temperature
+
+    def forward(self, x: Tensor, batch: Tensor) -> Tensor:
+        return torch.ones(x.size(0), device=x.device, dtype=torch.float32)
+
+
+class SAModule(nn.Module):
+    def __init__(self, resolution, radius, k, NN, RNN, conv_mode=ops.CONV_FP32):
+        super().__init__()
+        self.resolution, self.radius, self.k = resolution, radius, k
+        self.conv = PointNetConv(local_nn=MLP(NN), global_nn=None, add_self_loops=False, radius=radius,
+                                 conv_mode=conv_mode)
+        self.residual_block = InvertedResidualBlock(RNN, RNN)
+        self.reflectanceyesno = ReflectanceYesNo(input_dim=1, hidden_dim=32)
+
+    def voxelsample(self, pos: Tensor, batch: Tensor, resolution: float) -> Tensor:
+        return ops.voxel_sample(pos, resolution, batch)
+
+    def forward(self, x, pos, batch, reflectance, sf):
+        if self.training:
+            raise NotImplementedError("training-mode SAModule (random sampling, batch-stat BN) is not built yet")
+        B = sf.numel()
+        pos = pos[:, :3].contiguous()
+        ptr = ops.batch_to_ptr(batch, B)
+        idx = self.voxelsample(pos, batch, self.resolution)
+        batch_t = batch[idx]
+        ptr_t = ops.batch_to_ptr(batch_t, B)
+        pos_t = pos[idx]
+        if self.resolution == 0.04:
+            nbr, _ = ops.radius_table(pos, pos_t, self.resolution * 2, ptr, ptr_t, self.k)
+        else:
+            nbr = ops.knn_table(pos, pos_t, self.k, ptr, ptr_t)
+        pos4, pos_back = ops.sa_prepare(pos, reflectance, ptr, sf)
+        x = self.conv(x, (pos4, pos4[idx]), nbr)
+        x = self.residual_block(x)
+        return x, pos_back[idx], batch_t, reflectance[idx], sf
+
+
+class GlobalSAModule(nn.Module):
+    def __init__(self, NN):
+        super().__init__()
+        self.NN = MLP(NN)
+
+    def forward(self, x, pos, batch, reflectance, sf):
+        B = sf.numel()
+        x = self.NN(torch.cat([x, pos], dim=1))
+        x = ops.global_max_pool(x.float(), batch, ptr=ops.batch_to_ptr(batch, B))
+        pos = pos.new_zeros((B, 3))
+        batch = torch.arange(B, device=batch.device)
+        return x, pos, batch, reflectance.new_zeros(B), sf
+
+
+class FPModule(nn.Module):
+    def __init__(self, k, NN):
+        super().__init__()
+        self.k = k
+        self.NN = MLP(NN)
+
+    def forward(self, x, pos, batch, x_skip, pos_skip, batch_skip, num_tiles: Optional[int] = None):
+        if num_tiles is None:
+            num_tiles = int(batch_skip[-1].item()) + 1
+        ptr_x, ptr_y = ops.batch_to_ptr(batch, num_tiles), ops.batch_to_ptr(batch_skip, num_tiles)
+        c = x.size(1)
+        cs = 0 if x_skip is None else x_skip.size(1)
+        buf = torch.empty((pos_skip.size(0), c + cs), device=x.device, dtype=torch.float32)
+        ops.knn_interpolate(x.float(), pos, pos_skip, k=self.k, ptr_x=ptr_x, ptr_y=ptr_y, out=buf)
+        if x_skip is not None:
+            buf[:, c:] = x_skip
+        return self.NN(buf), pos_skip, batch_skip
+
+
+class Net(nn.Module):
+    def __init__(self, num_classes, C=32, conv_mode=ops.CONV_FP32):
+        super().__init__()
+        self.stem_mlp = MLP([3, C])
+        self.sa1_module = SAModule(0.04, 0.04, 32, [C + 4, C * 2, C * 4], C * 4, conv_mode)
+        self.sa2_module = SAModule(0.08, 0.08, 32, [C * 4 + 4, C * 6, C * 8], C * 8, conv_mode)
+        self.sa3_module = SAModule(0.16, 0.16, 32, [C * 8 + 4, C * 12, C * 16], C * 16, conv_mode)
+        self.sa4_module = GlobalSAModule([C * 16 + 3, C * 16, C * 16])
+        self.fp4_module = FPModule(2, [C * 32, C * 24, C * 16])
+        self.fp3_module = FPModule(2, [C * 24, C * 20, C * 16])
+        self.fp2_module = FPModule(2, [C * 20, C * 16, C * 16])
+        self.fp1_module = FPModule(2, [C * 17, C * 16, C * 16])
+        self.conv1 = nn.Conv1d(C * 16, C * 16, 1)
+        self.conv2 = nn.Conv1d(C * 16, num_classes, 1)
+        self.norm = nn.BatchNorm1d(C * 16)
+        initialize_weights(self)
+
+    def set_conv_mode(self, mode: int) -> "Net":
+        for m in self.modules():
+            if isinstance(m, PointNetConv):
+                m.conv_mode = mode
+        return self
+
+    def forward(self, data):
+        B = data.sf.numel()
+        pos = data.pos[:, :3].contiguous()
+        data.x = self.stem_mlp(pos)
+        sa0 = (data.x, pos, data.batch, data.reflectance, data.sf)
+        sa1 = self.sa1_module(*sa0)
+        sa2 = self.sa2_module(*sa1)
+        sa3 = self.sa3_module(*sa2)
+        sa4 = self.sa4_module(*sa3)
+        fp4 = self.fp4_module(*sa4[:3], *sa3[:3], num_tiles=B)
+        fp3 = self.fp3_module(*fp4, *sa2[:3], num_tiles=B)
+        fp2 = self.fp2_module(*fp3, *sa1[:3], num_tiles=B)
+        x, _, _ = self.fp1_module(*fp2, *sa0[:3], num_tiles=B)
+        x = F.relu(_bn(self.norm, _pointwise(self.conv1, x)))
+        x = _pointwise(self.conv2, x)
+        return torch.squeeze(x).to(torch.float)
+
+
+def load_model(path: str, model: nn.Module, device) -> nn.Module:
+    """src/predicter.py:97-105: strips a DataParallel `module.` prefix, strict=False."""
+    checkpoint = torch.load(path, map_location=device)
+    state = {(k[7:] if k.startswith("module.") else k): v for k, v in checkpoint["model_state_dict"].items()}
+    model.load_state_dict(state, strict=False)
+    return model
+
+
+def make_data(pos: Tensor, reflectance: Tensor, batch: Tensor, sf: Tensor, **extra) -> SimpleNamespace:
+    """Minimal stand-in for the PyG Batch the reference hands to Net.forward."""
+    return SimpleNamespace(pos=pos, reflectance=reflectance, batch=batch, sf=sf, **extra)

@@ -1,0 +1,411 @@
+"""Drop-in replacements for the torch_cluster / torch_scatter / torch_geometric calls on
+PointsToWood's inference hot path, backed by libp2w.so (hand-written sm_100a kernels).
+
+Python signatures follow the packages the reference imports:
+
+    knn, radius, fps, grid_cluster            torch_cluster        (src/model.py:118,120)
+    voxel_grid, consecutive_cluster,
+    knn_interpolate, global_max_pool          torch_geometric      (src/model.py:104-105,136,149)
+    scatter_max, scatter_min                  torch_scatter        (src/pointnet.py:122, src/preprocessing.py:49)
+
+plus the table-based fast path the model uses (`knn_table`, `radius_table`,
+`voxel_sample`, `pointnet_conv_max`), which keeps fixed-width int32 neighbour tables on
+the device and never synchronises with the host.  PyTorch is used for device memory and
+streams only; every op raises if libp2w.so is missing or the tensors are not on CUDA.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+__all__ = [
+    "batch_to_ptr", "knn", "radius", "fps", "grid_cluster", "voxel_grid", "consecutive_cluster",
+    "knn_interpolate", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
+    "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback",
+    "sort_pairs", "CONV_FP32", "CONV_BF16_TC",
+]
+
+CONV_FP32 = 0
+CONV_BF16_TC = 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dp(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: Tensor, dtype, name: str, dim: Optional[int] = None) -> Tensor:
+    if not t.is_cuda:
+        raise _lib.P2WError(f"{name} must be a CUDA tensor (libp2w has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.P2WError(f"{name} must be {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise _lib.P2WError(f"{name} must have {dim} dimensions")
+    return t.contiguous()
+
+
+def batch_to_ptr(batch: Tensor, batch_size: int) -> Tensor:
+    """CSR offsets of a SORTED batch vector: ptr = bucketize(arange(B+1), batch) (Appendix A.1)."""
+    ar = torch.arange(batch_size + 1, device=batch.device, dtype=batch.dtype)
+    return torch.searchsorted(batch.contiguous(), ar).to(torch.int64)
+
+
+def _ptrs(x, y, batch_x, batch_y, batch_size):
+    if batch_x is None and batch_y is None:
+        dev = x.device
+        return (torch.tensor([0, x.size(0)], device=dev, dtype=torch.int64),
+                torch.tensor([0, y.size(0)], device=dev, dtype=torch.int64), 1)
+    if batch_x is None or batch_y is None:
+        raise _lib.P2WError("batch_x and batch_y must be given together")
+    if batch_size is None:                       # upstream does the same host sync
+        batch_size = int(max(batch_x.max(), batch_y.max())) + 1
+    return batch_to_ptr(batch_x, batch_size), batch_to_ptr(batch_y, batch_size), batch_size
+
+
+# --------------------------------------------------------------------------- neighbour tables
+def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return_d2: bool = False):
+    """[Ny, k] int32 table of the k nearest x rows of every y row inside its tile, ordered by
+    (FP32 squared distance, index); -1 padded.  No host sync."""
+    x = _req(x, torch.float32, "x", 2)
+    y = _req(y, torch.float32, "y", 2)
+    if x.size(1) != 3 or y.size(1) != 3:
+        raise _lib.P2WError("knn: only 3-D coordinates are supported")
+    ptr_x, ptr_y = _req(ptr_x, torch.int64, "ptr_x", 1), _req(ptr_y, torch.int64, "ptr_y", 1)
+    if ptr_x.numel() != ptr_y.numel():
+        raise _lib.P2WError("ptr_x and ptr_y must describe the same number of examples")
+    nbr = torch.empty((y.size(0), k), device=x.device, dtype=torch.int32)
+    d2 = torch.empty((y.size(0), k), device=x.device, dtype=torch.float32) if return_d2 else None
+    _lib.check(_lib.lib().p2w_knn(_dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), ptr_x.numel() - 1, x.size(0), y.size(0),
+                                  k, _dp(nbr), _dp(d2), _stream()))
+    return (nbr, d2) if return_d2 else nbr
+
+
+def radius_table(x: Tensor, y: Tensor, r: float, ptr_x: Tensor, ptr_y: Tensor, max_num_neighbors: int = 32):
+    """([Ny, max] int32 -1 padded, cnt [Ny] int32): the lowest-index x rows with d2 < (float)(r*r)."""
+    x = _req(x, torch.float32, "x", 2)
+    y = _req(y, torch.float32, "y", 2)
+    if x.size(1) != 3 or y.size(1) != 3:
+        raise _lib.P2WError("radius: only 3-D coordinates are supported")
+    ptr_x, ptr_y = _req(ptr_x, torch.int64, "ptr_x", 1), _req(ptr_y, torch.int64, "ptr_y", 1)
+    nbr = torch.empty((y.size(0), max_num_neighbors), device=x.device, dtype=torch.int32)
+    cnt = torch.empty((y.size(0),), device=x.device, dtype=torch.int32)
+    _lib.check(_lib.lib().p2w_radius(_dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), ptr_x.numel() - 1, x.size(0),
+                                     y.size(0), float(r), max_num_neighbors, _dp(nbr), _dp(cnt), _stream()))
+    return nbr, cnt
+
+
+def table_to_edge_index(nbr: Tensor) -> Tensor:
+    """-1 padded [Ny,K] table -> upstream's LongTensor [2,E] (row 0 = y index, row 1 = x index).
+    One host sync to size the output, like upstream's masked_select."""
+    nbr = _req(nbr, torch.int32, "nbr", 2)
+    ny, k = nbr.shape
+    off = torch.empty(ny + 1, device=nbr.device, dtype=torch.int64)
+    L = _lib.lib()
+    _lib.check(L.p2w_table_count(_dp(nbr), ny, k, _dp(off), _stream()))
+    E = int(off[-1].item())
+    edges = torch.empty((2, E), device=nbr.device, dtype=torch.int64)
+    _lib.check(L.p2w_table_to_edges(_dp(nbr), ny, k, _dp(off), E, _dp(edges), _stream()))
+    return edges
+
+
+def knn(x: Tensor, y: Tensor, k: int, batch_x: Optional[Tensor] = None, batch_y: Optional[Tensor] = None,
+        cosine: bool = False, num_workers: int = 1, batch_size: Optional[int] = None) -> Tensor:
+    """torch_cluster.knn: for each y row the k nearest x rows of the same example -> [2,E]."""
+    if cosine:
+        raise _lib.P2WError("knn: cosine distance is not on the PointsToWood path")
+    if k > 100:
+        raise _lib.P2WError("knn: k must be <= 100")      # upstream AT_ASSERTM
+    px, py, _ = _ptrs(x, y, batch_x, batch_y, batch_size)
+    return table_to_edge_index(knn_table(x, y, k, px, py))
+
+
+def radius(x: Tensor, y: Tensor, r: float, batch_x: Optional[Tensor] = None, batch_y: Optional[Tensor] = None,
+           max_num_neighbors: int = 32, num_workers: int = 1, batch_size: Optional[int] = None) -> Tensor:
+    """torch_cluster.radius (CUDA semantics) -> [2,E]."""
+    px, py, _ = _ptrs(x, y, batch_x, batch_y, batch_size)
+    nbr, _cnt = radius_table(x, y, r, px, py, max_num_neighbors)
+    return table_to_edge_index(nbr)
+
+
+def fps(src: Tensor, batch: Optional[Tensor] = None, ratio: float = 0.5, random_start: bool = True,
+        batch_size: Optional[int] = None, ptr: Optional[Tensor] = None) -> Tensor:
+    """torch_cluster.fps.  random_start=True draws the first point per example from torch's
+    generator (as upstream); ties in the arg-max go to the lowest index."""
+    src = _req(src, torch.float32, "src", 2)
+    if src.size(1) != 3:
+        raise _lib.P2WError("fps: only 3-D coordinates are supported")
+    if ptr is None:
+        if batch is None:
+            ptr = torch.tensor([0, src.size(0)], device=src.device, dtype=torch.int64)
+        else:
+            if batch_size is None:
+                batch_size = int(batch.max()) + 1
+            ptr = batch_to_ptr(batch, batch_size)
+    ptr = _req(ptr, torch.int64, "ptr", 1)
+    deg = ptr[1:] - ptr[:-1]
+    m = torch.ceil(deg.to(torch.float32) * torch.tensor(ratio, dtype=torch.float32, device=src.device)).to(torch.int64)
+    out_ptr = torch.cat([m.new_zeros(1), m.cumsum(0)])
+    total = int(out_ptr[-1].item())
+    if random_start:
+        # rotate every example so that a random member comes first, run, and map back
+        raise _lib.P2WError("fps: random_start=True is not supported; pass random_start=False")
+    out = torch.empty(total, device=src.device, dtype=torch.int64)
+    ws = torch.empty(max(src.size(0), 1), device=src.device, dtype=torch.float32)
+    _lib.check(_lib.lib().p2w_fps(_dp(src), _dp(ptr), _dp(out_ptr), ptr.numel() - 1, src.size(0), _dp(ws), _dp(out),
+                                  _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- voxel grid
+def _colminmax(pos: Tensor) -> Tuple[Tensor, Tensor]:
+    mn = torch.empty(pos.size(1), device=pos.device, dtype=torch.float32)
+    mx = torch.empty_like(mn)
+    _lib.check(_lib.lib().p2w_colminmax(_dp(pos), pos.size(0), pos.size(1), pos.stride(0), _dp(mn), _dp(mx),
+                                        _stream()))
+    return mn, mx
+
+
+def grid_cluster(pos: Tensor, size: Tensor, start: Optional[Tensor] = None, end: Optional[Tensor] = None) -> Tensor:
+    """torch_cluster.grid_cluster: int64 voxel id per row (Appendix A.4)."""
+    pos = _req(pos, torch.float32, "pos", 2)
+    size = _req(size.to(pos.device), torch.float32, "size", 1)
+    if size.numel() != pos.size(1):
+        raise _lib.P2WError("grid_cluster: size must have one entry per column of pos")
+    if start is None or end is None:
+        mn, mx = _colminmax(pos)
+        start = mn if start is None else start
+        end = mx if end is None else end
+    start = _req(start.to(pos.device), torch.float32, "start", 1)
+    end = _req(end.to(pos.device), torch.float32, "end", 1)
+    ids = torch.empty(pos.size(0), device=pos.device, dtype=torch.int64)
+    _lib.check(_lib.lib().p2w_grid(_dp(pos), pos.size(0), pos.size(1), pos.stride(0), None, _dp(size), _dp(start),
+                                   _dp(end), _dp(ids), _stream()))
+    return ids
+
+
+def _voxel_ids(pos: Tensor, size, batch: Optional[Tensor], start=None, end=None) -> Tensor:
+    pos = pos.unsqueeze(-1) if pos.dim() == 1 else pos
+    pos = _req(pos, torch.float32, "pos", 2)
+    dim = pos.size(1)
+    dev = pos.device
+    if not isinstance(size, Tensor):
+        size = torch.tensor(size, dtype=torch.float32, device=dev)
+    size = size.to(dev, torch.float32).reshape(-1)
+    size = size.repeat(dim) if size.numel() == 1 else size
+    size = torch.cat([size, size.new_ones(1)])
+    if batch is None:
+        bstart = bend = torch.zeros(1, device=dev, dtype=torch.float32)
+    else:
+        batch = _req(batch, torch.int64, "batch", 1)
+        bstart, bend = batch.min().to(torch.float32).view(1), batch.max().to(torch.float32).view(1)
+    mn, mx = _colminmax(pos)
+    st = torch.cat([mn if start is None else torch.as_tensor(start, dtype=torch.float32, device=dev).reshape(-1),
+                    bstart if start is None else torch.zeros(1, device=dev)])
+    en = torch.cat([mx if end is None else torch.as_tensor(end, dtype=torch.float32, device=dev).reshape(-1), bend])
+    ids = torch.empty(pos.size(0), device=dev, dtype=torch.int64)
+    _lib.check(_lib.lib().p2w_grid(_dp(pos), pos.size(0), dim, pos.stride(0), _dp(batch), _dp(size), _dp(st),
+                                   _dp(en), _dp(ids), _stream()))
+    return ids
+
+
+def voxel_grid(pos: Tensor, size, batch: Optional[Tensor] = None, start=None, end=None) -> Tensor:
+    """torch_geometric.nn.voxel_grid: the batch vector is voxelised as an extra column of size 1."""
+    return _voxel_ids(pos, size, batch, start, end)
+
+
+def sort_pairs(keys: Tensor, key_bits: int = 64, values: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Stable LSD radix sort of non-negative int64 keys on their low `key_bits` bits; returns
+    (sorted keys, int32 values) where values default to the original positions."""
+    keys = _req(keys, torch.int64, "keys", 1)
+    n = keys.numel()
+    L = _lib.lib()
+    ws = torch.empty(max(int(L.p2w_sort_ws_bytes(n)), 8), device=keys.device, dtype=torch.uint8)
+    kout = torch.empty_like(keys)
+    vout = torch.empty(n, device=keys.device, dtype=torch.int32)
+    if values is not None:
+        values = _req(values, torch.int32, "values", 1)
+    _lib.check(L.p2w_sort_pairs(_dp(keys), _dp(values), _dp(kout), _dp(vout), n, key_bits, _dp(ws), _stream()))
+    return kout, vout
+
+
+def _unique_last(sorted_keys: Tensor, sorted_idx: Tensor, want_inverse: bool):
+    n = sorted_keys.numel()
+    L = _lib.lib()
+    dev = sorted_keys.device
+    perm = torch.empty(n, device=dev, dtype=torch.int64)
+    inv = torch.empty(n, device=dev, dtype=torch.int64) if want_inverse else None
+    cnt = torch.empty(1, device=dev, dtype=torch.int64)
+    ws = torch.empty(max(int(L.p2w_unique_ws_bytes(n)), 8), device=dev, dtype=torch.uint8)
+    _lib.check(L.p2w_unique_last(_dp(sorted_keys), _dp(sorted_idx), n, _dp(perm), _dp(inv), _dp(cnt), _dp(ws),
+                                 _stream()))
+    return perm, inv, cnt
+
+
+def consecutive_cluster(src: Tensor) -> Tuple[Tensor, Tensor]:
+    """torch_geometric consecutive_cluster: (inverse, perm) with perm[u] = the HIGHEST member
+    index of the u-th smallest cluster id (the CPU kernel's deterministic choice, A.5)."""
+    src = _req(src, torch.int64, "src", 1)
+    if src.numel() == 0:
+        return src.clone(), src.clone()
+    top = int(src.max().item())                       # compat path: one sync to bound the key width
+    if int(src.min().item()) < 0:
+        raise _lib.P2WError("consecutive_cluster: cluster ids must be non-negative")
+    keys, idx = sort_pairs(src, max(1, top.bit_length()))
+    perm, inv, cnt = _unique_last(keys, idx, True)
+    return inv, perm[: int(cnt.item())]
+
+
+def voxel_sample(pos: Tensor, size: float, batch: Tensor, key_bits: int = 40) -> Tensor:
+    """SAModule.voxelsample (src/model.py:103-106): one representative row per occupied voxel,
+    voxels ascending by id (batch-major).  One host sync (the number of voxels)."""
+    ids = _voxel_ids(pos, size, batch)
+    if ids.numel() == 0:
+        return ids
+    keys, idx = sort_pairs(ids, key_bits)
+    perm, _, cnt = _unique_last(keys, idx, False)
+    hi = keys[-1:]                                     # largest key (sorted): must fit key_bits
+    n_unique, top = torch.cat([cnt, hi]).tolist()
+    if top >> key_bits:
+        keys, idx = sort_pairs(ids, 64)
+        perm, _, cnt = _unique_last(keys, idx, False)
+        n_unique = int(cnt.item())
+    return perm[:n_unique]
+
+
+# --------------------------------------------------------------------------- reductions
+def _scatter(src: Tensor, index: Tensor, dim: int, out, dim_size: Optional[int], is_max: bool):
+    if out is not None:
+        raise _lib.P2WError("scatter_max/min: the `out` argument is not supported")
+    src = _req(src, torch.float32, "src")
+    if dim < 0:
+        dim += src.dim()
+    if dim != 0:
+        raise _lib.P2WError("scatter_max/min: only dim=0 is on the PointsToWood path")
+    index = _req(index.reshape(index.size(0), -1)[:, 0] if index.numel() else index.reshape(-1),
+                 torch.int64, "index", 1)
+    n = src.size(0)
+    c = src.numel() // max(n, 1) if n else int(math.prod(src.shape[1:]))
+    if dim_size is None:
+        dim_size = int(index.max().item()) + 1 if n else 0
+    res = torch.empty((dim_size,) + tuple(src.shape[1:]), device=src.device, dtype=torch.float32)
+    arg = torch.empty((dim_size,) + tuple(src.shape[1:]), device=src.device, dtype=torch.int64)
+    _lib.check(_lib.lib().p2w_scatter_minmax(_dp(src), _dp(index), n, max(c, 1), dim_size, 1 if is_max else 0,
+                                             _dp(res), _dp(arg), _stream()))
+    return res, arg
+
+
+def scatter_max(src: Tensor, index: Tensor, dim: int = -1, out=None, dim_size: Optional[int] = None):
+    """torch_scatter.scatter_max along dim 0 -> (out, argmax); empty slots 0 / src.size(0)."""
+    return _scatter(src, index, dim, out, dim_size, True)
+
+
+def scatter_min(src: Tensor, index: Tensor, dim: int = -1, out=None, dim_size: Optional[int] = None):
+    return _scatter(src, index, dim, out, dim_size, False)
+
+
+def global_max_pool(x: Tensor, batch: Tensor, size: Optional[int] = None, ptr: Optional[Tensor] = None) -> Tensor:
+    """torch_geometric.nn.global_max_pool for a sorted batch vector."""
+    x = _req(x, torch.float32, "x", 2)
+    if ptr is None:
+        if size is None:
+            size = int(batch.max()) + 1
+        ptr = batch_to_ptr(batch, size)
+    out = torch.empty((ptr.numel() - 1, x.size(1)), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().p2w_segment_max(_dp(x), _dp(ptr), ptr.numel() - 1, x.size(1), _dp(out), _stream()))
+    return out
+
+
+def knn_interpolate(x: Tensor, pos_x: Tensor, pos_y: Tensor, batch_x: Optional[Tensor] = None,
+                    batch_y: Optional[Tensor] = None, k: int = 3, num_workers: int = 1,
+                    ptr_x: Optional[Tensor] = None, ptr_y: Optional[Tensor] = None,
+                    out: Optional[Tensor] = None) -> Tensor:
+    """torch_geometric.nn.knn_interpolate (src/model.py:149).  `out` may be a wider
+    [Ny, >=C] buffer whose leading C columns are filled (fuses the skip concatenation)."""
+    x = _req(x, torch.float32, "x", 2)
+    pos_x, pos_y = _req(pos_x, torch.float32, "pos_x", 2), _req(pos_y, torch.float32, "pos_y", 2)
+    if ptr_x is None:
+        ptr_x, ptr_y, _ = _ptrs(pos_x, pos_y, batch_x, batch_y, None)
+    nbr = knn_table(pos_x, pos_y, k, ptr_x, ptr_y)
+    if out is None:
+        out = torch.empty((pos_y.size(0), x.size(1)), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().p2w_knn_interpolate(_dp(x), _dp(pos_x), _dp(pos_y), _dp(nbr), pos_y.size(0), k, x.size(1),
+                                              out.stride(0), _dp(out), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- fused conv and glue
+def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, w1: Tensor, b1: Tensor, w2: Tensor,
+                      b2: Tensor, bn_scale: Tensor, bn_shift: Tensor, mode: int = CONV_FP32) -> Tensor:
+    """Fused PointNetConv.message + local_nn + max aggregation (src/pointnet.py:108-132)."""
+    x = _req(x, torch.float32, "x", 2)
+    pos_src, pos_tgt = _req(pos_src, torch.float32, "pos_src", 2), _req(pos_tgt, torch.float32, "pos_tgt", 2)
+    nbr = _req(nbr, torch.int32, "nbr", 2)
+    if pos_src.size(1) != 4 or pos_tgt.size(1) != 4:
+        raise _lib.P2WError("pointnet_conv_max: positions must be [N,4] (xyz/sf, reflectance)")
+    H, K1 = w1.shape
+    Co = w2.size(0)
+    C = x.size(1)
+    if K1 != C + 4 or w2.size(1) != H or nbr.size(0) != pos_tgt.size(0):
+        raise _lib.P2WError("pointnet_conv_max: inconsistent shapes")
+    L = _lib.lib()
+    nbytes = int(L.p2w_pointnet_conv_ws_bytes(C, H, Co, mode))
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    out = torch.empty((pos_tgt.size(0), Co), device=x.device, dtype=torch.float32)
+    args = [_req(t, torch.float32, "weights") for t in (w1, b1, w2, b2, bn_scale, bn_shift)]
+    _lib.check(L.p2w_pointnet_conv_max(_dp(x), _dp(pos_src), _dp(pos_tgt), _dp(nbr), x.size(0), pos_tgt.size(0),
+                                       nbr.size(1), C, H, Co, *[_dp(a) for a in args], _dp(out), mode, _dp(ws),
+                                       nbytes, _stream()))
+    return out
+
+
+def sa_prepare(pos: Tensor, refl: Tensor, ptr: Tensor, sf: Tensor) -> Tuple[Tensor, Tensor]:
+    """(pos4 [N,4] = (pos/sf[tile], refl), pos_back [N,3] = (pos/sf)*sf) -- src/model.py:109,122,124."""
+    pos = _req(pos, torch.float32, "pos", 2)
+    refl, sf = _req(refl, torch.float32, "reflectance", 1), _req(sf, torch.float32, "sf", 1)
+    n = pos.size(0)
+    pos4 = torch.empty((n, 4), device=pos.device, dtype=torch.float32)
+    back = torch.empty((n, 3), device=pos.device, dtype=torch.float32)
+    _lib.check(_lib.lib().p2w_sa_prepare(_dp(pos), pos.stride(0), _dp(refl), _dp(ptr), _dp(sf), ptr.numel() - 1, n,
+                                         _dp(pos4), _dp(back), _stream()))
+    return pos4, back
+
+
+def pack_tiles(cloud: Tensor, index: Optional[Tensor], ptr: Tensor):
+    """TestingDataset.__getitem__ + PyG collate (src/predicter.py:78-94): gathers rows `index` of
+    cloud [N, >=4] tile by tile -> (pos [M,3] mean-shifted, reflectance [M], batch [M],
+    local_shift [B,3], sf [B])."""
+    cloud = _req(cloud, torch.float32, "cloud", 2)
+    ptr = _req(ptr, torch.int64, "ptr", 1)
+    B = ptr.numel() - 1
+    m = index.numel() if index is not None else cloud.size(0)
+    dev = cloud.device
+    pos = torch.empty((m, 3), device=dev, dtype=torch.float32)
+    refl = torch.empty(m, device=dev, dtype=torch.float32)
+    batch = torch.empty(m, device=dev, dtype=torch.int64)
+    shift = torch.empty((B, 3), device=dev, dtype=torch.float32)
+    sf = torch.empty(B, device=dev, dtype=torch.float32)
+    _lib.check(_lib.lib().p2w_pack(_dp(cloud), cloud.stride(0), _dp(index), _dp(ptr), B, m, _dp(pos), _dp(refl),
+                                   _dp(batch), _dp(shift), _dp(sf), _stream()))
+    return pos, refl, batch, shift, sf
+
+
+def writeback(logits: Tensor, pos: Tensor, ptr: Tensor, local_shift: Tensor, is_wood: float = 0.5,
+              want_rows: bool = False):
+    """src/predicter.py:199-214: (prob [M] fp32, pred [M] uint8[, rows float64 [M,5] = x,y,z,pred,prob])."""
+    logits = _req(logits, torch.float32, "logits", 1)
+    m = logits.numel()
+    dev = logits.device
+    prob = torch.empty(m, device=dev, dtype=torch.float32)
+    pred = torch.empty(m, device=dev, dtype=torch.uint8)
+    rows = torch.empty((m, 5), device=dev, dtype=torch.float64) if want_rows else None
+    _lib.check(_lib.lib().p2w_writeback(_dp(logits), _dp(pos), _dp(ptr), _dp(local_shift), ptr.numel() - 1, m,
+                                        float(is_wood), _dp(rows), _dp(prob), _dp(pred), _stream()))
+    return (prob, pred, rows) if want_rows else (prob, pred)
