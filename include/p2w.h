@@ -95,11 +95,13 @@ int p2w_sort_pairs(const uint64_t *keys_in, const int32_t *vals_in, uint64_t *ke
 size_t p2w_unique_ws_bytes(int64_t n);
 /* torch_geometric consecutive_cluster (src/model.py:105) on SORTED keys with their
  * original indices (ascending inside equal keys, as the stable sort leaves them):
- * perm[u] = highest original index of the u-th distinct key, inverse[orig] = u (may be NULL),
- * *num_unique (device int64) = number of distinct keys.  ws: p2w_unique_ws_bytes(n). */
+ * perm[u] = highest original index of the u-th distinct key, inverse[orig] = u,
+ * seg_start[u] = first sorted position of the u-th key and seg_start[num_unique] = n (the CSR
+ * of src/preprocessing.py:59-63's per-voxel member lists); perm / inverse / seg_start may be
+ * NULL.  *num_unique (device int64) = number of distinct keys.  ws: p2w_unique_ws_bytes(n). */
 int p2w_unique_last(const uint64_t *sorted_keys, const int32_t *sorted_idx, int64_t n,
-                    int64_t *perm, int64_t *inverse, int64_t *num_unique, void *ws,
-                    p2w_stream_t stream);
+                    int64_t *perm, int64_t *inverse, int64_t *seg_start, int64_t *num_unique,
+                    void *ws, p2w_stream_t stream);
 
 /* ---- K5: fused PointNetConv: gather -> per-edge MLP -> max --------------------------
  * Replaces MessagePassing.propagate(aggr='max') around PointNetConv.message
@@ -159,6 +161,31 @@ int p2w_pack(const float *cloud, int32_t ld, const int64_t *index, const int64_t
 int p2w_writeback(const float *logits, const float *pos, const int64_t *ptr,
                   const float *local_shift, int32_t num_tiles, int64_t m, float is_wood,
                   double *out64, float *prob, uint8_t *pred, p2w_stream_t stream);
+
+/* ---- K6: tiling front end (src/preprocessing.py:18-64, 116-120) ---------------------------
+ * p2w_ground_normalize (gpu_ground, :37-53): 5 m XY cells with edges x_min + 5 i (bucketize:
+ * cell = number of edges strictly below the coordinate), per-cell min z, n_z = z - min.
+ * cell_min is a caller workspace of nbx*nby floats; mnmx = {x_min, y_min} on the device.
+ * p2w_reflectance_keys + p2w_sort_pairs(32 bits) + p2w_reflectance_normalize
+ * (quantile_normalize_reflectance, :18-30): rank (stable) -> q = (rank+1)/(N+1) clamped to
+ * [1e-7, 1-1e-7] -> erfinv(2q-1)*sqrt(2); then out = 2 (v-min)/(max-min) - 1.
+ * p2w_assemble5: feat [n,5] = (x, y, z, reflectance_scaled, n_z), the array the reference
+ * voxelises with all five columns (:52,58).
+ * p2w_priority_keys (stand-in for torch.multinomial without replacement, :116-118, which is
+ * random in the reference): priority = w_i / u_i with w = refl - min(refl) + 1e-8 and u a
+ * counter-based hash of (seed, point index) in (0,1]; key = (tile_rank << 32) | ~bits(priority),
+ * so an ascending sort lists every oversized tile's members by descending priority. */
+int p2w_ground_normalize(const float *cloud, int32_t ld, int64_t n, const float *mn_xy,
+                         float cell, int32_t nbx, int32_t nby, float *cell_min, float *n_z,
+                         p2w_stream_t stream);
+int p2w_reflectance_keys(const float *cloud, int32_t ld, int32_t col, int64_t n, uint64_t *keys,
+                         p2w_stream_t stream);
+int p2w_reflectance_normalize(const int32_t *sorted_idx, int64_t n, float *v, float *mnmx_ws,
+                              float *out, p2w_stream_t stream);
+int p2w_assemble5(const float *cloud, int32_t ld, const float *refl, const float *n_z, int64_t n,
+                  float *feat, p2w_stream_t stream);
+int p2w_priority_keys(const float *feat, const int32_t *members, const int32_t *member_tile,
+                      int64_t m, float refl_min, uint32_t seed, uint64_t *keys, p2w_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,145 @@
+"""CPU restatement of PointsToWood's host pipeline around the network: tiling
+(/root/reference/pointstowood/src/preprocessing.py:18-64, 79-127), batch packing
+(src/predicter.py:78-94 + PyG collate) and write-back (src/predicter.py:199-214).
+
+TEST INFRASTRUCTURE (checker + timed CPU arm), numpy / torch-CPU only.  PARITY UNPINNED: the
+reference has no tests for this path and its preprocessing cannot run here at all (it hard-codes
+device='cuda', :43-44,83,86, and imports torch_geometric / torch_scatter); what is restated is
+the arithmetic of the cited lines.  Where the reference is random or order-unstable the same
+deterministic choices as the CUDA path are pinned:
+  * stable sort for reflectance ranks (C.9);
+  * > max_pts tiles: priority sampling w_i/u_i with a counter-based hash instead of
+    torch.multinomial (C.5), rows by descending priority;
+  * consecutive batches of `batch_size` tiles in tile order, nothing dropped (C.4);
+  * local_shift = mean accumulated in float64 (the reference's fp32 torch.mean depends on its
+    vectorised summation order).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import oracle as O
+from . import ref_model
+
+SUBSAMPLE_SEED = 141190
+
+
+def ground_normalize(xyz: np.ndarray) -> np.ndarray:
+    """gpu_ground (:37-53): 5 m XY cells from bucketize on edges min + 5 i; n_z = z - cell min."""
+    x, y, z = (np.ascontiguousarray(xyz[:, d], dtype=np.float32) for d in range(3))
+    cells = []
+    for v in (x, y):
+        lo, hi = v.min(), np.float32(v.max() + np.float32(5.0))
+        nb = max(1, int(math.ceil((float(hi) - float(lo)) / 5.0)))
+        edges = (lo + np.float32(5.0) * np.arange(nb, dtype=np.float32)).astype(np.float32)
+        cells.append((np.searchsorted(edges, v, side="left"), nb))
+    cid = cells[0][0].astype(np.int64) * (cells[1][1] + 1) + cells[1][0]
+    mins = np.full(int(cid.max()) + 1, np.inf, dtype=np.float32)
+    np.minimum.at(mins, cid, z)
+    return (z - mins[cid]).astype(np.float32)
+
+
+def quantile_normalize_reflectance(refl: np.ndarray) -> np.ndarray:
+    """:18-30 with a stable sort."""
+    refl = np.ascontiguousarray(refl, dtype=np.float32)
+    n = len(refl)
+    order = np.argsort(refl, kind="stable")
+    ranks = np.empty(n, dtype=np.int64)
+    ranks[order] = np.arange(n)
+    q = (ranks.astype(np.float32) + np.float32(1.0)) / np.float32(n + 1)
+    q = np.clip(q, np.float32(1e-7), np.float32(1.0) - np.float32(1e-7))
+    v = (torch.erfinv(torch.from_numpy(np.float32(2.0) * q - np.float32(1.0))) * torch.sqrt(torch.tensor(2.0))).numpy()
+    mn, mx = v.min(), v.max()
+    return (np.float32(2.0) * (v - mn) / (mx - mn) - np.float32(1.0)).astype(np.float32)
+
+
+def _mix32(h: np.ndarray) -> np.ndarray:
+    h = h.astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    h = (h * np.uint32(0x85EBCA6B)).astype(np.uint32)
+    h ^= h >> np.uint32(13)
+    h = (h * np.uint32(0xC2B2AE35)).astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    return h
+
+
+def priorities(refl_scaled: np.ndarray, idx: np.ndarray, refl_min: np.float32, seed: int) -> np.ndarray:
+    """w_i / u_i, w = refl - min + 1e-8 (:99,104), u = hash(seed, i) in (0, 1]."""
+    with np.errstate(over="ignore"):
+        w = (refl_scaled[idx] - refl_min + np.float32(1e-8)).astype(np.float32)
+        h = _mix32((idx.astype(np.uint32) * np.uint32(0x9E3779B9) + np.uint32(seed & 0xFFFFFFFF)).astype(np.uint32))
+    u = ((h >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(5.9604644775390625e-08)
+    return (w / u).astype(np.float32)
+
+
+def tile(feat5: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=16384, seed=SUBSAMPLE_SEED):
+    """grid() + the > max_pts branch of write_voxels (:55-64, 116-120) -> list of index arrays."""
+    tiles, grids = [], []
+    refl_min = feat5[:, 3].min()
+    for size in gridsize:
+        ids = O.grid(feat5, np.full(5, size, np.float32))
+        order = np.argsort(ids, kind="stable")
+        sid = ids[order]
+        starts = np.concatenate([[0], np.nonzero(sid[1:] != sid[:-1])[0] + 1, [len(sid)]])
+        for a, b in zip(starts[:-1], starts[1:]):
+            if b - a < min_pts:
+                continue
+            idx = order[a:b]
+            if len(idx) > max_pts:
+                pr = priorities(feat5[:, 3], idx, refl_min, seed)
+                sel = np.lexsort((idx, -pr.astype(np.float64)))[:max_pts]     # priority desc, index asc
+                idx = idx[sel]
+            tiles.append(idx.astype(np.int64))
+            grids.append(size)
+    return tiles, np.asarray(grids, np.float32)
+
+
+def preprocess(cloud: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=16384, seed=SUBSAMPLE_SEED):
+    """write_voxels (:79-127): returns (feat5 [N,5], tiles)."""
+    cloud = np.ascontiguousarray(cloud, dtype=np.float32)
+    n_z = ground_normalize(cloud[:, :3])
+    refl = cloud[:, 3]
+    if not np.all(refl == 0):
+        refl = quantile_normalize_reflectance(refl)
+    feat5 = np.concatenate([cloud[:, :3], refl[:, None], n_z[:, None]], 1).astype(np.float32)
+    tiles, grids = tile(feat5, gridsize, min_pts, max_pts, seed)
+    return feat5, tiles, grids
+
+
+def pack(feat5: np.ndarray, tiles):
+    """TestingDataset.__getitem__ + collate (src/predicter.py:78-94)."""
+    pos, refl, batch, shift, sf = [], [], [], [], []
+    for b, idx in enumerate(tiles):
+        rows = feat5[idx]
+        mean = (rows[:, :3].astype(np.float64).sum(0) / len(rows)).astype(np.float32)
+        p = (rows[:, :3] - mean).astype(np.float32)
+        sq = p * p
+        sf.append(np.sqrt((sq[:, 0] + sq[:, 1]) + sq[:, 2]).max())
+        pos.append(p)
+        refl.append(rows[:, 3])
+        batch.append(np.full(len(rows), b, np.int64))
+        shift.append(mean)
+    return (np.concatenate(pos), np.concatenate(refl), np.concatenate(batch), np.stack(shift),
+            np.asarray(sf, np.float32))
+
+
+def classify(sd, feat5, tiles, batch_size=8, is_wood=0.5, max_batches=None):
+    """The inference loop (src/predicter.py:193-217) -> classified rows float64 [M,5]."""
+    out = []
+    nb = 0
+    for t0 in range(0, len(tiles), batch_size):
+        if max_batches is not None and nb >= max_batches:
+            break
+        group = tiles[t0:t0 + batch_size]
+        pos, refl, batch, shift, sf = pack(feat5, group)
+        logits = ref_model.net_forward(sd, torch.from_numpy(pos), torch.from_numpy(refl), torch.from_numpy(batch),
+                                       torch.from_numpy(sf))
+        prob = torch.sigmoid(torch.nan_to_num(logits)).numpy()
+        pred = (prob >= is_wood).astype(np.float64)
+        xyz = pos.astype(np.float64) + shift.astype(np.float64)[batch]
+        out.append(np.concatenate([xyz, pred[:, None], prob.astype(np.float64)[:, None]], 1))
+        nb += 1
+    return np.concatenate(out) if out else np.zeros((0, 5))

@@ -28,7 +28,7 @@ SIGNATURES = {
     "p2w_sort_ws_bytes": (c_size_t, [c_int64]),
     "p2w_sort_pairs": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, _P]),
     "p2w_unique_ws_bytes": (c_size_t, [c_int64]),
-    "p2w_unique_last": (c_int32, [_P, _P, c_int64, _P, _P, _P, _P, _P]),
+    "p2w_unique_last": (c_int32, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "p2w_pointnet_conv_max": (c_int32, [_P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                         _P, _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
     "p2w_pointnet_conv_ws_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
@@ -37,6 +37,11 @@ SIGNATURES = {
     "p2w_scatter_minmax": (c_int32, [_P, _P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
     "p2w_sa_prepare": (c_int32, [_P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P, _P]),
     "p2w_pack": (c_int32, [_P, c_int32, _P, _P, c_int32, c_int64, _P, _P, _P, _P, _P, _P]),
+    "p2w_ground_normalize": (c_int32, [_P, c_int32, c_int64, _P, c_float, c_int32, c_int32, _P, _P, _P]),
+    "p2w_reflectance_keys": (c_int32, [_P, c_int32, c_int32, c_int64, _P, _P]),
+    "p2w_reflectance_normalize": (c_int32, [_P, c_int64, _P, _P, _P, _P]),
+    "p2w_assemble5": (c_int32, [_P, c_int32, _P, _P, c_int64, _P, _P]),
+    "p2w_priority_keys": (c_int32, [_P, _P, _P, c_int64, c_float, ctypes.c_uint32, _P, _P]),
     "p2w_writeback": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_float, _P, _P, _P, _P]),
 }
 

@@ -155,42 +155,57 @@ __global__ void __launch_bounds__(NW * 32)
                 for (int t = threadIdx.x; t < npts * 3; t += NW * 32) sm.buf[bsel][t] = x[first * 3 + t];
                 __syncthreads();
             }
-            const int64_t lo = (x0 > first) ? x0 : first;
-            const int64_t hi = (x1 < first + CH) ? x1 : first + CH;
+            // candidates of this chunk, as 32-bit offsets from the chunk start
+            const int lo = static_cast<int>(((x0 > first) ? x0 : first) - first);
+            const int hi = static_cast<int>(((x1 < first + CH) ? x1 : first + CH) - first);
+            const int ibase = static_cast<int>(first);
             bool any_mine = false;
+            float act_thr[QW];   // queries of other tiles (or already full) can never be hit
 #pragma unroll
-            for (int u = 0; u < QW; u++) any_mine |= mine[u];
+            for (int u = 0; u < QW; u++) {
+                any_mine |= mine[u];
+                act_thr[u] = mine[u] ? (RADIUS ? r2 : thr_d[u]) : -1.f;
+            }
             if (any_mine) {
-                for (int64_t base = lo; base < hi; base += 32) {
-                    const int64_t j = base + lane;
-                    const bool valid = j < hi;
-                    const int o = static_cast<int>((valid ? j : lo) - first) * 3;
+                for (int base = lo; base < hi; base += 32) {
+                    const int jl = base + lane;
+                    const bool valid = jl < hi;
+                    const int o = (valid ? jl : lo) * 3;
                     const float cx = buf[o], cy = buf[o + 1], cz = buf[o + 2];
-                    const int ji = static_cast<int>(j);
+                    float d[QW];
+                    bool anyhit = false;
 #pragma unroll
                     for (int u = 0; u < QW; u++) {
-                        if (!mine[u]) continue;
                         const float dx = __fsub_rn(cx, qx[u]), dy = __fsub_rn(cy, qy[u]), dz = __fsub_rn(cz, qz[u]);
-                        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                        d[u] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                        // superset of the exact test: radius d < r2, kNN (d, j) < (thr_d, thr_i)
+                        anyhit |= RADIUS ? (d[u] < act_thr[u]) : (d[u] <= act_thr[u]);
+                    }
+                    if (!__any_sync(FULL, anyhit && valid)) continue;
+                    const int ji = ibase + jl;
+#pragma unroll
+                    for (int u = 0; u < QW; u++) {
                         if (RADIUS) {
-                            const bool hit = valid && d < r2;
+                            const bool hit = valid && d[u] < act_thr[u];
                             const unsigned m = __ballot_sync(FULL, hit);
                             if (m) {
                                 const int slot = cnt[u] + __popc(m & ((1u << lane) - 1u));
                                 if (hit && slot < k) nbr[q[u] * k + slot] = ji;
                                 cnt[u] += __popc(m);
-                                if (cnt[u] >= k) { cnt[u] = k; mine[u] = false; }
+                                if (cnt[u] >= k) { cnt[u] = k; mine[u] = false; act_thr[u] = -1.f; }
                             }
                         } else {
-                            unsigned m = __ballot_sync(FULL, valid && key_less(d, ji, thr_d[u], thr_i[u]));
+                            unsigned m = __ballot_sync(FULL, valid && d[u] <= act_thr[u] &&
+                                                                 key_less(d[u], ji, thr_d[u], thr_i[u]));
                             while (m) {
                                 const int l = __ffs(m) - 1;
                                 m &= m - 1;
-                                const float cd = __shfl_sync(FULL, d, l);
+                                const float cd = __shfl_sync(FULL, d[u], l);
                                 const int ci = __shfl_sync(FULL, ji, l);
                                 if (key_less(cd, ci, thr_d[u], thr_i[u])) {
                                     top[u].insert(cd, ci, lane);
                                     top[u].kth(k, thr_d[u], thr_i[u]);
+                                    act_thr[u] = thr_d[u];
                                 }
                             }
                         }

@@ -263,13 +263,18 @@ __global__ void __launch_bounds__(256) head_flag_kernel(const uint64_t *__restri
 __global__ void __launch_bounds__(256) unique_last_kernel(const uint64_t *__restrict__ keys,
                                                           const int32_t *__restrict__ idx, int64_t n,
                                                           const int64_t *__restrict__ excl,
-                                                          int64_t *__restrict__ perm, int64_t *__restrict__ inverse) {
+                                                          int64_t *__restrict__ perm, int64_t *__restrict__ inverse,
+                                                          int64_t *__restrict__ seg_start) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const bool head = (i == 0 || keys[i] != keys[i - 1]);
     const int64_t u = excl[i] + (head ? 1 : 0) - 1;
     if (inverse) inverse[idx[i]] = u;
-    if (i == n - 1 || keys[i] != keys[i + 1]) perm[u] = idx[i];
+    if (seg_start && head) seg_start[u] = i;
+    if (i == n - 1 || keys[i] != keys[i + 1]) {
+        if (perm) perm[u] = idx[i];
+        if (seg_start && i == n - 1) seg_start[u + 1] = n;
+    }
 }
 
 }  // namespace
@@ -344,7 +349,8 @@ extern "C" int p2w_sort_pairs(const uint64_t *keys_in, const int32_t *vals_in, u
 extern "C" size_t p2w_unique_ws_bytes(int64_t n) { return static_cast<size_t>(8 * (n + 1) + 8 * (scan_blocks(n) + 2)); }
 
 extern "C" int p2w_unique_last(const uint64_t *sorted_keys, const int32_t *sorted_idx, int64_t n, int64_t *perm,
-                               int64_t *inverse, int64_t *num_unique, void *ws, p2w_stream_t stream) {
+                               int64_t *inverse, int64_t *seg_start, int64_t *num_unique, void *ws,
+                               p2w_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     if (n == 0) {
         cudaMemsetAsync(num_unique, 0, 8, st);
@@ -356,6 +362,6 @@ extern "C" int p2w_unique_last(const uint64_t *sorted_keys, const int32_t *sorte
     head_flag_kernel<<<blocks, 256, 0, st>>>(sorted_keys, n, flag);
     int rc = scan_exclusive(flag, flag, n, bsum, num_unique, st);
     if (rc) return rc;
-    unique_last_kernel<<<blocks, 256, 0, st>>>(sorted_keys, sorted_idx, n, flag, perm, inverse);
+    unique_last_kernel<<<blocks, 256, 0, st>>>(sorted_keys, sorted_idx, n, flag, perm, inverse, seg_start);
     return check_launch("p2w_unique_last");
 }

@@ -236,16 +236,20 @@ def sort_pairs(keys: Tensor, key_bits: int = 64, values: Optional[Tensor] = None
     return kout, vout
 
 
-def _unique_last(sorted_keys: Tensor, sorted_idx: Tensor, want_inverse: bool):
+def _unique_last(sorted_keys: Tensor, sorted_idx: Tensor, want_inverse: bool, want_perm: bool = True,
+                 want_starts: bool = False):
     n = sorted_keys.numel()
     L = _lib.lib()
     dev = sorted_keys.device
-    perm = torch.empty(n, device=dev, dtype=torch.int64)
+    perm = torch.empty(n, device=dev, dtype=torch.int64) if want_perm else None
     inv = torch.empty(n, device=dev, dtype=torch.int64) if want_inverse else None
+    starts = torch.empty(n + 1, device=dev, dtype=torch.int64) if want_starts else None
     cnt = torch.empty(1, device=dev, dtype=torch.int64)
     ws = torch.empty(max(int(L.p2w_unique_ws_bytes(n)), 8), device=dev, dtype=torch.uint8)
-    _lib.check(L.p2w_unique_last(_dp(sorted_keys), _dp(sorted_idx), n, _dp(perm), _dp(inv), _dp(cnt), _dp(ws),
-                                 _stream()))
+    _lib.check(L.p2w_unique_last(_dp(sorted_keys), _dp(sorted_idx), n, _dp(perm), _dp(inv), _dp(starts), _dp(cnt),
+                                 _dp(ws), _stream()))
+    if want_starts:
+        return perm, inv, cnt, starts
     return perm, inv, cnt
 
 

@@ -1,0 +1,98 @@
+"""Inference driver: the B200-native counterpart of src/predicter.py (SemanticSegmentation).
+
+Per batch of `batch_size` tiles (src/predicter.py:193-215): K7 packs the tiles straight from the
+on-device TileStore (mean shift, scale factor, concatenation -- :78-94 and PyG's collate), the
+network runs on the libp2w ops, K8 turns logits into (x, y, z, pred, prob) rows (:199-214).
+No `.pt` files, no per-tile torch.load, no Python loop over tiles inside a batch.
+
+Pinned batch composition (the reference's BalancedBatchSampler shuffles with an unseeded RNG and
+silently drops leftover tiles): tiles in TileStore order, consecutive
+groups of `batch_size`, the last group may be short, nothing is dropped.  A tile's sub-sampled
+representatives depend on its batch-mates (C.3), so the CPU oracle uses the same rule.
+
+Multi-GPU: batches are independent; `shard_batches` deals whole batches to
+ranks longest-first, there is no collective on the inference path, rank 0 gathers the rows.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import model as M
+from . import ops
+from .preprocessing import TileStore
+
+__all__ = ["plan_batches", "shard_batches", "classify_tiles", "SemanticSegmentation"]
+
+
+def plan_batches(num_tiles: int, batch_size: int) -> List[Tuple[int, int]]:
+    """[(first_tile, last_tile_exclusive)] -- consecutive groups of batch_size tiles."""
+    return [(t, min(t + batch_size, num_tiles)) for t in range(0, num_tiles, batch_size)]
+
+
+def shard_batches(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, world_size: int, rank: int):
+    """Greedy longest-first assignment of whole batches to ranks by point count; returns the
+    indices (into `batches`) owned by `rank`, in ascending order.  Deterministic on every rank."""
+    load = np.zeros(world_size, dtype=np.int64)
+    owner = np.empty(len(batches), dtype=np.int64)
+    pts = np.array([ptr[b] - ptr[a] for a, b in batches], dtype=np.int64)
+    for i in np.argsort(-pts, kind="stable"):
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += pts[i]
+    return [i for i in range(len(batches)) if owner[i] == rank]
+
+
+@torch.no_grad()
+def classify_tiles(net: torch.nn.Module, tiles: TileStore, batch_size: int = 8, is_wood: float = 0.5,
+                   batch_ids: Optional[Iterable[int]] = None, want_rows: bool = False, autocast_bf16: bool = False):
+    """Runs the network over the tiles.  Returns (prob float32 [M'], pred uint8 [M'], rows float64
+    [M',5] or None, row_offsets) on the device, in batch order; M' covers the selected batches."""
+    dev = tiles.feat.device
+    batches = plan_batches(tiles.num_tiles, batch_size)
+    if batch_ids is None:
+        batch_ids = range(len(batches))
+    ptr_dev = torch.as_tensor(tiles.ptr, device=dev)
+    probs, preds, rows, spans = [], [], [], []
+    for bi in batch_ids:
+        t0, t1 = batches[bi]
+        lo, hi = int(tiles.ptr[t0]), int(tiles.ptr[t1])
+        bptr = ptr_dev[t0: t1 + 1] - lo
+        pos, refl, batch, shift, sf = ops.pack_tiles(tiles.feat, tiles.members[lo:hi], bptr)
+        data = M.make_data(pos, refl, batch, sf, local_shift=shift.reshape(-1), ptr=bptr)
+        if autocast_bf16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = net(data)
+        else:
+            logits = net(data)
+        out = ops.writeback(logits.float().reshape(-1), pos, bptr, shift, is_wood, want_rows=want_rows)
+        probs.append(out[0])
+        preds.append(out[1])
+        if want_rows:
+            rows.append(out[2])
+        spans.append((lo, hi))
+    cat = (lambda xs: torch.cat(xs) if xs else torch.empty(0, device=dev))
+    return cat(probs), cat(preds), (cat(rows) if want_rows else None), spans
+
+
+def SemanticSegmentation(args):
+    """src/predicter.py:148-236 up to `classified_pc` (:217).  Expects args.tiles (from
+    preprocessing.preprocess) and the reference's flags (batch_size, is_wood, model, wdir).
+    Sets args.classified_pc (float64 [M,5] numpy: x, y, z, pred, prob) and returns args.
+    The spatial vote (collect_predictions, :107-142) is the next row of SURVEY.md §8(f)."""
+    device = torch.device("cuda")
+    net = getattr(args, "net", None)
+    if net is None:
+        net = M.Net(num_classes=1).to(device)
+        path = os.path.join(getattr(args, "wdir", "."), "model", getattr(args, "model", "model.pth"))
+        try:
+            M.load_model(path, net, device)
+        except KeyError:
+            raise Exception(f"No model loaded at {path}")
+    net.eval()
+    _, _, rows, _ = classify_tiles(net, args.tiles, args.batch_size, args.is_wood, want_rows=True)
+    args.classified_pc = rows.cpu().numpy()
+    return args

@@ -1,0 +1,185 @@
+"""Tiling front end: the B200-native counterpart of src/preprocessing.py (Voxelise / preprocess).
+
+Same class, method and argument names as the reference, but everything stays on the device:
+instead of one `voxels/voxel_k.pt` file per tile (src/preprocessing.py:125) the result is a
+`TileStore` -- the 5-column feature array plus a CSR of member indices -- which
+`predicter.SemanticSegmentation` consumes directly.
+
+Pinned choices where the reference is random or order-unstable (the CPU
+oracle oracle/ref_pipeline.py pins the same ones):
+* reflectance ranks come from a STABLE sort (C.9);
+* tiles with more than `maxpoints` members are thinned by priority sampling (w_i / u_i, the
+  weights of :99,104 and a counter-based hash for u) instead of torch.multinomial (C.5); rows
+  are ordered by descending priority;
+* tiles are listed 2 m voxels first, then 4 m voxels, each by ascending voxel id (:57-63).
+Inputs must be finite (the reference's NaN row filters, :100,123, are not reproduced).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+
+__all__ = ["TileStore", "Voxelise", "preprocess", "SUBSAMPLE_SEED"]
+
+SUBSAMPLE_SEED = 141190          # the reference's global seed (src/trainer.py:25-26)
+
+
+@dataclass
+class TileStore:
+    feat: Tensor            # [N,5] float32 device: x, y, z, reflectance (normalised), n_z
+    members: Tensor         # [M] int64 device: point ids, tile-major, reference row order inside a tile
+    ptr: np.ndarray         # [T+1] int64 host: tile t owns members[ptr[t]:ptr[t+1]]
+    grid_of_tile: np.ndarray  # [T] float32 host: the grid size that produced the tile
+
+    @property
+    def num_tiles(self) -> int:
+        return len(self.ptr) - 1
+
+    @property
+    def sizes(self) -> np.ndarray:
+        return np.diff(self.ptr)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Voxelise:
+    def __init__(self, pos, vxpath=None, minpoints=512, maxpoints=16384, gridsize=(2.0, 4.0), pointspacing=0.01,
+                 seed: int = SUBSAMPLE_SEED):
+        self.pos = pos
+        self.vxpath = vxpath
+        self.minpoints = minpoints
+        self.maxpoints = maxpoints
+        self.gridsize = list(gridsize)
+        self.pointspacing = min(self.gridsize) / 100.0
+        self.seed = seed
+        self.cloud: Optional[Tensor] = None
+        self.n_z: Optional[Tensor] = None
+        self.refl: Optional[Tensor] = None
+
+    # ---- src/preprocessing.py:37-53
+    def gpu_ground(self) -> Tensor:
+        cloud = self.cloud
+        n = cloud.size(0)
+        L = _lib.lib()
+        mn, mx = ops._colminmax(cloud[:, :2])
+        lo = mn.cpu().numpy()
+        hi = (mx + 5.0).cpu().numpy()          # x_max + grid_resolution, rounded in fp32 like the tensor op
+        nb = [max(1, int(math.ceil((float(hi[d]) - float(lo[d])) / 5.0))) for d in range(2)]
+        cell_min = torch.empty((nb[0] + 1) * (nb[1] + 1), device=cloud.device, dtype=torch.float32)
+        n_z = torch.empty(n, device=cloud.device, dtype=torch.float32)
+        _lib.check(L.p2w_ground_normalize(cloud.data_ptr(), cloud.stride(0), n, mn.data_ptr(), 5.0, nb[0], nb[1],
+                                          cell_min.data_ptr(), n_z.data_ptr(), _stream()))
+        self.n_z = n_z
+        return n_z
+
+    # ---- src/preprocessing.py:18-30
+    def quantile_normalize_reflectance(self) -> Tensor:
+        cloud = self.cloud
+        n = cloud.size(0)
+        L = _lib.lib()
+        keys = torch.empty(n, device=cloud.device, dtype=torch.int64)
+        _lib.check(L.p2w_reflectance_keys(cloud.data_ptr(), cloud.stride(0), 3, n, keys.data_ptr(), _stream()))
+        _, order = ops.sort_pairs(keys, 32)
+        v = torch.empty(n, device=cloud.device, dtype=torch.float32)
+        out = torch.empty(n, device=cloud.device, dtype=torch.float32)
+        mnmx = torch.empty(2, device=cloud.device, dtype=torch.float32)
+        _lib.check(L.p2w_reflectance_normalize(order.data_ptr(), n, v.data_ptr(), mnmx.data_ptr(), out.data_ptr(),
+                                               _stream()))
+        return out
+
+    # ---- src/preprocessing.py:55-64: per grid size, the member lists of voxels with >= minpoints
+    def grid(self, feat: Tensor):
+        out = []
+        for size in self.gridsize:
+            mn, mx = ops._colminmax(feat)
+            ext = torch.stack([mn, mx]).cpu().numpy()
+            cells = 1
+            for d in range(feat.size(1)):
+                cells *= int(np.float32(ext[1, d] - ext[0, d]) / np.float32(size)) + 1
+            bits = max(1, int(cells).bit_length())
+            sz = torch.full((feat.size(1),), float(size), device=feat.device, dtype=torch.float32)
+            ids = ops.grid_cluster(feat, sz, mn, mx)
+            keys, order = ops.sort_pairs(ids, bits)
+            _, _, cnt, starts = ops._unique_last(keys, order, False, want_perm=False, want_starts=True)
+            nvox = int(cnt.item())
+            seg = starts[: nvox + 1].cpu().numpy()
+            out.append((float(size), order, seg))
+        return out
+
+    def _thin(self, feat: Tensor, order: Tensor, seg: np.ndarray, big: np.ndarray, refl_min: float) -> List[Tensor]:
+        """Priority-sample `maxpoints` members of every oversized voxel (stand-in for :116-118)."""
+        dev = feat.device
+        L = _lib.lib()
+        pieces = [order[seg[v]: seg[v + 1]] for v in big]
+        members = torch.cat(pieces)
+        rank = torch.repeat_interleave(torch.arange(len(big), device=dev, dtype=torch.int32),
+                                       torch.as_tensor(seg[big + 1] - seg[big], device=dev))
+        keys = torch.empty(members.numel(), device=dev, dtype=torch.int64)
+        _lib.check(L.p2w_priority_keys(feat.data_ptr(), members.data_ptr(), rank.data_ptr(), members.numel(),
+                                       float(refl_min), self.seed & 0xFFFFFFFF, keys.data_ptr(), _stream()))
+        _, pos = ops.sort_pairs(keys, 32 + max(1, int(len(big)).bit_length()))
+        picked = members[pos.long()]
+        offs = np.concatenate([[0], np.cumsum(seg[big + 1] - seg[big])])
+        return [picked[offs[i]: offs[i] + self.maxpoints] for i in range(len(big))]
+
+    # ---- src/preprocessing.py:79-127
+    def write_voxels(self) -> TileStore:
+        pos = self.pos
+        if hasattr(pos, "values"):                                   # pandas DataFrame, as in the reference
+            has_nz = "n_z" in pos.columns
+            arr = np.ascontiguousarray(pos.values, dtype=np.float32)
+        else:
+            has_nz = False
+            arr = pos
+        cloud = torch.as_tensor(arr, dtype=torch.float32)
+        if not cloud.is_cuda:
+            cloud = cloud.cuda(non_blocking=True)
+        self.cloud = cloud = cloud.contiguous()
+        if cloud.dim() != 2 or cloud.size(1) < 4:
+            raise _lib.P2WError("Voxelise: the cloud needs x, y, z, reflectance columns")
+        n_z = cloud[:, -1].contiguous() if has_nz else self.gpu_ground()
+        self.n_z = n_z
+        reflectance_not_zero = bool((cloud[:, 3] != 0).any().item())
+        refl = self.quantile_normalize_reflectance() if reflectance_not_zero else None
+        n = cloud.size(0)
+        feat = torch.empty((n, 5), device=cloud.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2w_assemble5(cloud.data_ptr(), cloud.stride(0), None if refl is None else refl.data_ptr(),
+                                            n_z.data_ptr(), n, feat.data_ptr(), _stream()))
+        pieces: List[Tensor] = []
+        sizes: List[int] = []
+        grids: List[float] = []
+        refl_min = float(feat[:, 3].min().item()) if reflectance_not_zero else 0.0
+        for size, order, seg in self.grid(feat):
+            counts = np.diff(seg)
+            keep = np.nonzero(counts >= self.minpoints)[0]
+            big = keep[counts[keep] > self.maxpoints]
+            if len(big) and not reflectance_not_zero:
+                raise NotImplementedError("oversized tiles without reflectance (torch.randint path, :120)")
+            thinned = dict(zip(big.tolist(), self._thin(feat, order, seg, big, refl_min))) if len(big) else {}
+            for v in keep.tolist():
+                m = thinned[v] if v in thinned else order[seg[v]: seg[v + 1]]
+                pieces.append(m)
+                sizes.append(int(m.numel()))
+                grids.append(size)
+        members = torch.cat(pieces).to(torch.int64) if pieces else torch.empty(0, dtype=torch.int64, device=cloud.device)
+        ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        return TileStore(feat=feat, members=members, ptr=ptr, grid_of_tile=np.asarray(grids, dtype=np.float32))
+
+
+def preprocess(args) -> None:
+    """src/preprocessing.py:129-131: tiles into args.tiles (instead of files under args.vxfile),
+    n_z appended to args.pc when it is a DataFrame."""
+    vox = Voxelise(args.pc, vxpath=getattr(args, "vxfile", None), minpoints=args.min_pts, maxpoints=args.max_pts,
+                   pointspacing=getattr(args, "resolution", 0.01), gridsize=args.grid_size)
+    args.tiles = vox.write_voxels()
+    if hasattr(args.pc, "columns"):
+        args.pc["n_z"] = vox.n_z.cpu().numpy()

@@ -108,7 +108,7 @@ def test_radius_sa1_subset_queries(ops):
     ref, ref_cnt = O.radius(x, x[idx], 0.08, px, py, 32)
     nbr, cnt = ops.radius_table(_dev(x), _dev(x[idx]), 0.08, _dev(px), _dev(py), 32)
     assert np.array_equal(nbr.cpu().numpy().astype(np.int64), ref)
-    assert (ref_cnt == 32).mean() > 0.2          # truncation really happens
+    assert (ref_cnt == 32).mean() > 0.1          # truncation really happens
 
 
 @pytest.mark.parametrize("sizes,ratio", [([3000], 0.05), ([1000, 1, 17000, 250], 0.01), ([64], 1.0)])
