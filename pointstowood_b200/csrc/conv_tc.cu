@@ -1,10 +1,458 @@
-// conv_tc.cu -- K5 on tcgen05 tensor cores (placeholder until the TMEM kernel lands).
+// conv_tc.cu -- K5 on the 5th-generation tensor cores: fused gather -> per-edge MLP -> max with
+// BF16 operands, FP32 accumulation in TMEM (tcgen05.mma, cta_group::1, M=128 x N=128 x K=16).
+//
+// Replaces MessagePassing.propagate(aggr='max') around PointNetConv.message
+// (src/pointnet.py:108,116-132).  The contraction is run TRANSPOSED so that the max over a
+// target's 32 edges never crosses threads:
+//
+//     D1^T[h, e] = sum_k W1[h, k] * msg[e, k]        A = W1 (K-major), B = msg tile (K-major)
+//     D2^T[c, e] = sum_h W2[c, h] * hid[e, h]        A = W2 (K-major), B = hid tile (MN-major)
+//
+// An accumulator block is 128 channels (TMEM lanes) x 128 edges (TMEM columns = 4 targets x 32
+// edges).  An epilogue thread owns one channel: bias / ReLU / BatchNorm are per-thread constants
+// and the segment max is a 32-long register reduction.  Per CTA (persistent, one edge tile at a
+// time):
+//   warps 0-7  workers: gather x_j rows + geometry into the msg tile (bf16, canonical no-swizzle
+//              K-major layout), epilogue 1 (TMEM -> ReLU -> bf16 hid tile in shared memory),
+//              epilogue 2 (TMEM -> ReLU -> BN -> max -> out[t, c], coalesced over c);
+//   warp 8     one thread issues tcgen05.mma and tcgen05.commit;
+//   warp 9     one thread streams the pre-packed bf16 weights through a 4-stage ring of 8 KB
+//              slices with 1-D TMA bulk copies (the weights stay L2 resident).
+// Two 128-column accumulators alternate, so the MMAs of block j+1 overlap the epilogue of block j.
+// The [E, C+4], [E, H] and [E, C'] edge tensors of the reference never exist in HBM.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
+namespace p2w {
+namespace {
+
+constexpr int NT = 128;                        // edges per tile (MMA N)
+constexpr int TPT = NT / 32;                   // targets per tile
+constexpr int SLICE_K = 32;                    // k extent of one ring slice (two K=16 MMAs)
+constexpr int SLICE_BYTES = 128 * SLICE_K * 2; // 8 KB: [4 k-chunks][128 rows][8 bf16]
+constexpr int STAGES = 4;
+constexpr int WORKERS = 256;
+constexpr int THREADS = WORKERS + 64;
+constexpr int LBO1 = NT * 16 + 16;             // k-chunk stride of the msg tile, padded against bank conflicts
+constexpr int TMEM_COLS = 2 * NT;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct ConvTcParams {
+    const float *x, *pos_src, *pos_tgt;
+    const int32_t *nbr;
+    int64_t n_tgt;
+    int K, C, H, Co, K1p, NB1, NB2, num_tiles;
+    const unsigned char *wpack;
+    const float *b1p, *b2p, *scale, *shift;
+    float *out;
+};
+
+// ---- tcgen05 / TMEM wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;       // descriptor version (Blackwell); layout type 0 = no swizzle
+    return d;
+}
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, A K-major, B K- or MN-major, M=128, N=NT
+__host__ __device__ constexpr uint32_t instr_desc(bool b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) |
+           (static_cast<uint32_t>(NT >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // .x (low half) = a
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+struct SmemLayout {
+    uint32_t ring, b1, b2, sj, svalid, bars, tmem, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int K1p, int H) {
+    SmemLayout L;
+    L.ring = 0;
+    L.b1 = L.ring + STAGES * SLICE_BYTES;
+    L.b2 = L.b1 + (K1p / 8) * LBO1;
+    L.b2 = (L.b2 + 127u) & ~127u;
+    L.sj = L.b2 + (NT / 8) * (H * 16);
+    L.svalid = L.sj + NT * 4;
+    L.bars = (L.svalid + TPT * 4 + 7u) & ~7u;
+    L.tmem = L.bars + 8 * (2 * STAGES + 8);
+    L.total = L.tmem + 16;
+    return L;
+}
+
+__global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const SmemLayout L = smem_layout(p.K1p, p.H);
+    unsigned char *ring = smem + L.ring;
+    unsigned char *b1 = smem + L.b1;
+    unsigned char *b2 = smem + L.b2;
+    int *s_j = reinterpret_cast<int *>(smem + L.sj);
+    int *s_valid = reinterpret_cast<int *>(smem + L.svalid);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint64_t *ring_full = bars, *ring_empty = bars + STAGES;
+    uint64_t *acc_full = bars + 2 * STAGES, *acc_empty = acc_full + 2;
+    uint64_t *b1_full = acc_empty + 2, *b1_empty = b1_full + 1, *b2_full = b1_full + 2, *b2_empty = b1_full + 3;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L.tmem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.K1p >> 3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], WORKERS); }
+        mbar_init(b1_full, WORKERS);
+        mbar_init(b1_empty, 1);
+        mbar_init(b2_full, WORKERS);
+        mbar_init(b2_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // K padding of the msg tile (chunks after the geometry chunk) is zero for the whole kernel
+    for (int i = threadIdx.x; i < (kchunks - (p.C >> 3) - 1) * NT; i += THREADS) {
+        const int kc = (p.C >> 3) + 1 + i / NT, n = i % NT;
+        *reinterpret_cast<uint4 *>(b1 + kc * LBO1 + n * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int n1 = p.K1p / SLICE_K, n2 = p.H / SLICE_K;   // ring slices per accumulator block
+
+    if (warp == 9) {
+        // ------------------------------------------------ weight producer
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t ph = 0;
+            const int per_tile = p.NB1 * n1 + p.NB2 * n2;
+            for (int it = 0; it < my_tiles; it++) {
+                for (int s = 0; s < per_tile; s++) {
+                    mbar_wait(&ring_empty[slot], ph ^ 1);
+                    mbar_arrive_expect_tx(&ring_full[slot], SLICE_BYTES);
+                    bulk_g2s(ring + slot * SLICE_BYTES, p.wpack + static_cast<size_t>(s) * SLICE_BYTES, SLICE_BYTES,
+                             &ring_full[slot]);
+                    if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int slot = 0, acc = 0;
+            uint32_t ph = 0, tph = 0, use[2] = {0, 0};
+            const uint32_t ring_a = smem_u32(ring), b1_a = smem_u32(b1), b2_a = smem_u32(b2);
+            constexpr uint32_t ID1 = instr_desc(false), ID2 = instr_desc(true);
+            for (int it = 0; it < my_tiles; it++) {
+                for (int layer = 0; layer < 2; layer++) {
+                    mbar_wait(layer == 0 ? b1_full : b2_full, tph);
+                    tc_fence_after();
+                    const int nb = layer == 0 ? p.NB1 : p.NB2, ns = layer == 0 ? n1 : n2;
+                    for (int blk = 0; blk < nb; blk++) {
+                        mbar_wait(&acc_empty[acc], (use[acc] & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_addr = tmem_base + acc * NT;
+                        for (int s = 0; s < ns; s++) {
+                            mbar_wait(&ring_full[slot], ph);
+                            tc_fence_after();
+#pragma unroll
+                            for (int kk = 0; kk < 2; kk++) {
+                                const uint64_t ad = smem_desc(ring_a + slot * SLICE_BYTES + kk * 4096, 2048, 128);
+                                const uint64_t bd =
+                                    layer == 0 ? smem_desc(b1_a + (s * 4 + kk * 2) * LBO1, LBO1, 128)
+                                               : smem_desc(b2_a + (s * 2 + kk) * 256, 128, p.H * 16);
+                                umma(d_addr, ad, bd, layer == 0 ? ID1 : ID2, (s | kk) ? 1u : 0u);
+                            }
+                            umma_commit(&ring_empty[slot]);
+                            if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                        }
+                        umma_commit(&acc_full[acc]);
+                        use[acc]++;
+                        acc ^= 1;
+                    }
+                    umma_commit(layer == 0 ? b1_empty : b2_empty);
+                }
+                tph ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------ workers: gather + epilogues
+        int acc = 0;
+        uint32_t tph = 0, use[2] = {0, 0};
+        const int q = warp & 3, ch = warp >> 2;
+        const int CPR = p.C >> 3;
+        const int cpr_c = CPR < 32 ? CPR : 32;
+        const int rpw = 32 / cpr_c;
+        const int ck = lane % cpr_c, ri = lane / cpr_c;
+        const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int64_t t0 = static_cast<int64_t>(tile) * TPT;
+            worker_bar();                          // everyone is done with s_j / s_valid of the previous tile
+            mbar_wait(b1_empty, tph ^ 1);          // MMA1 of the previous tile no longer reads the msg tile
+            if (warp < TPT) {
+                const int64_t t = t0 + warp;
+                int j = (t < p.n_tgt && lane < p.K) ? p.nbr[t * p.K + lane] : -1;
+                const unsigned m = __ballot_sync(FULL, j >= 0);
+                const int jf = m ? __shfl_sync(FULL, j, __ffs(m) - 1) : 0;
+                if (j < 0) j = jf;                 // padded slot: duplicate a valid edge (max unchanged)
+                const int n = warp * 32 + lane;
+                s_j[n] = j;
+                if (lane == 0) s_valid[warp] = m ? 1 : 0;
+                const float4 ps = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j);
+                const float4 pt = __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + (t < p.n_tgt ? t : 0));
+                const float dx = ps.x - pt.x, dy = ps.y - pt.y, dz = ps.z - pt.z;
+                float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+                for (int o = 16; o; o >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(FULL, nrm, o));
+                const float den = nrm + 1e-8f;
+                uint4 g;
+                g.x = pack_bf16(dx / den, dy / den);
+                g.y = pack_bf16(dz / den, ps.w);
+                g.z = 0;
+                g.w = 0;
+                *reinterpret_cast<uint4 *>(b1 + CPR * LBO1 + n * 16) = g;
+            }
+            worker_bar();
+            // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
+            for (int r0 = warp * rpw; r0 < NT; r0 += 8 * rpw * 4) {
+                float4 lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int n = r0 + u * 8 * rpw + ri;
+                    if (n < NT && ck < CPR) {
+                        const float4 *src =
+                            reinterpret_cast<const float4 *>(p.x + static_cast<int64_t>(s_j[n]) * p.C + ck * 8);
+                        lo[u] = __ldg(src);
+                        hi[u] = __ldg(src + 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int n = r0 + u * 8 * rpw + ri;
+                    if (n < NT && ck < CPR) {
+                        uint4 v;
+                        v.x = pack_bf16(lo[u].x, lo[u].y);
+                        v.y = pack_bf16(lo[u].z, lo[u].w);
+                        v.z = pack_bf16(hi[u].x, hi[u].y);
+                        v.w = pack_bf16(hi[u].z, hi[u].w);
+                        *reinterpret_cast<uint4 *>(b1 + ck * LBO1 + n * 16) = v;
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(b1_full);
+
+            // ---- epilogue 1: hid[e, h] = relu(D1^T[h, e] + b1[h]) as the MN-major B operand of layer 2
+            for (int blk = 0; blk < p.NB1; blk++) {
+                mbar_wait(&acc_full[acc], use[acc] & 1);
+                tc_fence_after();
+                if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // MMA2 of the previous tile is done with hid
+                const int h = blk * 128 + 32 * q + lane;
+                const float bias = p.b1p[h];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int n0 = ch * 64 + c * 32;
+                    uint32_t r[32];
+                    tmem_ld32(lane_taddr + acc * NT + n0, r);
+                    if (h < p.H) {
+                        unsigned char *dst = b2 + (n0 >> 3) * (p.H * 16) + (h >> 3) * 128 + (h & 7) * 16;
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            uint4 v;
+                            v.x = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 0]) + bias, 0.f),
+                                            fmaxf(__uint_as_float(r[8 * g + 1]) + bias, 0.f));
+                            v.y = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 2]) + bias, 0.f),
+                                            fmaxf(__uint_as_float(r[8 * g + 3]) + bias, 0.f));
+                            v.z = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 4]) + bias, 0.f),
+                                            fmaxf(__uint_as_float(r[8 * g + 5]) + bias, 0.f));
+                            v.w = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 6]) + bias, 0.f),
+                                            fmaxf(__uint_as_float(r[8 * g + 7]) + bias, 0.f));
+                            *reinterpret_cast<uint4 *>(dst + g * (p.H * 16)) = v;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[acc]);
+                use[acc]++;
+                acc ^= 1;
+            }
+            fence_proxy_async();
+            mbar_arrive(b2_full);
+
+            // ---- epilogue 2: out[t, c] = max_e BN(relu(D2^T[c, e] + b2[c]))
+            for (int blk = 0; blk < p.NB2; blk++) {
+                mbar_wait(&acc_full[acc], use[acc] & 1);
+                tc_fence_after();
+                const int co = blk * 128 + 32 * q + lane;
+                const float bias = p.b2p[co], sc = p.scale[co], sh = p.shift[co];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int tt = ch * 2 + c;
+                    uint32_t r[32];
+                    tmem_ld32(lane_taddr + acc * NT + tt * 32, r);
+                    float m = __int_as_float(0xff800000);
+#pragma unroll
+                    for (int e = 0; e < 32; e++)
+                        m = fmaxf(m, fmaf(fmaxf(__uint_as_float(r[e]) + bias, 0.f), sc, sh));
+                    const int64_t t = t0 + tt;
+                    if (t < p.n_tgt && co < p.Co) p.out[t * p.Co + co] = s_valid[tt] ? m : 0.f;
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[acc]);
+                use[acc]++;
+                acc ^= 1;
+            }
+            tph ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// w [R, Kreal] fp32 row-major -> bf16 [NB][Kp/8][128][8] (zero padded): every ring slice contiguous
+__global__ void prepack_kernel(const float *__restrict__ w, int R, int Kreal, int NB, int Kp,
+                               __nv_bfloat16 *__restrict__ out) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = static_cast<int64_t>(NB) * Kp * 128;
+    if (idx >= total) return;
+    const int e = static_cast<int>(idx & 7);
+    const int r = static_cast<int>((idx >> 3) & 127);
+    const int kc = static_cast<int>((idx >> 10) % (Kp >> 3));
+    const int blk = static_cast<int>((idx >> 10) / (Kp >> 3));
+    const int row = blk * 128 + r, k = kc * 8 + e;
+    out[idx] = __float2bfloat16((row < R && k < Kreal) ? w[static_cast<int64_t>(row) * Kreal + k] : 0.f);
+}
+
+__global__ void padvec_kernel(const float *__restrict__ v, int n, int np, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) out[i] = i < n ? v[i] : 0.f;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct TcPlan {
+    int K1p, NB1, NB2;
+    size_t w1_bytes, w2_bytes, off_b1, off_b2, off_scale, off_shift, total;
+};
+inline TcPlan tc_plan(int c_in, int hidden, int c_out) {
+    TcPlan t;
+    t.K1p = round_up(c_in + 4, SLICE_K);
+    t.NB1 = (hidden + 127) / 128;
+    t.NB2 = (c_out + 127) / 128;
+    t.w1_bytes = static_cast<size_t>(t.NB1) * t.K1p * 128 * 2;
+    t.w2_bytes = static_cast<size_t>(t.NB2) * hidden * 128 * 2;
+    t.off_b1 = t.w1_bytes + t.w2_bytes;
+    t.off_b2 = t.off_b1 + sizeof(float) * t.NB1 * 128;
+    t.off_scale = t.off_b2 + sizeof(float) * t.NB2 * 128;
+    t.off_shift = t.off_scale + sizeof(float) * t.NB2 * 128;
+    t.total = t.off_shift + sizeof(float) * t.NB2 * 128 + 256;
+    return t;
+}
+
+}  // namespace
+}  // namespace p2w
+
 using namespace p2w;
-size_t p2w_conv_tc_ws_bytes(int32_t, int32_t, int32_t) { return 256; }
-int p2w_conv_tc_launch(const float *, const float *, const float *, const int32_t *, int64_t, int64_t, int32_t,
-                       int32_t, int32_t, int32_t, const float *, const float *, const float *, const float *,
-                       const float *, const float *, float *, void *, size_t, cudaStream_t) {
-    set_error("p2w_pointnet_conv_max: BF16 tensor-core mode not built");
-    return P2W_EINVAL;
+
+size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out) { return tc_plan(c_in, hidden, c_out).total; }
+
+int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
+                       int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out, const float *w1,
+                       const float *b1, const float *w2, const float *b2, const float *bn_scale,
+                       const float *bn_shift, float *out, void *ws, size_t ws_bytes, cudaStream_t st) {
+    (void)n_src;
+    P2W_REQUIRE(c_in % 8 == 0 && c_in >= 8, "p2w_pointnet_conv_max(bf16): c_in=%d must be a multiple of 8", c_in);
+    P2W_REQUIRE(hidden % SLICE_K == 0, "p2w_pointnet_conv_max(bf16): hidden=%d must be a multiple of 32", hidden);
+    P2W_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(pos_src) & 15u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(pos_tgt) & 15u) == 0 && (reinterpret_cast<uintptr_t>(ws) & 127u) == 0,
+                "p2w_pointnet_conv_max(bf16): x / pos / workspace must be 16-byte aligned");
+    const TcPlan t = tc_plan(c_in, hidden, c_out);
+    P2W_REQUIRE(ws_bytes >= t.total, "p2w_pointnet_conv_max(bf16): workspace too small");
+    const SmemLayout L = smem_layout(t.K1p, hidden);
+    P2W_REQUIRE(L.total <= 227 * 1024, "p2w_pointnet_conv_max(bf16): layer too wide for one CTA (%u bytes smem)",
+                L.total);
+    unsigned char *base = static_cast<unsigned char *>(ws);
+    __nv_bfloat16 *w1p = reinterpret_cast<__nv_bfloat16 *>(base);
+    __nv_bfloat16 *w2p = reinterpret_cast<__nv_bfloat16 *>(base + t.w1_bytes);
+    float *b1p = reinterpret_cast<float *>(base + t.off_b1);
+    float *b2p = reinterpret_cast<float *>(base + t.off_b2);
+    float *scp = reinterpret_cast<float *>(base + t.off_scale);
+    float *shp = reinterpret_cast<float *>(base + t.off_shift);
+    {
+        const int64_t n1 = static_cast<int64_t>(t.NB1) * t.K1p * 128, n2 = static_cast<int64_t>(t.NB2) * hidden * 128;
+        prepack_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(w1, hidden, c_in + 4, t.NB1, t.K1p, w1p);
+        prepack_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(w2, c_out, hidden, t.NB2, hidden, w2p);
+        padvec_kernel<<<(t.NB1 * 128 + 255) / 256, 256, 0, st>>>(b1, hidden, t.NB1 * 128, b1p);
+        padvec_kernel<<<(t.NB2 * 128 + 255) / 256, 256, 0, st>>>(b2, c_out, t.NB2 * 128, b2p);
+        padvec_kernel<<<(t.NB2 * 128 + 255) / 256, 256, 0, st>>>(bn_scale, c_out, t.NB2 * 128, scp);
+        padvec_kernel<<<(t.NB2 * 128 + 255) / 256, 256, 0, st>>>(bn_shift, c_out, t.NB2 * 128, shp);
+    }
+    ConvTcParams p;
+    p.x = x; p.pos_src = pos_src; p.pos_tgt = pos_tgt; p.nbr = nbr;
+    p.n_tgt = n_tgt; p.K = k; p.C = c_in; p.H = hidden; p.Co = c_out;
+    p.K1p = t.K1p; p.NB1 = t.NB1; p.NB2 = t.NB2;
+    p.num_tiles = static_cast<int>((n_tgt + TPT - 1) / TPT);
+    p.wpack = base; p.b1p = b1p; p.b2p = b2p; p.scale = scp; p.shift = shp; p.out = out;
+    static int sm_count = 0;
+    static unsigned smem_set = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = kNumSMs;
+    }
+    if (L.total > smem_set) {
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        smem_set = L.total;
+    }
+    const int per_sm = (L.total <= 110 * 1024) ? 2 : 1;     // TMEM: 2 x 256 columns fit one SM
+    int grid = sm_count * per_sm;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    conv_tc_kernel<<<grid, THREADS, L.total, st>>>(p);
+    return check_launch("p2w_pointnet_conv_max(bf16)");
 }

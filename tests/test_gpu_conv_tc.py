@@ -1,0 +1,89 @@
+"""GPU parity of the tcgen05 / TMEM fused PointNetConv (bf16 operands, fp32 accumulation) against
+the reference fixture and the FP32 kernel.  BASELINE.json north_star: 1e-2 on the wood
+probability in bf16 MLP mode."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def p2w():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import pointstowood_b200.model as model
+    from pointstowood_b200 import ops
+    return model, ops
+
+
+def _conv_inputs(g, tag):
+    sd = {k[len(tag) + 1:]: torch.from_numpy(g[k]) for k in g.files
+          if k.startswith(tag + ".") and k[len(tag) + 1].isdigit()}
+    scale = sd["1.2.weight"] / torch.sqrt(sd["1.2.running_var"] + 1e-5)
+    shift = sd["1.2.bias"] - sd["1.2.running_mean"] * scale
+    w = [sd["0.0.weight"], sd["0.0.bias"], sd["1.0.weight"], sd["1.0.bias"], scale, shift]
+    pos = torch.from_numpy(g[tag + ".pos"])
+    idx = torch.from_numpy(g[tag + ".idx"].astype(np.int64))
+    return torch.from_numpy(g[tag + ".x"]), pos, pos[idx], torch.from_numpy(g[tag + ".nbr"]), w
+
+
+@pytest.mark.parametrize("tag", ["sa1", "sa2", "sa3"])
+def test_fused_conv_bf16_tensor_core_matches_fixture(p2w, golden_dir, tag):
+    _, ops = p2w
+    g = np.load(os.path.join(golden_dir, "conv.npz"))
+    x, ps, pt, nbr, w = _conv_inputs(g, tag)
+    out = ops.pointnet_conv_max(x.cuda(), ps.cuda(), pt.cuda(), nbr.cuda(), *[t.cuda() for t in w],
+                                mode=ops.CONV_BF16_TC)
+    torch.cuda.synchronize()
+    ref = g[tag + ".out"]
+    err = np.abs(out.cpu().numpy() - ref)
+    # bf16 operands: 2^-9 relative per product, K <= 384 terms
+    assert err.max() <= 3e-2 * max(1.0, np.abs(ref).max()), f"max err {err.max()}"
+    assert err.mean() <= 4e-3 * max(1.0, np.abs(ref).mean())
+
+
+def test_fused_conv_bf16_many_tiles_and_missing_edges(p2w):
+    """More targets than CTAs (persistent loop, ring and accumulator phases wrap many times),
+    a ragged tail tile and targets without edges."""
+    _, ops = p2w
+    g = torch.Generator().manual_seed(3)
+    C, H, Co, ns, nt = 128, 192, 256, 5000, 2 * 148 * 4 * 3 + 7
+    x = torch.randn(ns, C, generator=g)
+    ps = torch.cat([torch.rand(ns, 3, generator=g), torch.randn(ns, 1, generator=g)], 1)
+    idx = torch.randint(0, ns, (nt,), generator=g)
+    nbr = torch.randint(0, ns, (nt, 32), generator=g, dtype=torch.int32)
+    cnt = torch.randint(0, 33, (nt,), generator=g)
+    nbr[torch.arange(32)[None, :] >= cnt[:, None]] = -1
+    w1 = torch.randn(H, C + 4, generator=g) * 0.1
+    w2 = torch.randn(Co, H, generator=g) * 0.1
+    b1, b2 = torch.randn(H, generator=g) * 0.1, torch.randn(Co, generator=g) * 0.1
+    sc = torch.where(torch.rand(Co, generator=g) < 0.2, -1.0, 1.0) * (torch.rand(Co, generator=g) + 0.5)
+    sh = torch.randn(Co, generator=g) * 0.1
+    args = [t.cuda() for t in (x, ps, ps[idx], nbr, w1, b1, w2, b2, sc, sh)]
+    ref = ops.pointnet_conv_max(*args, mode=ops.CONV_FP32)
+    out = ops.pointnet_conv_max(*args, mode=ops.CONV_BF16_TC)
+    torch.cuda.synchronize()
+    assert (out[cnt.cuda() == 0] == 0).all()
+    err = (out - ref).abs()
+    assert err.max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
+    assert err.mean().item() <= 4e-3 * max(1.0, ref.abs().mean().item())
+
+
+def test_net_forward_bf16_conv_within_1e2(p2w, golden_dir):
+    model_mod, ops = p2w
+    g = np.load(os.path.join(golden_dir, "net_b.npz"))
+    sd = ref_model.seeded_state_dict()
+    net = model_mod.Net(num_classes=1, conv_mode=ops.CONV_BF16_TC)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    data = model_mod.make_data(torch.from_numpy(g["pos"]).cuda(), torch.from_numpy(g["reflectance"]).cuda(),
+                               torch.from_numpy(g["batch"].astype(np.int64)).cuda(), torch.from_numpy(g["sf"]).cuda())
+    with torch.no_grad():
+        logits = net(data)
+    p, p_ref = torch.sigmoid(logits).cpu().numpy(), torch.sigmoid(torch.from_numpy(g["logits"])).numpy()
+    assert np.abs(p - p_ref).max() <= 1e-2
