@@ -1,0 +1,280 @@
+"""bench.py -- points classified / second for PointsToWood's inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+
+Workload (BASELINE.json configs[1]): the predict.py path on a synthetic 1 M-point TLS plot
+(xyz + reflectance), grid_size 2.0 4.0, min_pts 128, max_pts 16384, batch_size 8, seeded random
+weights (the checkpoint is not shipped).  One STEP = one complete pass over the plot: height /
+reflectance normalisation and 5-D voxel tiling (K6), then for every batch of 8 tiles packing (K7),
+the network (voxel sampling K4, radius / kNN K1-K2, fused PointNetConv K5, kNN interpolation,
+torch/cuBLAS dense blocks) and write-back (K8), up to the `classified_pc` rows of
+src/predicter.py:217.  The spatial vote after it is outside the region on
+both arms.
+
+`value`   : N_points * steps / device time, cloud resident in HBM when the clock starts.
+`e2e`     : the same through the host-facing API: pinned host cloud -> H2D -> pipeline -> D2H of the
+            per-point probability / label, copies inside the timed region.
+`roofline`: the dominant libp2w kernel of the step, timed live with CUDA events.
+`cpu_baseline` / `--impl reference`: the reference's host + model code cannot be imported on the
+            GPU box (torch_geometric, torch_cluster, torch_scatter absent), so the CPU arm is the
+            oracle's restatement (oracle/ref_pipeline.py + ref_model.py, kind "port") on all host
+            threads, on a bounded sample of the same plot, extrapolated to the whole plot.
+N > 1 (torchrun): every rank classifies its own 1 M-point plot (seed 1 + rank): weak scaling, no
+collective on the data path; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_POINTS = 1_000_000
+CFG = dict(grid_size=(2.0, 4.0), min_pts=128, max_pts=16384, batch_size=8, is_wood=0.5)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# --------------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_arm(n_points: int, seed: int, budget_s: float = 20.0):
+    """Times the oracle restatement of the same pipeline on the host cores: full tiling, then as
+    many batches as fit the budget, extrapolated by tile points to the whole plot."""
+    import torch
+    from oracle import oracle as O
+    from oracle import ref_model, ref_pipeline
+    from pointstowood_b200.synthetic import tls_plot
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)                       # predict.py:79-84
+    O.lib().orc_set_threads(cores)
+    cloud, _ = tls_plot(n_points, seed)
+    sd = ref_model.seeded_state_dict()
+    t0 = time.perf_counter()
+    feat5, tiles, _ = ref_pipeline.preprocess(cloud, CFG["grid_size"], CFG["min_pts"], CFG["max_pts"])
+    t_pre = time.perf_counter() - t0
+    total_pts = sum(len(t) for t in tiles)
+    # sample batches evenly across the tile list (2 m tiles are small, 4 m tiles large)
+    nb = (len(tiles) + CFG["batch_size"] - 1) // CFG["batch_size"]
+    order = np.linspace(0, nb - 1, num=min(nb, 64)).round().astype(int)
+    done_pts, t_cls, used = 0, 0.0, 0
+    for b in dict.fromkeys(order.tolist()):
+        group = tiles[b * CFG["batch_size"]:(b + 1) * CFG["batch_size"]]
+        t1 = time.perf_counter()
+        ref_pipeline.classify(sd, feat5, group, CFG["batch_size"], CFG["is_wood"])
+        t_cls += time.perf_counter() - t1
+        done_pts += sum(len(t) for t in group)
+        used += 1
+        if t_cls > budget_s:
+            break
+    est = t_pre + t_cls * total_pts / max(done_pts, 1)
+    return dict(value=n_points / est, unit="points/s", cores=cores, kind="port",
+                sample=f"full tiling ({t_pre:.2f} s) + {used} of {nb} batches ({done_pts} of {total_pts} tile points, "
+                       f"{t_cls:.1f} s), extrapolated by tile points"), est
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, est = cpu_arm(N_POINTS, 1, budget_s=12.0)
+        if i >= args.warmup:
+            vals.append(est)
+    ms = float(np.mean(vals)) * 1e3
+    value = N_POINTS / (ms / 1e3)
+    base["value"] = value
+    line = dict(impl="reference", metric="points classified/sec", value=value, unit="points/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="predict 1M-point synthetic TLS plot, grid 2/4 m, min_pts 128, max_pts 16384, "
+                                     "batch_size 8 (CPU: reference pipeline restated on oracle ops, bounded sample)"),
+                cpu_baseline=base,
+                e2e=dict(value=value, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="p2w", choices=["p2w", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from pointstowood_b200 import _lib, ops
+    from pointstowood_b200 import model as M
+    from pointstowood_b200.predicter import classify_tiles
+    from pointstowood_b200.preprocessing import Voxelise
+    from pointstowood_b200.synthetic import tls_plot
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    n_points = args.points
+    peaks = load_peaks()
+    L = _lib.lib()
+
+    cloud_np, _ = tls_plot(n_points, 1 + rank)
+    host = torch.from_numpy(cloud_np).pin_memory()
+    dev_cloud = host.cuda()
+    bf16 = args.precision == "bf16"
+    torch.manual_seed(141190)
+    net = M.Net(num_classes=1, conv_mode=ops.CONV_BF16_TC if bf16 else ops.CONV_FP32)
+    M.randomise_bn_(net, 5)
+    net = net.cuda().eval()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    def step(cloud):
+        store = Voxelise(cloud, minpoints=CFG["min_pts"], maxpoints=CFG["max_pts"], gridsize=CFG["grid_size"]).write_voxels()
+        prob, pred, _, _ = classify_tiles(net, store, CFG["batch_size"], CFG["is_wood"], autocast_bf16=bf16)
+        return store, prob, pred
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        store, prob, pred = step(dev_cloud)
+    tile_points = int(store.ptr[-1])
+    out_prob = torch.empty(tile_points, dtype=torch.float32).pin_memory()
+    out_pred = torch.empty(tile_points, dtype=torch.uint8).pin_memory()
+
+    # ---- device-resident steps, dominant kernel timed live with CUDA events
+    ops.KERNEL_TIMER.reset("p2w_pointnet_conv_max" if bf16 else "p2w_knn")
+    barrier()
+    launches0 = L.p2w_launch_count()
+    with ClockSampler(local) as clk:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step(dev_cloud)
+        ev1.record()
+        barrier()
+    launches = L.p2w_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1) / args.steps
+    kt = ops.KERNEL_TIMER.summary()
+    ops.KERNEL_TIMER.reset(None)
+
+    # ---- end to end through the host-facing API (pinned host in, host out)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cloud = host.cuda(non_blocking=True)
+        _, prob, pred = step(cloud)
+        out_prob.copy_(prob, non_blocking=True)
+        out_pred.copy_(pred, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        roof = None
+        if kt["launches"]:
+            per_launch_ms = kt["ms"] / kt["launches"]
+            if bf16:
+                achieved = kt["work"] / kt["launches"] / per_launch_ms / 1e9          # TFLOP/s
+                roof = dict(kernel="conv_tc_kernel (fused gather-MLP-max, tcgen05)", bound="tensor", achieved=achieved,
+                            peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
+                            peak_source=f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
+                            traffic=None, launches=kt["launches"], avg_launch_ms=per_launch_ms)
+            else:
+                achieved = kt["work"] / kt["launches"] / per_launch_ms / 1e6          # GB/s
+                roof = dict(kernel="sweep_kernel (kNN)", bound="hbm", achieved=achieved, peak=peaks["hbm"],
+                            unit="GB/s", frac=achieved / peaks["hbm"], peak_source=peaks["src"], traffic=None,
+                            launches=kt["launches"], avg_launch_ms=per_launch_ms)
+        line = dict(metric="points classified/sec", value=world * n_points / (ms / 1e3), unit="points/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="bf16" if bf16 else "f32", data="synthetic",
+                    config=dict(workload=f"predict {n_points}-point synthetic TLS plot per GPU, grid 2/4 m, min_pts 128, "
+                                         "max_pts 16384, batch_size 8, seeded weights",
+                                tile_points=tile_points, tiles=int(store.num_tiles),
+                                l2="inputs larger than L2 are not guaranteed: every step re-tiles and re-packs the "
+                                   "whole plot (writes > 126 MB of intermediates) between kernel repeats"),
+                    e2e=dict(value=world * n_points / (ms_e2e / 1e3), unit="points/s", h2d_bytes_per_step=int(host.numel() * 4),
+                             d2h_bytes_per_step=int(tile_points * 5)),
+                    gpu_launches=int(launches), clocks=clk.summary(), roofline=roof)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_arm(n_points, 1, budget_s=15.0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,8 @@ int p2w_version(void);
 const char *p2w_last_error(void);
 /* Number of SMs / compute capability of the current device (host query). */
 int p2w_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+/* Number of kernels libp2w has enqueued since it was loaded (all streams, this process). */
+long long p2w_launch_count(void);
 
 /* ---- K1: exact k nearest neighbours -------------------------------------------------
  * Replaces torch_cluster::knn (src/model.py:120 SA2/SA3 k=32; :149 knn_interpolate k=2).

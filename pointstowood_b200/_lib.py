@@ -18,6 +18,7 @@ SIGNATURES = {
     "p2w_version": (c_int32, []),
     "p2w_last_error": (c_char_p, []),
     "p2w_device_info": (c_int32, [_P, _P, _P]),
+    "p2w_launch_count": (ctypes.c_longlong, []),
     "p2w_knn": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_int32, _P, _P, _P]),
     "p2w_radius": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_double, c_int32, _P, _P, _P]),
     "p2w_table_count": (c_int32, [_P, c_int64, c_int32, _P, _P]),

@@ -16,6 +16,8 @@ constexpr int kNumSMs = 148;   // B200; grids for persistent kernels are sized f
 
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);
+void count_launches(int n);   // kernels enqueued by libp2w since load (bench.py's gpu_launches)
+long long launches();
 
 #define P2W_REQUIRE(cond, ...)                 \
     do {                                       \
@@ -24,6 +26,9 @@ int check_launch(const char *what);
             return P2W_EINVAL;                 \
         }                                      \
     } while (0)
+
+// every kernel launch goes through this macro so that p2w_launch_count() is exact
+#define P2W_LAUNCH(kernel, ...) p2w::count_launches(1), kernel<<<__VA_ARGS__>>>
 
 static inline cudaStream_t as_stream(p2w_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -248,8 +248,8 @@ extern "C" int p2w_pointnet_conv_max(const float *x, const float *pos_src, const
     float *w2t = w1t + static_cast<size_t>(K1) * hidden;
     // 16-byte alignment of the second panel for the float4 loads
     w2t = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(w2t) + 15) & ~uintptr_t(15));
-    transpose_kernel<<<(K1 * hidden + 255) / 256, 256, 0, st>>>(w1, hidden, K1, w1t);
-    transpose_kernel<<<(hidden * c_out + 255) / 256, 256, 0, st>>>(w2, c_out, hidden, w2t);
+    P2W_LAUNCH(transpose_kernel, (K1 * hidden + 255) / 256, 256, 0, st)(w1, hidden, K1, w1t);
+    P2W_LAUNCH(transpose_kernel, (hidden * c_out + 255) / 256, 256, 0, st)(w2, c_out, hidden, w2t);
     const size_t smem = sizeof(float) * 32 * ((K1 | 1) + (hidden | 1));
     P2W_REQUIRE(smem <= 200 * 1024, "p2w_pointnet_conv_max: layer too wide for the FP32 kernel");
     static size_t smem_set = 0;
@@ -258,8 +258,7 @@ extern "C" int p2w_pointnet_conv_max(const float *x, const float *pos_src, const
         smem_set = smem;
     }
     int64_t grid = n_tgt < 148 * 16 ? n_tgt : 148 * 16;
-    conv_simt_kernel<<<(unsigned)grid, CONV_WARPS * 32, smem, st>>>(x, pos_src, pos_tgt, nbr, n_tgt, k, c_in, hidden,
-                                                                    c_out, w1t, b1, w2t, b2, bn_scale, bn_shift, out);
+    P2W_LAUNCH(conv_simt_kernel, (unsigned)grid, CONV_WARPS * 32, smem, st)(x, pos_src, pos_tgt, nbr, n_tgt, k, c_in, hidden, c_out, w1t, b1, w2t, b2, bn_scale, bn_shift, out);
     return check_launch("p2w_pointnet_conv_max");
 }
 
@@ -269,8 +268,7 @@ extern "C" int p2w_knn_interpolate(const float *x, const float *pos_x, const flo
     P2W_REQUIRE(k >= 1 && k <= 32, "p2w_knn_interpolate: k=%d outside [1,32]", k);
     P2W_REQUIRE(c >= 1 && ld_out >= c, "p2w_knn_interpolate: bad channel count / stride");
     if (ny == 0) return P2W_OK;
-    interp_kernel<<<(unsigned)((ny * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(x, pos_x, pos_y, nbr, ny, k, c,
-                                                                                    ld_out, out);
+    P2W_LAUNCH(interp_kernel, (unsigned)((ny * 32 + 255) / 256), 256, 0, as_stream(stream))(x, pos_x, pos_y, nbr, ny, k, c, ld_out, out);
     return check_launch("p2w_knn_interpolate");
 }
 
@@ -278,7 +276,7 @@ extern "C" int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_s
                                p2w_stream_t stream) {
     P2W_REQUIRE(num_segments >= 1 && c >= 1, "p2w_segment_max: bad sizes");
     dim3 grid(num_segments, (c + 127) / 128);
-    segment_max_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, ptr, c, out);
+    P2W_LAUNCH(segment_max_kernel, grid, 128, 0, as_stream(stream))(x, ptr, c, out);
     return check_launch("p2w_segment_max");
 }
 
@@ -288,12 +286,12 @@ extern "C" int p2w_scatter_minmax(const float *src, const int64_t *index, int64_
     cudaStream_t st = as_stream(stream);
     const int64_t total = dim_size * c;
     if (total == 0) return P2W_OK;
-    scatter_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, arg, total, is_max, n);
+    P2W_LAUNCH(scatter_init_kernel, (unsigned)((total + 255) / 256), 256, 0, st)(out, arg, total, is_max, n);
     if (n > 0) {
         const unsigned blocks = (unsigned)((n * c + 255) / 256);
-        scatter_reduce_kernel<<<blocks, 256, 0, st>>>(src, index, n, c, is_max, out);
-        if (arg) scatter_arg_kernel<<<blocks, 256, 0, st>>>(src, index, n, c, out, arg);
+        P2W_LAUNCH(scatter_reduce_kernel, blocks, 256, 0, st)(src, index, n, c, is_max, out);
+        if (arg) P2W_LAUNCH(scatter_arg_kernel, blocks, 256, 0, st)(src, index, n, c, out, arg);
     }
-    scatter_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, arg, total, n);
+    P2W_LAUNCH(scatter_final_kernel, (unsigned)((total + 255) / 256), 256, 0, st)(out, arg, total, n);
     return check_launch("p2w_scatter_minmax");
 }

@@ -162,39 +162,42 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 
     if (warp == 9) {
         // ------------------------------------------------ weight producer
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t ph = 0;
-            const int per_tile = p.NB1 * n1 + p.NB2 * n2;
-            for (int it = 0; it < my_tiles; it++) {
-                for (int s = 0; s < per_tile; s++) {
-                    mbar_wait(&ring_empty[slot], ph ^ 1);
+        // (the whole warp walks the loop so that it reaches the final barrier converged; lane 0 issues)
+        int slot = 0;
+        uint32_t ph = 0;
+        const int per_tile = p.NB1 * n1 + p.NB2 * n2;
+        for (int it = 0; it < my_tiles; it++) {
+            for (int s = 0; s < per_tile; s++) {
+                mbar_wait(&ring_empty[slot], ph ^ 1);
+                if (lane == 0) {
                     mbar_arrive_expect_tx(&ring_full[slot], SLICE_BYTES);
                     bulk_g2s(ring + slot * SLICE_BYTES, p.wpack + static_cast<size_t>(s) * SLICE_BYTES, SLICE_BYTES,
                              &ring_full[slot]);
-                    if (++slot == STAGES) { slot = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++slot == STAGES) { slot = 0; ph ^= 1; }
             }
         }
     } else if (warp == 8) {
-        // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            int slot = 0, acc = 0;
-            uint32_t ph = 0, tph = 0, use[2] = {0, 0};
-            const uint32_t ring_a = smem_u32(ring), b1_a = smem_u32(b1), b2_a = smem_u32(b2);
-            constexpr uint32_t ID1 = instr_desc(false), ID2 = instr_desc(true);
-            for (int it = 0; it < my_tiles; it++) {
-                for (int layer = 0; layer < 2; layer++) {
-                    mbar_wait(layer == 0 ? b1_full : b2_full, tph);
+        // ------------------------------------------------ MMA issuer (lane 0 issues, the warp stays converged)
+        int slot = 0, acc = 0;
+        uint32_t ph = 0, tph = 0, use0 = 0, use1 = 0;
+        const uint32_t ring_a = smem_u32(ring), b1_a = smem_u32(b1), b2_a = smem_u32(b2);
+        constexpr uint32_t ID1 = instr_desc(false), ID2 = instr_desc(true);
+        for (int it = 0; it < my_tiles; it++) {
+            for (int layer = 0; layer < 2; layer++) {
+                mbar_wait(layer == 0 ? b1_full : b2_full, tph);
+                tc_fence_after();
+                const int nb = layer == 0 ? p.NB1 : p.NB2, ns = layer == 0 ? n1 : n2;
+                for (int blk = 0; blk < nb; blk++) {
+                    const uint32_t use = acc ? use1 : use0;
+                    mbar_wait(&acc_empty[acc], (use & 1) ^ 1);
                     tc_fence_after();
-                    const int nb = layer == 0 ? p.NB1 : p.NB2, ns = layer == 0 ? n1 : n2;
-                    for (int blk = 0; blk < nb; blk++) {
-                        mbar_wait(&acc_empty[acc], (use[acc] & 1) ^ 1);
+                    const uint32_t d_addr = tmem_base + acc * NT;
+                    for (int s = 0; s < ns; s++) {
+                        mbar_wait(&ring_full[slot], ph);
                         tc_fence_after();
-                        const uint32_t d_addr = tmem_base + acc * NT;
-                        for (int s = 0; s < ns; s++) {
-                            mbar_wait(&ring_full[slot], ph);
-                            tc_fence_after();
+                        if (lane == 0) {
 #pragma unroll
                             for (int kk = 0; kk < 2; kk++) {
                                 const uint64_t ad = smem_desc(ring_a + slot * SLICE_BYTES + kk * 4096, 2048, 128);
@@ -204,21 +207,24 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                                 umma(d_addr, ad, bd, layer == 0 ? ID1 : ID2, (s | kk) ? 1u : 0u);
                             }
                             umma_commit(&ring_empty[slot]);
-                            if (++slot == STAGES) { slot = 0; ph ^= 1; }
                         }
-                        umma_commit(&acc_full[acc]);
-                        use[acc]++;
-                        acc ^= 1;
+                        __syncwarp();
+                        if (++slot == STAGES) { slot = 0; ph ^= 1; }
                     }
-                    umma_commit(layer == 0 ? b1_empty : b2_empty);
+                    if (lane == 0) umma_commit(&acc_full[acc]);
+                    __syncwarp();
+                    if (acc) use1++; else use0++;
+                    acc ^= 1;
                 }
-                tph ^= 1;
+                if (lane == 0) umma_commit(layer == 0 ? b1_empty : b2_empty);
+                __syncwarp();
             }
+            tph ^= 1;
         }
     } else {
         // ------------------------------------------------ workers: gather + epilogues
         int acc = 0;
-        uint32_t tph = 0, use[2] = {0, 0};
+        uint32_t tph = 0, use0 = 0, use1 = 0;
         const int q = warp & 3, ch = warp >> 2;
         const int CPR = p.C >> 3;
         const int cpr_c = CPR < 32 ? CPR : 32;
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 
             // ---- epilogue 1: hid[e, h] = relu(D1^T[h, e] + b1[h]) as the MN-major B operand of layer 2
             for (int blk = 0; blk < p.NB1; blk++) {
-                mbar_wait(&acc_full[acc], use[acc] & 1);
+                mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
                 if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // MMA2 of the previous tile is done with hid
                 const int h = blk * 128 + 32 * q + lane;
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[acc]);
-                use[acc]++;
+                if (acc) use1++; else use0++;
                 acc ^= 1;
             }
             fence_proxy_async();
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 
             // ---- epilogue 2: out[t, c] = max_e BN(relu(D2^T[c, e] + b2[c]))
             for (int blk = 0; blk < p.NB2; blk++) {
-                mbar_wait(&acc_full[acc], use[acc] & 1);
+                mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
                 const int co = blk * 128 + 32 * q + lane;
                 const float bias = p.b2p[co], sc = p.scale[co], sh = p.shift[co];
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[acc]);
-                use[acc]++;
+                if (acc) use1++; else use0++;
                 acc ^= 1;
             }
             tph ^= 1;
@@ -425,12 +431,12 @@ int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tg
     float *shp = reinterpret_cast<float *>(base + t.off_shift);
     {
         const int64_t n1 = static_cast<int64_t>(t.NB1) * t.K1p * 128, n2 = static_cast<int64_t>(t.NB2) * hidden * 128;
-        prepack_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(w1, hidden, c_in + 4, t.NB1, t.K1p, w1p);
-        prepack_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(w2, c_out, hidden, t.NB2, hidden, w2p);
-        padvec_kernel<<<(t.NB1 * 128 + 255) / 256, 256, 0, st>>>(b1, hidden, t.NB1 * 128, b1p);
-        padvec_kernel<<<(t.NB2 * 128 + 255) / 256, 256, 0, st>>>(b2, c_out, t.NB2 * 128, b2p);
-        padvec_kernel<<<(t.NB2 * 128 + 255) / 256, 256, 0, st>>>(bn_scale, c_out, t.NB2 * 128, scp);
-        padvec_kernel<<<(t.NB2 * 128 + 255) / 256, 256, 0, st>>>(bn_shift, c_out, t.NB2 * 128, shp);
+        P2W_LAUNCH(prepack_kernel, (unsigned)((n1 + 255) / 256), 256, 0, st)(w1, hidden, c_in + 4, t.NB1, t.K1p, w1p);
+        P2W_LAUNCH(prepack_kernel, (unsigned)((n2 + 255) / 256), 256, 0, st)(w2, c_out, hidden, t.NB2, hidden, w2p);
+        P2W_LAUNCH(padvec_kernel, (t.NB1 * 128 + 255) / 256, 256, 0, st)(b1, hidden, t.NB1 * 128, b1p);
+        P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(b2, c_out, t.NB2 * 128, b2p);
+        P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(bn_scale, c_out, t.NB2 * 128, scp);
+        P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(bn_shift, c_out, t.NB2 * 128, shp);
     }
     ConvTcParams p;
     p.x = x; p.pos_src = pos_src; p.pos_tgt = pos_tgt; p.nbr = nbr;
@@ -453,6 +459,6 @@ int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tg
     const int per_sm = (L.total <= 110 * 1024) ? 2 : 1;     // TMEM: 2 x 256 columns fit one SM
     int grid = sm_count * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    conv_tc_kernel<<<grid, THREADS, L.total, st>>>(p);
+    P2W_LAUNCH(conv_tc_kernel, grid, THREADS, L.total, st)(p);
     return check_launch("p2w_pointnet_conv_max(bf16)");
 }

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace p2w {
@@ -13,6 +15,10 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -41,3 +47,5 @@ extern "C" int p2w_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     if (cc_minor) *cc_minor = prop.minor;
     return P2W_OK;
 }
+
+extern "C" long long p2w_launch_count(void) { return p2w::launches(); }

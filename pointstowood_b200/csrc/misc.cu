@@ -137,8 +137,7 @@ extern "C" int p2w_sa_prepare(const float *pos, int32_t ld_pos, const float *ref
     P2W_REQUIRE(ld_pos >= 3 && num_tiles >= 1, "p2w_sa_prepare: bad sizes");
     P2W_REQUIRE((reinterpret_cast<uintptr_t>(pos4) & 15u) == 0, "p2w_sa_prepare: pos4 must be 16-byte aligned");
     if (n == 0) return P2W_OK;
-    sa_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(pos, ld_pos, refl, ptr, sf,
-                                                                                  num_tiles, n, pos4, pos_back);
+    P2W_LAUNCH(sa_prepare_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream))(pos, ld_pos, refl, ptr, sf, num_tiles, n, pos4, pos_back);
     return check_launch("p2w_sa_prepare");
 }
 
@@ -147,7 +146,7 @@ extern "C" int p2w_pack(const float *cloud, int32_t ld, const int64_t *index, co
                         p2w_stream_t stream) {
     P2W_REQUIRE(ld >= 4 && num_tiles >= 1, "p2w_pack: cloud needs x,y,z,reflectance columns");
     (void)m;
-    pack_kernel<<<num_tiles, 1024, 0, as_stream(stream)>>>(cloud, ld, index, ptr, pos, refl, batch, local_shift, sf);
+    P2W_LAUNCH(pack_kernel, num_tiles, 1024, 0, as_stream(stream))(cloud, ld, index, ptr, pos, refl, batch, local_shift, sf);
     return check_launch("p2w_pack");
 }
 
@@ -156,8 +155,6 @@ extern "C" int p2w_writeback(const float *logits, const float *pos, const int64_
                              p2w_stream_t stream) {
     P2W_REQUIRE(num_tiles >= 1, "p2w_writeback: bad sizes");
     if (m == 0) return P2W_OK;
-    writeback_kernel<<<(unsigned)((m + 255) / 256), 256, 0, as_stream(stream)>>>(logits, pos, ptr, local_shift,
-                                                                                 num_tiles, m, is_wood, out64, prob,
-                                                                                 pred);
+    P2W_LAUNCH(writeback_kernel, (unsigned)((m + 255) / 256), 256, 0, as_stream(stream))(logits, pos, ptr, local_shift, num_tiles, m, is_wood, out64, prob, pred);
     return check_launch("p2w_writeback");
 }

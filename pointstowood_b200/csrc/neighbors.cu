@@ -264,8 +264,7 @@ int launch_sweep(const float *x, const float *y, const int64_t *ptr_x, const int
     }
     const int use_bulk = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) ? 1 : 0;
     const int64_t grid = (ny + NW * QW - 1) / (NW * QW);
-    kern<<<(unsigned)grid, NW * 32, sizeof(SweepSmem), st>>>(x, y, ptr_x, ptr_y, B, nx, ny, k, r2, use_bulk, nbr, d2,
-                                                             cnt);
+    P2W_LAUNCH(kern, (unsigned)grid, NW * 32, sizeof(SweepSmem), st)(x, y, ptr_x, ptr_y, B, nx, ny, k, r2, use_bulk, nbr, d2, cnt);
     return check_launch(RADIUS ? "p2w_radius" : "p2w_knn");
 }
 
@@ -459,16 +458,15 @@ extern "C" int p2w_radius(const float *x, const float *y, const int64_t *ptr_x, 
 
 extern "C" int p2w_table_count(const int32_t *nbr, int64_t ny, int32_t k, int64_t *edge_offset, p2w_stream_t stream) {
     cudaStream_t st = as_stream(stream);
-    if (ny > 0) table_count_kernel<<<(unsigned)((ny * 32 + 255) / 256), 256, 0, st>>>(nbr, ny, k, edge_offset);
-    scan_small_kernel<<<1, 1024, 0, st>>>(edge_offset, ny);
+    if (ny > 0) P2W_LAUNCH(table_count_kernel, (unsigned)((ny * 32 + 255) / 256), 256, 0, st)(nbr, ny, k, edge_offset);
+    P2W_LAUNCH(scan_small_kernel, 1, 1024, 0, st)(edge_offset, ny);
     return check_launch("p2w_table_count");
 }
 
 extern "C" int p2w_table_to_edges(const int32_t *nbr, int64_t ny, int32_t k, const int64_t *edge_offset,
                                   int64_t num_edges, int64_t *edges, p2w_stream_t stream) {
     if (ny == 0 || num_edges == 0) return P2W_OK;
-    table_fill_kernel<<<(unsigned)((ny * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(nbr, ny, k, edge_offset,
-                                                                                        num_edges, edges);
+    P2W_LAUNCH(table_fill_kernel, (unsigned)((ny * 32 + 255) / 256), 256, 0, as_stream(stream))(nbr, ny, k, edge_offset, num_edges, edges);
     return check_launch("p2w_table_to_edges");
 }
 
@@ -476,6 +474,6 @@ extern "C" int p2w_fps(const float *src, const int64_t *ptr, const int64_t *out_
                        float *dist_ws, int64_t *out, p2w_stream_t stream) {
     P2W_REQUIRE(num_tiles >= 1, "p2w_fps: num_tiles must be positive");
     if (n == 0) return P2W_OK;
-    fps_kernel<<<num_tiles, FPS_T, 0, as_stream(stream)>>>(src, ptr, out_ptr, dist_ws, out);
+    P2W_LAUNCH(fps_kernel, num_tiles, FPS_T, 0, as_stream(stream))(src, ptr, out_ptr, dist_ws, out);
     return check_launch("p2w_fps");
 }

@@ -134,7 +134,6 @@ __global__ void __launch_bounds__(256) priority_keys_kernel(const float *__restr
 
 using namespace p2w;
 
-#define P2W_GRID1D(n) (unsigned)(((n) + 255) / 256), 256, 0, st
 
 extern "C" int p2w_ground_normalize(const float *cloud, int32_t ld, int64_t n, const float *mn_xy, float cell,
                                     int32_t nbx, int32_t nby, float *cell_min, float *n_z, p2w_stream_t stream) {
@@ -142,9 +141,9 @@ extern "C" int p2w_ground_normalize(const float *cloud, int32_t ld, int64_t n, c
     cudaStream_t st = as_stream(stream);
     if (n == 0) return P2W_OK;
     const int64_t cells = static_cast<int64_t>(nbx + 1) * (nby + 1);
-    fill_kernel<<<P2W_GRID1D(cells)>>>(cell_min, cells, kPosInf);
-    ground_min_kernel<<<P2W_GRID1D(n)>>>(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min);
-    ground_apply_kernel<<<P2W_GRID1D(n)>>>(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min, n_z);
+    P2W_LAUNCH(fill_kernel, (unsigned)(((cells) + 255) / 256), 256, 0, st)(cell_min, cells, kPosInf);
+    P2W_LAUNCH(ground_min_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min);
+    P2W_LAUNCH(ground_apply_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min, n_z);
     return check_launch("p2w_ground_normalize");
 }
 
@@ -152,7 +151,7 @@ extern "C" int p2w_reflectance_keys(const float *cloud, int32_t ld, int32_t col,
                                     p2w_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     if (n == 0) return P2W_OK;
-    refl_keys_kernel<<<P2W_GRID1D(n)>>>(cloud, ld, col, n, keys);
+    P2W_LAUNCH(refl_keys_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(cloud, ld, col, n, keys);
     return check_launch("p2w_reflectance_keys");
 }
 
@@ -160,10 +159,10 @@ extern "C" int p2w_reflectance_normalize(const int32_t *sorted_idx, int64_t n, f
                                          p2w_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     if (n == 0) return P2W_OK;
-    fill_kernel<<<1, 32, 0, st>>>(mnmx_ws, 1, kPosInf);
-    fill_kernel<<<1, 32, 0, st>>>(mnmx_ws + 1, 1, kNegInf);
-    refl_normal_kernel<<<P2W_GRID1D(n)>>>(sorted_idx, n, v, mnmx_ws);
-    refl_scale_kernel<<<P2W_GRID1D(n)>>>(v, n, mnmx_ws, out);
+    P2W_LAUNCH(fill_kernel, 1, 32, 0, st)(mnmx_ws, 1, kPosInf);
+    P2W_LAUNCH(fill_kernel, 1, 32, 0, st)(mnmx_ws + 1, 1, kNegInf);
+    P2W_LAUNCH(refl_normal_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(sorted_idx, n, v, mnmx_ws);
+    P2W_LAUNCH(refl_scale_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(v, n, mnmx_ws, out);
     return check_launch("p2w_reflectance_normalize");
 }
 
@@ -171,7 +170,7 @@ extern "C" int p2w_assemble5(const float *cloud, int32_t ld, const float *refl, 
                              float *feat, p2w_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     if (n == 0) return P2W_OK;
-    assemble5_kernel<<<P2W_GRID1D(n)>>>(cloud, ld, refl, n_z, n, feat);
+    P2W_LAUNCH(assemble5_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(cloud, ld, refl, n_z, n, feat);
     return check_launch("p2w_assemble5");
 }
 
@@ -179,6 +178,6 @@ extern "C" int p2w_priority_keys(const float *feat, const int32_t *members, cons
                                  float refl_min, uint32_t seed, uint64_t *keys, p2w_stream_t stream) {
     cudaStream_t st = as_stream(stream);
     if (m == 0) return P2W_OK;
-    priority_keys_kernel<<<P2W_GRID1D(m)>>>(feat, members, member_tile, m, refl_min, seed, keys);
+    P2W_LAUNCH(priority_keys_kernel, (unsigned)(((m) + 255) / 256), 256, 0, st)(feat, members, member_tile, m, refl_min, seed, keys);
     return check_launch("p2w_priority_keys");
 }

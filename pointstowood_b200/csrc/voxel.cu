@@ -157,9 +157,9 @@ inline int64_t scan_blocks(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; 
 int scan_exclusive(const int64_t *in, int64_t *out, int64_t n, int64_t *bsum, int64_t *total_out, cudaStream_t st) {
     const int64_t nb = scan_blocks(n);
     if (nb == 0) return P2W_OK;
-    scan_partial_kernel<<<(unsigned)nb, SCAN_T, 0, st>>>(in, n, bsum);
-    scan_single_kernel<<<1, 1024, 0, st>>>(bsum, nb);
-    scan_apply_kernel<<<(unsigned)nb, SCAN_T, 0, st>>>(in, n, bsum, out, total_out);
+    P2W_LAUNCH(scan_partial_kernel, (unsigned)nb, SCAN_T, 0, st)(in, n, bsum);
+    P2W_LAUNCH(scan_single_kernel, 1, 1024, 0, st)(bsum, nb);
+    P2W_LAUNCH(scan_apply_kernel, (unsigned)nb, SCAN_T, 0, st)(in, n, bsum, out, total_out);
     return check_launch("scan_exclusive");
 }
 
@@ -286,12 +286,12 @@ extern "C" int p2w_colminmax(const float *pos, int64_t n, int32_t dim, int32_t l
                              p2w_stream_t stream) {
     P2W_REQUIRE(dim >= 1 && dim <= 8 && ld >= dim, "p2w_colminmax: dim=%d ld=%d unsupported", dim, ld);
     cudaStream_t st = as_stream(stream);
-    minmax_init_kernel<<<1, 32, 0, st>>>(mn, mx, dim);
+    P2W_LAUNCH(minmax_init_kernel, 1, 32, 0, st)(mn, mx, dim);
     if (n > 0) {
         int64_t blocks = (n + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
         switch (dim) {
-#define P2W_MM(D) case D: minmax_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(pos, n, ld, mn, mx); break;
+#define P2W_MM(D) case D: P2W_LAUNCH(minmax_kernel<D>, (unsigned)blocks, 256, 0, st)(pos, n, ld, mn, mx); break;
             P2W_MM(1) P2W_MM(2) P2W_MM(3) P2W_MM(4) P2W_MM(5) P2W_MM(6) P2W_MM(7) P2W_MM(8)
 #undef P2W_MM
         }
@@ -303,8 +303,7 @@ extern "C" int p2w_grid(const float *pos, int64_t n, int32_t dim, int32_t ld, co
                         const float *start, const float *end, int64_t *ids, p2w_stream_t stream) {
     P2W_REQUIRE(dim >= 1 && ld >= dim, "p2w_grid: dim=%d ld=%d unsupported", dim, ld);
     if (n == 0) return P2W_OK;
-    grid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(pos, n, dim, ld, batch, size, start, end,
-                                                                            ids);
+    P2W_LAUNCH(grid_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream))(pos, n, dim, ld, batch, size, start, end, ids);
     return check_launch("p2w_grid");
 }
 
@@ -336,10 +335,10 @@ extern "C" int p2w_sort_pairs(const uint64_t *keys_in, const int32_t *vals_in, u
         const bool to_out = ((passes - 1 - ps) % 2) == 0;
         uint64_t *kout = to_out ? keys_out : ktmp;
         int32_t *vout = to_out ? vals_out : vtmp;
-        rs_hist_kernel<<<p.nb, RS_T, 0, st>>>(kin, n, p.per_block, ps * 8, p.nb, counts);
+        P2W_LAUNCH(rs_hist_kernel, p.nb, RS_T, 0, st)(kin, n, p.per_block, ps * 8, p.nb, counts);
         int rc = scan_exclusive(counts, counts, ncnt, bsum, nullptr, st);
         if (rc) return rc;
-        rs_scatter_kernel<<<p.nb, RS_T, 0, st>>>(kin, vin, n, p.per_block, ps * 8, p.nb, counts, kout, vout);
+        P2W_LAUNCH(rs_scatter_kernel, p.nb, RS_T, 0, st)(kin, vin, n, p.per_block, ps * 8, p.nb, counts, kout, vout);
         kin = kout;
         vin = vout;
     }
@@ -359,9 +358,9 @@ extern "C" int p2w_unique_last(const uint64_t *sorted_keys, const int32_t *sorte
     int64_t *flag = static_cast<int64_t *>(ws);
     int64_t *bsum = flag + n + 1;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    head_flag_kernel<<<blocks, 256, 0, st>>>(sorted_keys, n, flag);
+    P2W_LAUNCH(head_flag_kernel, blocks, 256, 0, st)(sorted_keys, n, flag);
     int rc = scan_exclusive(flag, flag, n, bsum, num_unique, st);
     if (rc) return rc;
-    unique_last_kernel<<<blocks, 256, 0, st>>>(sorted_keys, sorted_idx, n, flag, perm, inverse, seg_start);
+    P2W_LAUNCH(unique_last_kernel, blocks, 256, 0, st)(sorted_keys, sorted_idx, n, flag, perm, inverse, seg_start);
     return check_launch("p2w_unique_last");
 }

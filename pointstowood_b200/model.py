@@ -29,7 +29,7 @@ from torch import Tensor, nn
 from . import ops
 
 __all__ = ["Net", "SAModule", "GlobalSAModule", "FPModule", "InvertedResidualBlock", "PointNetConv", "MLP",
-           "initialize_weights", "load_model"]
+           "initialize_weights", "load_model", "randomise_bn_", "make_data"]
 
 
 def initialize_weights(model: nn.Module) -> None:
@@ -273,6 +273,21 @@ def load_model(path: str, model: nn.Module, device) -> nn.Module:
     checkpoint = torch.load(path, map_location=device)
     state = {(k[7:] if k.startswith("module.") else k): v for k, v in checkpoint["model_state_dict"].items()}
     model.load_state_dict(state, strict=False)
+    return model
+
+
+def randomise_bn_(model: nn.Module, seed: int = 5) -> nn.Module:
+    """Seeded, non-trivial BatchNorm statistics for random-weight benchmarks (the shipped
+    checkpoint is absent, so eval-mode BN would otherwise be the identity)."""
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            c = m.num_features
+            with torch.no_grad():
+                m.running_mean.copy_(torch.randn(c, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(c, generator=g) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(c, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(c, generator=g) * 0.1)
     return model
 
 

@@ -38,6 +38,35 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _KernelTimer:
+    """bench.py's live roofline probe: CUDA-event pairs on the launching stream around every call
+    of ONE chosen C-ABI entry point, with the algorithmic work (bytes or FLOPs) of each call."""
+
+    def __init__(self):
+        self.target, self.pairs, self.work = None, [], 0.0
+
+    def reset(self, target):
+        self.target, self.pairs, self.work = target, [], 0.0
+
+    def call(self, name, work, fn, *args):
+        if self.target != name:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        self.pairs.append((e0, e1))
+        self.work += work
+        return rc
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return dict(launches=len(self.pairs), ms=sum(a.elapsed_time(b) for a, b in self.pairs), work=self.work)
+
+
+KERNEL_TIMER = _KernelTimer()
+
+
 def _dp(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -83,8 +112,9 @@ def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return
         raise _lib.P2WError("ptr_x and ptr_y must describe the same number of examples")
     nbr = torch.empty((y.size(0), k), device=x.device, dtype=torch.int32)
     d2 = torch.empty((y.size(0), k), device=x.device, dtype=torch.float32) if return_d2 else None
-    _lib.check(_lib.lib().p2w_knn(_dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), ptr_x.numel() - 1, x.size(0), y.size(0),
-                                  k, _dp(nbr), _dp(d2), _stream()))
+    work = 12.0 * (x.size(0) + y.size(0)) + 16.0 * y.size(0) * k + 16.0 * ptr_x.numel()
+    _lib.check(KERNEL_TIMER.call("p2w_knn", work, _lib.lib().p2w_knn, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y),
+                                 ptr_x.numel() - 1, x.size(0), y.size(0), k, _dp(nbr), _dp(d2), _stream()))
     return (nbr, d2) if return_d2 else nbr
 
 
@@ -364,9 +394,10 @@ def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, 
     ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
     out = torch.empty((pos_tgt.size(0), Co), device=x.device, dtype=torch.float32)
     args = [_req(t, torch.float32, "weights") for t in (w1, b1, w2, b2, bn_scale, bn_shift)]
-    _lib.check(L.p2w_pointnet_conv_max(_dp(x), _dp(pos_src), _dp(pos_tgt), _dp(nbr), x.size(0), pos_tgt.size(0),
-                                       nbr.size(1), C, H, Co, *[_dp(a) for a in args], _dp(out), mode, _dp(ws),
-                                       nbytes, _stream()))
+    flops = float(pos_tgt.size(0)) * 32.0 * (2.0 * (C + 4) * H + 2.0 * H * Co)
+    _lib.check(KERNEL_TIMER.call("p2w_pointnet_conv_max", flops, L.p2w_pointnet_conv_max, _dp(x), _dp(pos_src),
+                                 _dp(pos_tgt), _dp(nbr), x.size(0), pos_tgt.size(0), nbr.size(1), C, H, Co,
+                                 *[_dp(a) for a in args], _dp(out), mode, _dp(ws), nbytes, _stream()))
     return out
 
 
