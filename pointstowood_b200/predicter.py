@@ -25,7 +25,7 @@ from . import model as M
 from . import ops
 from .preprocessing import TileStore
 
-__all__ = ["plan_batches", "shard_batches", "classify_tiles", "SemanticSegmentation"]
+__all__ = ["plan_batches", "shard_batches", "classify_tiles", "gather_rows", "SemanticSegmentation"]
 
 
 def plan_batches(num_tiles: int, batch_size: int) -> List[Tuple[int, int]]:
@@ -76,6 +76,26 @@ def classify_tiles(net: torch.nn.Module, tiles: TileStore, batch_size: int = 8, 
         spans.append((lo, hi))
     cat = (lambda xs: torch.cat(xs) if xs else torch.empty(0, device=dev))
     return cat(probs), cat(preds), (cat(rows) if want_rows else None), spans
+
+
+def gather_rows(rows: torch.Tensor, batch_ids: Sequence[int], dst: int = 0):
+    """The one exchange of the multi-GPU inference path: every rank sends the rows it classified
+    (any [m, c] tensor, batch order) and the batch indices they belong to; `dst` gets the pieces of
+    all ranks as a list of (batch_ids, rows) and re-orders them by batch.  Works on NCCL (device
+    tensors) and gloo (host tensors); returns None on the other ranks."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    meta = [None] * world
+    dist.all_gather_object(meta, (list(batch_ids), int(rows.size(0))))
+    width = rows.size(1)
+    longest = max(m[1] for m in meta)
+    padded = rows.new_zeros((longest, width))
+    padded[: rows.size(0)] = rows
+    bucket = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bucket, dst=dst)
+    if rank != dst:
+        return None
+    return [(meta[r][0], bucket[r][: meta[r][1]]) for r in range(world)]
 
 
 def SemanticSegmentation(args):
