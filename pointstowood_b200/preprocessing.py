@@ -134,7 +134,7 @@ class Voxelise:
     # ---- src/preprocessing.py:79-127
     def write_voxels(self) -> TileStore:
         pos = self.pos
-        if hasattr(pos, "values"):                                   # pandas DataFrame, as in the reference
+        if hasattr(pos, "columns"):                                  # pandas DataFrame, as in the reference
             has_nz = "n_z" in pos.columns
             arr = np.ascontiguousarray(pos.values, dtype=np.float32)
         else:

@@ -235,3 +235,22 @@ def test_errors_are_loud(ops):
         ops.knn_table(x.cpu(), x, 4, torch.tensor([0, 10]).cuda(), torch.tensor([0, 10]).cuda())
     with pytest.raises(P2WError):
         ops.knn(x, x, 4, cosine=True)
+
+
+def test_torch_ops_namespace_matches_upstream_schemas(ops):
+    """torch.ops.p2w.* take the dispatcher-level arguments of torch_cluster / torch_scatter."""
+    import pointstowood_b200.torch_ops  # noqa: F401
+    rng = np.random.default_rng(12)
+    x, y, px, py = _tiles(rng, [700, 300], [90, 40])
+    e = torch.ops.p2w.knn(_dev(x), _dev(y), _dev(px), _dev(py), 8, False, 1)
+    assert np.array_equal(e.cpu().numpy(), O.table_to_edges(O.knn(x, y, 8, px, py)))
+    e = torch.ops.p2w.radius(_dev(x), _dev(y), _dev(px), _dev(py), 0.2, 16, 1, False)
+    assert np.array_equal(e.cpu().numpy(), O.table_to_edges(O.radius(x, y, 0.2, px, py, 16)[0]))
+    out = torch.ops.p2w.fps(_dev(x), _dev(px), torch.tensor([0.1]).cuda(), False)
+    assert np.array_equal(out.cpu().numpy(), O.fps(x, px, 0.1))
+    sz = np.array([0.1, 0.1, 0.1], np.float32)
+    assert np.array_equal(torch.ops.p2w.grid(_dev(x), _dev(sz), None, None).cpu().numpy(), O.grid(x, sz))
+    src = rng.normal(size=(1000, 1)).astype(np.float32)
+    idx = np.sort(rng.integers(0, 50, 1000)).astype(np.int64)
+    m, _ = torch.ops.p2w.scatter_max(_dev(src), _dev(idx), 0, None, 50)
+    assert np.array_equal(m.cpu().numpy(), O.scatter_max(src, idx, 50))
