@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch-points", type=int, default=1 << 20,
+                    help="points of consecutive reference batches that share one launch set")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -186,15 +188,16 @@ def main():
     dev_cloud = host.cuda()
     bf16 = args.precision == "bf16"
     torch.manual_seed(141190)
-    net = M.Net(num_classes=1, conv_mode=ops.CONV_BF16_TC if bf16 else ops.CONV_FP32)
+    net = M.Net(num_classes=1)
     M.randomise_bn_(net, 5)
-    net = net.cuda().eval()
+    net = net.cuda().eval().set_precision("bf16" if bf16 else "fp32")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
 
     def step(cloud):
         store = Voxelise(cloud, minpoints=CFG["min_pts"], maxpoints=CFG["max_pts"], gridsize=CFG["grid_size"]).write_voxels()
-        prob, pred, _, _ = classify_tiles(net, store, CFG["batch_size"], CFG["is_wood"], autocast_bf16=bf16)
+        prob, pred, _, _ = classify_tiles(net, store, CFG["batch_size"], CFG["is_wood"],
+                                          max_points_per_launch=args.launch_points)
         return store, prob, pred
 
     def barrier():

@@ -31,6 +31,9 @@ typedef void *p2w_stream_t; /* cudaStream_t */
 #define P2W_ECUDA (-2)    /* CUDA runtime error at launch */
 #define P2W_ENOGPU (-3)   /* no sm_100 device */
 
+#define P2W_F32 0         /* element types of the activation arrays that may be FP32 or BF16 */
+#define P2W_BF16 1
+
 #define P2W_MAX_K 128     /* upstream knn asserts k <= 100 */
 
 int p2w_version(void);
@@ -88,6 +91,19 @@ int p2w_grid(const float *pos, int64_t n, int32_t dim, int32_t ld, const int64_t
              const float *size, const float *start, const float *end, int64_t *ids,
              p2w_stream_t stream);
 
+/* Voxel keys for SEVERAL reference batches in one launch ("super-batch").  Tiles are the CSR
+ * tile_ptr [num_tiles+1] over points; group_ptr [num_groups+1] (device, over tiles) lists the
+ * reference batches (src/predicter.py:177-180, batch_size tiles each).  Each group is voxelised on
+ * its own grid, start/end = column min/max over that group's points, exactly what
+ * voxel_grid(pos, size, batch) does for one batch (src/model.py:104).
+ * keys[i] = (tile << spatial_bits) | spatial_id: ascending key order == the reference's ascending
+ * batch-major cluster id inside every group.  group_min/group_max: [num_groups,3] workspace/outputs;
+ * *overflow (device int32) is set to 1 when an id needs more than spatial_bits bits. */
+int p2w_voxel_keys_grouped(const float *pos, int64_t n, int32_t ld, const int64_t *tile_ptr,
+                           int32_t num_tiles, const int64_t *group_ptr, int32_t num_groups,
+                           float size, int32_t spatial_bits, float *group_min, float *group_max,
+                           uint64_t *keys, int32_t *overflow, p2w_stream_t stream);
+
 /* Stable LSD radix sort of (key, value) pairs on key bits [0, key_bits).
  * ws: p2w_sort_ws_bytes(n) bytes.  Results land in keys_out / vals_out. */
 size_t p2w_sort_ws_bytes(int64_t n);
@@ -124,6 +140,17 @@ int p2w_pointnet_conv_max(const float *x, const float *pos_src, const float *pos
                           const float *w1, const float *b1, const float *w2, const float *b2,
                           const float *bn_scale, const float *bn_shift, float *out,
                           int32_t mode, void *ws, size_t ws_bytes, p2w_stream_t stream);
+/* Extended form: feature rows in / out may be BF16 in the tensor-core mode (x_dtype, out_dtype =
+ * P2W_F32 | P2W_BF16), and flags & P2W_CONV_WS_PACKED says `ws` still holds the weights re-laid-out
+ * by an earlier call with the same (w1, b1, w2, b2, bn) and mode, so the packing kernels are skipped
+ * (a model packs once). */
+#define P2W_CONV_WS_PACKED 1
+int p2w_pointnet_conv_max_ex(const void *x, int32_t x_dtype, const float *pos_src, const float *pos_tgt,
+                             const int32_t *nbr, int64_t n_src, int64_t n_tgt, int32_t k,
+                             int32_t c_in, int32_t hidden, int32_t c_out,
+                             const float *w1, const float *b1, const float *w2, const float *b2,
+                             const float *bn_scale, const float *bn_shift, void *out, int32_t out_dtype,
+                             int32_t mode, void *ws, size_t ws_bytes, int32_t flags, p2w_stream_t stream);
 size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, int32_t mode);
 
 /* ---- knn_interpolate (src/model.py:149, torch_geometric.nn.knn_interpolate) ---------
@@ -131,6 +158,19 @@ size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, i
 int p2w_knn_interpolate(const float *x, const float *pos_x, const float *pos_y,
                         const int32_t *nbr, int64_t ny, int32_t k, int32_t c, int32_t ld_out,
                         float *out, p2w_stream_t stream);
+
+/* Same with FP32 or BF16 feature rows in and out (x_dtype / out_dtype = P2W_F32 | P2W_BF16); positions
+ * and weights stay FP32. */
+int p2w_knn_interpolate_ex(const void *x, int32_t x_dtype, const float *pos_x, const float *pos_y,
+                           const int32_t *nbr, int64_t ny, int32_t k, int32_t c, int32_t ld_out,
+                           void *out, int32_t out_dtype, p2w_stream_t stream);
+
+/* ---- dense-block epilogues (src/model.py:18-85, InvertedResidualBlock in eval mode) ------------
+ * What remains between two k=1 convolutions once every BatchNorm that follows a convolution is
+ * folded into its weights: y = relu(x*s1 + t1), and if s2 != NULL y = relu(y*s2 + t2), per channel,
+ * on [n, c] activations (c % 8 == 0; x may alias y). */
+int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, const float *s1, const float *t1,
+                    const float *s2, const float *t2, int32_t dtype, p2w_stream_t stream);
 
 /* ---- segment / scatter reductions ---------------------------------------------------
  * p2w_segment_max: torch_geometric global_max_pool (src/model.py:136) for a sorted batch

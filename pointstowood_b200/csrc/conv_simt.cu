@@ -8,6 +8,8 @@
 // registers.  BatchNorm is applied per edge BEFORE the max (its scale may be negative),
 // padded / missing edges are replaced by a duplicate of a valid one, so the [E, C'] edge
 // tensor never exists in HBM.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace p2w {
@@ -125,10 +127,16 @@ __global__ void __launch_bounds__(CONV_WARPS * 32)
 }
 
 // ------------------------------------------------------------------ knn_interpolate
-// warp per query; lanes over channels.  w = 1 / max(|p_x - p_y|^2, 1e-16)
-__global__ void __launch_bounds__(256) interp_kernel(const float *__restrict__ x, const float *__restrict__ pos_x,
+// warp per query; lanes over channels.  w = 1 / max(|p_x - p_y|^2, 1e-16).  TI / TO: float or bf16.
+__device__ __forceinline__ float ld_f(const float *p) { return *p; }
+__device__ __forceinline__ float ld_f(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_f(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st_f(__nv_bfloat16 *p, float v) { *p = __float2bfloat16(v); }
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) interp_kernel(const TI *__restrict__ x, const float *__restrict__ pos_x,
                                                      const float *__restrict__ pos_y, const int32_t *__restrict__ nbr,
-                                                     int64_t ny, int k, int c, int ld_out, float *__restrict__ out) {
+                                                     int64_t ny, int k, int c, int ld_out, TO *__restrict__ out) {
     const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= ny) return;
@@ -152,9 +160,9 @@ __global__ void __launch_bounds__(256) interp_kernel(const float *__restrict__ x
         for (int e = 0; e < k; e++) {
             const int je = __shfl_sync(FULL, j, e);
             const float we = __shfl_sync(FULL, w, e);
-            if (je >= 0 && ch < c) num = __fadd_rn(num, __fmul_rn(x[static_cast<int64_t>(je) * c + ch], we));
+            if (je >= 0 && ch < c) num = __fadd_rn(num, __fmul_rn(ld_f(x + static_cast<int64_t>(je) * c + ch), we));
         }
-        if (ch < c) out[q * ld_out + ch] = __fdiv_rn(num, den);
+        if (ch < c) st_f(out + q * ld_out + ch, __fdiv_rn(num, den));
     }
 }
 
@@ -216,10 +224,11 @@ __global__ void scatter_final_kernel(float *out, const int64_t *arg, int64_t tot
 
 using namespace p2w;
 
-int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
-                       int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out, const float *w1,
-                       const float *b1, const float *w2, const float *b2, const float *bn_scale,
-                       const float *bn_shift, float *out, void *ws, size_t ws_bytes, cudaStream_t st);
+int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const float *pos_tgt, const int32_t *nbr,
+                       int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out,
+                       const float *w1, const float *b1, const float *w2, const float *b2, const float *bn_scale,
+                       const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
+                       bool packed);
 size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out);
 
 extern "C" size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, int32_t mode) {
@@ -227,11 +236,17 @@ extern "C" size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32
     return sizeof(float) * (static_cast<size_t>(c_in + 4) * hidden + static_cast<size_t>(hidden) * c_out) + 256;
 }
 
-extern "C" int p2w_pointnet_conv_max(const float *x, const float *pos_src, const float *pos_tgt, const int32_t *nbr,
-                                     int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden,
-                                     int32_t c_out, const float *w1, const float *b1, const float *w2, const float *b2,
-                                     const float *bn_scale, const float *bn_shift, float *out, int32_t mode, void *ws,
-                                     size_t ws_bytes, p2w_stream_t stream) {
+static int conv_dispatch(const void *xv, int32_t x_dtype, const float *pos_src, const float *pos_tgt,
+                         const int32_t *nbr, int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden,
+                         int32_t c_out, const float *w1, const float *b1, const float *w2, const float *b2,
+                         const float *bn_scale, const float *bn_shift, void *outv, int32_t out_dtype, int32_t mode,
+                         void *ws, size_t ws_bytes, p2w_stream_t stream, bool packed) {
+    P2W_REQUIRE((x_dtype == P2W_F32 || x_dtype == P2W_BF16) && (out_dtype == P2W_F32 || out_dtype == P2W_BF16),
+                "p2w_pointnet_conv_max: unknown dtype");
+    P2W_REQUIRE(mode == P2W_CONV_BF16_TC || (x_dtype == P2W_F32 && out_dtype == P2W_F32),
+                "p2w_pointnet_conv_max: the FP32 mode takes and returns FP32 rows");
+    const float *x = static_cast<const float *>(xv);
+    float *out = static_cast<float *>(outv);
     P2W_REQUIRE(k >= 1 && k <= 32, "p2w_pointnet_conv_max: k=%d outside [1,32]", k);
     P2W_REQUIRE(c_in >= 1 && hidden % 8 == 0 && c_out % 8 == 0 && hidden > 0 && c_out > 0,
                 "p2w_pointnet_conv_max: hidden=%d and c_out=%d must be positive multiples of 8", hidden, c_out);
@@ -241,15 +256,18 @@ extern "C" int p2w_pointnet_conv_max(const float *x, const float *pos_src, const
     if (n_tgt == 0) return P2W_OK;
     cudaStream_t st = as_stream(stream);
     if (mode == P2W_CONV_BF16_TC)
-        return p2w_conv_tc_launch(x, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out, w1, b1, w2, b2,
-                                  bn_scale, bn_shift, out, ws, ws_bytes, st);
+        return p2w_conv_tc_launch(xv, x_dtype == P2W_BF16, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out,
+                                  w1, b1, w2, b2, bn_scale, bn_shift, outv, out_dtype == P2W_BF16, ws, ws_bytes, st,
+                                  packed);
     const int K1 = c_in + 4;
     float *w1t = static_cast<float *>(ws);
     float *w2t = w1t + static_cast<size_t>(K1) * hidden;
     // 16-byte alignment of the second panel for the float4 loads
     w2t = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(w2t) + 15) & ~uintptr_t(15));
-    P2W_LAUNCH(transpose_kernel, (K1 * hidden + 255) / 256, 256, 0, st)(w1, hidden, K1, w1t);
-    P2W_LAUNCH(transpose_kernel, (hidden * c_out + 255) / 256, 256, 0, st)(w2, c_out, hidden, w2t);
+    if (!packed) {
+        P2W_LAUNCH(transpose_kernel, (K1 * hidden + 255) / 256, 256, 0, st)(w1, hidden, K1, w1t);
+        P2W_LAUNCH(transpose_kernel, (hidden * c_out + 255) / 256, 256, 0, st)(w2, c_out, hidden, w2t);
+    }
     const size_t smem = sizeof(float) * 32 * ((K1 | 1) + (hidden | 1));
     P2W_REQUIRE(smem <= 200 * 1024, "p2w_pointnet_conv_max: layer too wide for the FP32 kernel");
     static size_t smem_set = 0;
@@ -262,14 +280,55 @@ extern "C" int p2w_pointnet_conv_max(const float *x, const float *pos_src, const
     return check_launch("p2w_pointnet_conv_max");
 }
 
+extern "C" int p2w_pointnet_conv_max(const float *x, const float *pos_src, const float *pos_tgt, const int32_t *nbr,
+                                     int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden,
+                                     int32_t c_out, const float *w1, const float *b1, const float *w2, const float *b2,
+                                     const float *bn_scale, const float *bn_shift, float *out, int32_t mode, void *ws,
+                                     size_t ws_bytes, p2w_stream_t stream) {
+    return conv_dispatch(x, P2W_F32, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out, w1, b1, w2, b2,
+                         bn_scale, bn_shift, out, P2W_F32, mode, ws, ws_bytes, stream, false);
+}
+
+extern "C" int p2w_pointnet_conv_max_ex(const void *x, int32_t x_dtype, const float *pos_src, const float *pos_tgt,
+                                        const int32_t *nbr, int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in,
+                                        int32_t hidden, int32_t c_out, const float *w1, const float *b1,
+                                        const float *w2, const float *b2, const float *bn_scale,
+                                        const float *bn_shift, void *out, int32_t out_dtype, int32_t mode, void *ws,
+                                        size_t ws_bytes, int32_t flags, p2w_stream_t stream) {
+    return conv_dispatch(x, x_dtype, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out, w1, b1, w2, b2,
+                         bn_scale, bn_shift, out, out_dtype, mode, ws, ws_bytes, stream,
+                         (flags & P2W_CONV_WS_PACKED) != 0);
+}
+
+extern "C" int p2w_knn_interpolate_ex(const void *x, int32_t x_dtype, const float *pos_x, const float *pos_y,
+                                      const int32_t *nbr, int64_t ny, int32_t k, int32_t c, int32_t ld_out, void *out,
+                                      int32_t out_dtype, p2w_stream_t stream) {
+    P2W_REQUIRE(k >= 1 && k <= 32, "p2w_knn_interpolate: k=%d outside [1,32]", k);
+    P2W_REQUIRE(c >= 1 && ld_out >= c, "p2w_knn_interpolate: bad channel count / stride");
+    P2W_REQUIRE((x_dtype == P2W_F32 || x_dtype == P2W_BF16) && (out_dtype == P2W_F32 || out_dtype == P2W_BF16),
+                "p2w_knn_interpolate: unknown dtype");
+    if (ny == 0) return P2W_OK;
+    cudaStream_t st = as_stream(stream);
+    const unsigned blocks = (unsigned)((ny * 32 + 255) / 256);
+    const float *xf = static_cast<const float *>(x);
+    const __nv_bfloat16 *xh = static_cast<const __nv_bfloat16 *>(x);
+    float *of = static_cast<float *>(out);
+    __nv_bfloat16 *oh = static_cast<__nv_bfloat16 *>(out);
+    if (x_dtype == P2W_F32 && out_dtype == P2W_F32)
+        P2W_LAUNCH((interp_kernel<float, float>), blocks, 256, 0, st)(xf, pos_x, pos_y, nbr, ny, k, c, ld_out, of);
+    else if (x_dtype == P2W_F32)
+        P2W_LAUNCH((interp_kernel<float, __nv_bfloat16>), blocks, 256, 0, st)(xf, pos_x, pos_y, nbr, ny, k, c, ld_out, oh);
+    else if (out_dtype == P2W_F32)
+        P2W_LAUNCH((interp_kernel<__nv_bfloat16, float>), blocks, 256, 0, st)(xh, pos_x, pos_y, nbr, ny, k, c, ld_out, of);
+    else
+        P2W_LAUNCH((interp_kernel<__nv_bfloat16, __nv_bfloat16>), blocks, 256, 0, st)(xh, pos_x, pos_y, nbr, ny, k, c, ld_out, oh);
+    return check_launch("p2w_knn_interpolate");
+}
+
 extern "C" int p2w_knn_interpolate(const float *x, const float *pos_x, const float *pos_y, const int32_t *nbr,
                                    int64_t ny, int32_t k, int32_t c, int32_t ld_out, float *out,
                                    p2w_stream_t stream) {
-    P2W_REQUIRE(k >= 1 && k <= 32, "p2w_knn_interpolate: k=%d outside [1,32]", k);
-    P2W_REQUIRE(c >= 1 && ld_out >= c, "p2w_knn_interpolate: bad channel count / stride");
-    if (ny == 0) return P2W_OK;
-    P2W_LAUNCH(interp_kernel, (unsigned)((ny * 32 + 255) / 256), 256, 0, as_stream(stream))(x, pos_x, pos_y, nbr, ny, k, c, ld_out, out);
-    return check_launch("p2w_knn_interpolate");
+    return p2w_knn_interpolate_ex(x, P2W_F32, pos_x, pos_y, nbr, ny, k, c, ld_out, out, P2W_F32, stream);
 }
 
 extern "C" int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_segments, int32_t c, float *out,

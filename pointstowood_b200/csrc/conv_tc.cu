@@ -39,13 +39,14 @@ constexpr int TMEM_COLS = 2 * NT;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct ConvTcParams {
-    const float *x, *pos_src, *pos_tgt;
+    const void *x;                 // [n_src, C] FP32 or BF16 (x_bf16)
+    const float *pos_src, *pos_tgt;
     const int32_t *nbr;
     int64_t n_tgt;
-    int K, C, H, Co, K1p, NB1, NB2, num_tiles;
+    int K, C, H, Co, K1p, NB1, NB2, num_tiles, x_bf16, out_bf16;
     const unsigned char *wpack;
     const float *b1p, *b2p, *scale, *shift;
-    float *out;
+    void *out;                     // [n_tgt, Co] FP32 or BF16 (out_bf16)
 };
 
 // ---- tcgen05 / TMEM wrappers
@@ -260,28 +261,47 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             }
             worker_bar();
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
-            for (int r0 = warp * rpw; r0 < NT; r0 += 8 * rpw * 4) {
-                float4 lo[4], hi[4];
+            if (p.x_bf16) {
+                const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16 *>(p.x);
+                for (int r0 = warp * rpw; r0 < NT; r0 += 8 * rpw * 4) {
+                    uint4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int n = r0 + u * 8 * rpw + ri;
-                    if (n < NT && ck < CPR) {
-                        const float4 *src =
-                            reinterpret_cast<const float4 *>(p.x + static_cast<int64_t>(s_j[n]) * p.C + ck * 8);
-                        lo[u] = __ldg(src);
-                        hi[u] = __ldg(src + 1);
+                    for (int u = 0; u < 4; u++) {
+                        const int n = r0 + u * 8 * rpw + ri;
+                        if (n < NT && ck < CPR)
+                            v[u] = __ldg(reinterpret_cast<const uint4 *>(xb + static_cast<int64_t>(s_j[n]) * p.C + ck * 8));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int n = r0 + u * 8 * rpw + ri;
+                        if (n < NT && ck < CPR) *reinterpret_cast<uint4 *>(b1 + ck * LBO1 + n * 16) = v[u];
                     }
                 }
+            } else {
+                const float *xf = static_cast<const float *>(p.x);
+                for (int r0 = warp * rpw; r0 < NT; r0 += 8 * rpw * 4) {
+                    float4 lo[4], hi[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int n = r0 + u * 8 * rpw + ri;
-                    if (n < NT && ck < CPR) {
-                        uint4 v;
-                        v.x = pack_bf16(lo[u].x, lo[u].y);
-                        v.y = pack_bf16(lo[u].z, lo[u].w);
-                        v.z = pack_bf16(hi[u].x, hi[u].y);
-                        v.w = pack_bf16(hi[u].z, hi[u].w);
-                        *reinterpret_cast<uint4 *>(b1 + ck * LBO1 + n * 16) = v;
+                    for (int u = 0; u < 4; u++) {
+                        const int n = r0 + u * 8 * rpw + ri;
+                        if (n < NT && ck < CPR) {
+                            const float4 *src =
+                                reinterpret_cast<const float4 *>(xf + static_cast<int64_t>(s_j[n]) * p.C + ck * 8);
+                            lo[u] = __ldg(src);
+                            hi[u] = __ldg(src + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int n = r0 + u * 8 * rpw + ri;
+                        if (n < NT && ck < CPR) {
+                            uint4 v;
+                            v.x = pack_bf16(lo[u].x, lo[u].y);
+                            v.y = pack_bf16(lo[u].z, lo[u].w);
+                            v.z = pack_bf16(hi[u].x, hi[u].y);
+                            v.w = pack_bf16(hi[u].z, hi[u].w);
+                            *reinterpret_cast<uint4 *>(b1 + ck * LBO1 + n * 16) = v;
+                        }
                     }
                 }
             }
@@ -341,7 +361,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                     for (int e = 0; e < 32; e++)
                         m = fmaxf(m, fmaf(fmaxf(__uint_as_float(r[e]) + bias, 0.f), sc, sh));
                     const int64_t t = t0 + tt;
-                    if (t < p.n_tgt && co < p.Co) p.out[t * p.Co + co] = s_valid[tt] ? m : 0.f;
+                    if (t < p.n_tgt && co < p.Co) {
+                        const float v = s_valid[tt] ? m : 0.f;
+                        if (p.out_bf16) static_cast<__nv_bfloat16 *>(p.out)[t * p.Co + co] = __float2bfloat16(v);
+                        else static_cast<float *>(p.out)[t * p.Co + co] = v;
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[acc]);
@@ -407,10 +431,11 @@ using namespace p2w;
 
 size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out) { return tc_plan(c_in, hidden, c_out).total; }
 
-int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
+int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
                        int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out, const float *w1,
                        const float *b1, const float *w2, const float *b2, const float *bn_scale,
-                       const float *bn_shift, float *out, void *ws, size_t ws_bytes, cudaStream_t st) {
+                       const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
+                       bool packed) {
     (void)n_src;
     P2W_REQUIRE(c_in % 8 == 0 && c_in >= 8, "p2w_pointnet_conv_max(bf16): c_in=%d must be a multiple of 8", c_in);
     P2W_REQUIRE(hidden % SLICE_K == 0, "p2w_pointnet_conv_max(bf16): hidden=%d must be a multiple of 32", hidden);
@@ -429,7 +454,7 @@ int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tg
     float *b2p = reinterpret_cast<float *>(base + t.off_b2);
     float *scp = reinterpret_cast<float *>(base + t.off_scale);
     float *shp = reinterpret_cast<float *>(base + t.off_shift);
-    {
+    if (!packed) {
         const int64_t n1 = static_cast<int64_t>(t.NB1) * t.K1p * 128, n2 = static_cast<int64_t>(t.NB2) * hidden * 128;
         P2W_LAUNCH(prepack_kernel, (unsigned)((n1 + 255) / 256), 256, 0, st)(w1, hidden, c_in + 4, t.NB1, t.K1p, w1p);
         P2W_LAUNCH(prepack_kernel, (unsigned)((n2 + 255) / 256), 256, 0, st)(w2, c_out, hidden, t.NB2, hidden, w2p);
@@ -439,6 +464,7 @@ int p2w_conv_tc_launch(const float *x, const float *pos_src, const float *pos_tg
         P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(bn_shift, c_out, t.NB2 * 128, shp);
     }
     ConvTcParams p;
+    p.x_bf16 = x_bf16; p.out_bf16 = out_bf16;
     p.x = x; p.pos_src = pos_src; p.pos_tgt = pos_tgt; p.nbr = nbr;
     p.n_tgt = n_tgt; p.K = k; p.C = c_in; p.H = hidden; p.Co = c_out;
     p.K1p = t.K1p; p.NB1 = t.NB1; p.NB2 = t.NB2;

@@ -1,0 +1,92 @@
+// dense.cu -- per-channel affine + ReLU epilogues between the dense per-point GEMMs of
+// InvertedResidualBlock (src/model.py:18-85).  In eval mode every BatchNorm1d that follows a
+// k=1 convolution folds into the convolution's weights; what is left between two GEMMs is
+//     depthwise(k=1) -> BN -> ReLU                       y = relu(x * s1 + t1)
+//     BN -> ReLU -> depthwise(k=1) -> BN -> ReLU         y = relu(relu(x * s1 + t1) * s2 + t2)
+// on [N, 4C] activations.  These are HBM-bound streaming kernels: one pass, 16-byte accesses,
+// FP32 or BF16 activations, FP32 per-channel constants.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace p2w {
+namespace {
+
+template <bool TWO>
+__device__ __forceinline__ float chain(float v, float s1, float t1, float s2, float t2) {
+    v = fmaxf(fmaf(v, s1, t1), 0.f);
+    if (TWO) v = fmaxf(fmaf(v, s2, t2), 0.f);
+    return v;
+}
+
+// one thread = 8 consecutive channels of one row
+template <bool TWO, bool BF16>
+__global__ void __launch_bounds__(256) affine_relu_kernel(const void *__restrict__ xin, void *__restrict__ yout,
+                                                          int64_t n, int c, const float *__restrict__ s1,
+                                                          const float *__restrict__ t1, const float *__restrict__ s2,
+                                                          const float *__restrict__ t2) {
+    const int c8 = c >> 3;
+    const int64_t total = n * c8;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % c8) * 8;
+        float a1[8], b1[8], a2[8], b2[8];
+        *reinterpret_cast<float4 *>(a1) = __ldg(reinterpret_cast<const float4 *>(s1 + ch));
+        *reinterpret_cast<float4 *>(a1 + 4) = __ldg(reinterpret_cast<const float4 *>(s1 + ch + 4));
+        *reinterpret_cast<float4 *>(b1) = __ldg(reinterpret_cast<const float4 *>(t1 + ch));
+        *reinterpret_cast<float4 *>(b1 + 4) = __ldg(reinterpret_cast<const float4 *>(t1 + ch + 4));
+        if (TWO) {
+            *reinterpret_cast<float4 *>(a2) = __ldg(reinterpret_cast<const float4 *>(s2 + ch));
+            *reinterpret_cast<float4 *>(a2 + 4) = __ldg(reinterpret_cast<const float4 *>(s2 + ch + 4));
+            *reinterpret_cast<float4 *>(b2) = __ldg(reinterpret_cast<const float4 *>(t2 + ch));
+            *reinterpret_cast<float4 *>(b2 + 4) = __ldg(reinterpret_cast<const float4 *>(t2 + ch + 4));
+        }
+        if (BF16) {
+            uint4 raw = reinterpret_cast<const uint4 *>(xin)[i];
+            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&raw);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float2 f = __bfloat1622float2(h[u]);
+                f.x = chain<TWO>(f.x, a1[2 * u], b1[2 * u], a2[2 * u], b2[2 * u]);
+                f.y = chain<TWO>(f.y, a1[2 * u + 1], b1[2 * u + 1], a2[2 * u + 1], b2[2 * u + 1]);
+                h[u] = __floats2bfloat162_rn(f.x, f.y);
+            }
+            reinterpret_cast<uint4 *>(yout)[i] = raw;
+        } else {
+            float v[8];
+            *reinterpret_cast<float4 *>(v) = reinterpret_cast<const float4 *>(xin)[2 * i];
+            *reinterpret_cast<float4 *>(v + 4) = reinterpret_cast<const float4 *>(xin)[2 * i + 1];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = chain<TWO>(v[u], a1[u], b1[u], a2[u], b2[u]);
+            reinterpret_cast<float4 *>(yout)[2 * i] = *reinterpret_cast<float4 *>(v);
+            reinterpret_cast<float4 *>(yout)[2 * i + 1] = *reinterpret_cast<float4 *>(v + 4);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace p2w
+
+using namespace p2w;
+
+extern "C" int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, const float *s1, const float *t1,
+                               const float *s2, const float *t2, int32_t dtype, p2w_stream_t stream) {
+    P2W_REQUIRE(c >= 8 && c % 8 == 0, "p2w_affine_relu: c=%d must be a multiple of 8", c);
+    P2W_REQUIRE(dtype == P2W_F32 || dtype == P2W_BF16, "p2w_affine_relu: unknown dtype %d", dtype);
+    P2W_REQUIRE((s2 == nullptr) == (t2 == nullptr), "p2w_affine_relu: s2 and t2 go together");
+    P2W_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(s1) |
+                  reinterpret_cast<uintptr_t>(t1) | reinterpret_cast<uintptr_t>(s2) | reinterpret_cast<uintptr_t>(t2)) &
+                 15u) == 0,
+                "p2w_affine_relu: pointers must be 16-byte aligned");
+    if (n == 0) return P2W_OK;
+    cudaStream_t st = as_stream(stream);
+    const int64_t total = n * (c >> 3);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const bool two = s2 != nullptr, bf = dtype == P2W_BF16;
+    if (two && bf) P2W_LAUNCH((affine_relu_kernel<true, true>), (unsigned)blocks, 256, 0, st)(x, y, n, c, s1, t1, s2, t2);
+    else if (two) P2W_LAUNCH((affine_relu_kernel<true, false>), (unsigned)blocks, 256, 0, st)(x, y, n, c, s1, t1, s2, t2);
+    else if (bf) P2W_LAUNCH((affine_relu_kernel<false, true>), (unsigned)blocks, 256, 0, st)(x, y, n, c, s1, t1, s2, t2);
+    else P2W_LAUNCH((affine_relu_kernel<false, false>), (unsigned)blocks, 256, 0, st)(x, y, n, c, s1, t1, s2, t2);
+    return check_launch("p2w_affine_relu");
+}

@@ -74,6 +74,75 @@ __global__ void __launch_bounds__(256) grid_kernel(const float *__restrict__ pos
     ids[i] = c;
 }
 
+
+// ------------------------------------------------------------------ grouped voxel keys (super-batches)
+// Several reference batches ("groups" of consecutive tiles) travel through one launch.  The reference
+// voxelises every batch on its own grid: start/end are the column min/max over the points of THAT batch
+// (torch_geometric.nn.voxel_grid), so the origin is per group.
+// One CTA per group reduces its points' xyz extent.
+__global__ void __launch_bounds__(512) group_minmax_kernel(const float *__restrict__ pos, int ld,
+                                                           const int64_t *__restrict__ tile_ptr,
+                                                           const int64_t *__restrict__ group_ptr,
+                                                           float *__restrict__ gmn, float *__restrict__ gmx) {
+    __shared__ float s_lo[16][3], s_hi[16][3];
+    const int g = blockIdx.x;
+    const int64_t lo_i = tile_ptr[group_ptr[g]], hi_i = tile_ptr[group_ptr[g + 1]];
+    float lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { lo[d] = __int_as_float(0x7f800000); hi[d] = __int_as_float(0xff800000); }
+    for (int64_t i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const float v = pos[i * ld + d];
+            lo[d] = fminf(lo[d], v);
+            hi[d] = fmaxf(hi[d], v);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        for (int o = 16; o; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(FULL, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(FULL, hi[d], o));
+        }
+        if (lane == 0) { s_lo[warp][d] = lo[d]; s_hi[warp][d] = hi[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        float a = s_lo[0][d], b = s_hi[0][d];
+        for (int w = 1; w < 16; w++) { a = fminf(a, s_lo[w][d]); b = fmaxf(b, s_hi[w][d]); }
+        gmn[g * 3 + d] = a;
+        gmx[g * 3 + d] = b;
+    }
+}
+
+// key = (tile << spatial_bits) | spatial id on the group's grid.  Inside one group this orders points
+// exactly like the reference's batch-major id (spatial + local_tile * cells); across groups it is
+// tile-major.  *overflow is raised when a spatial id does not fit spatial_bits.
+__global__ void __launch_bounds__(256) grid_grouped_kernel(const float *__restrict__ pos, int64_t n, int ld,
+                                                           const int64_t *__restrict__ tile_ptr, int num_tiles,
+                                                           const int64_t *__restrict__ group_ptr, int num_groups,
+                                                           const float *__restrict__ gmn,
+                                                           const float *__restrict__ gmx, float size,
+                                                           int spatial_bits, uint64_t *__restrict__ keys,
+                                                           int32_t *__restrict__ overflow) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = find_tile(tile_ptr, num_tiles, i);
+    const int g = find_tile(group_ptr, num_groups, t);
+    int64_t c = 0, k = 1;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float s = gmn[g * 3 + d];
+        const float p = __fsub_rn(pos[i * ld + d], s);
+        c += static_cast<int64_t>(__fdiv_rn(p, size)) * k;
+        k *= static_cast<int64_t>(__fdiv_rn(__fsub_rn(gmx[g * 3 + d], s), size)) + 1;
+    }
+    if (c >> spatial_bits) atomicExch(overflow, 1);
+    keys[i] = (static_cast<uint64_t>(t) << spatial_bits) | static_cast<uint64_t>(c);
+}
+
 // ------------------------------------------------------------------ multi-block exclusive scan (int64)
 constexpr int SCAN_T = 256, SCAN_V = 8, SCAN_TILE = SCAN_T * SCAN_V;
 
@@ -305,6 +374,23 @@ extern "C" int p2w_grid(const float *pos, int64_t n, int32_t dim, int32_t ld, co
     if (n == 0) return P2W_OK;
     P2W_LAUNCH(grid_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream))(pos, n, dim, ld, batch, size, start, end, ids);
     return check_launch("p2w_grid");
+}
+
+extern "C" int p2w_voxel_keys_grouped(const float *pos, int64_t n, int32_t ld, const int64_t *tile_ptr,
+                                      int32_t num_tiles, const int64_t *group_ptr, int32_t num_groups, float size,
+                                      int32_t spatial_bits, float *group_min, float *group_max, uint64_t *keys,
+                                      int32_t *overflow, p2w_stream_t stream) {
+    P2W_REQUIRE(ld >= 3 && num_tiles >= 1 && num_groups >= 1, "p2w_voxel_keys_grouped: bad sizes");
+    P2W_REQUIRE(spatial_bits >= 1 && spatial_bits <= 48, "p2w_voxel_keys_grouped: spatial_bits=%d", spatial_bits);
+    P2W_REQUIRE(size > 0.f, "p2w_voxel_keys_grouped: size must be positive");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
+    if (n == 0) return check_launch("p2w_voxel_keys_grouped");
+    P2W_LAUNCH(group_minmax_kernel, num_groups, 512, 0, st)(pos, ld, tile_ptr, group_ptr, group_min, group_max);
+    P2W_LAUNCH(grid_grouped_kernel, (unsigned)((n + 255) / 256), 256, 0, st)(pos, n, ld, tile_ptr, num_tiles, group_ptr,
+                                                                             num_groups, group_min, group_max, size,
+                                                                             spatial_bits, keys, overflow);
+    return check_launch("p2w_voxel_keys_grouped");
 }
 
 extern "C" size_t p2w_sort_ws_bytes(int64_t n) {

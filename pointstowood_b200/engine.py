@@ -1,0 +1,194 @@
+"""Eval-mode executor for pointstowood_b200.model.Net: the same arithmetic as Net.forward
+(/root/reference/pointstowood/src/model.py:226-245) re-scheduled for B200.
+
+* SUPER-BATCHES.  The reference runs `batch_size` (8) tiles per forward (src/predicter.py:177-199):
+  ~13 k points per launch set on a TLS plot, which leaves a B200 launch-bound.  Every op on the
+  path is per tile or per point except the voxel sub-sampling, whose grid origin is the min over one
+  batch.  `group_ptr` keeps that origin per reference batch, so any number
+  of batches travels through one set of launches with unchanged results.
+* FOLDED BATCHNORM.  In eval mode a BatchNorm1d after a k=1 convolution / Linear folds into its
+  weights; `Linear -> ReLU -> BN` (MLP, src/model.py:198-202) leaves a per-channel affine AFTER the
+  ReLU, which is folded FORWARD into the next Linear -- through knn_interpolate too, whose weights
+  sum to one (src/model.py:149).  What cannot fold (depthwise -> BN -> ReLU chains inside
+  InvertedResidualBlock, src/model.py:18-85) runs as one fused streaming kernel (p2w_affine_relu).
+  Folding is done in FP64 once per (weights, dtype).
+* DTYPE.  fp32 (parity mode, 1e-3) or bf16 activations / weights with FP32 accumulation (1e-2).
+  Dense GEMMs are library calls (cuBLASLt bias+ReLU epilogues through torch), as SURVEY.md §2 row 8
+  scopes them; the hot path -- sampling, radius / kNN, fused PointNetConv, interpolation, pooling
+  -- is libp2w.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+
+__all__ = ["InferenceEngine"]
+
+
+def _affine(bn: nn.BatchNorm1d):
+    s = bn.weight.double() * torch.rsqrt(bn.running_var.double() + bn.eps)
+    return s, bn.bias.double() - bn.running_mean.double() * s
+
+
+class _Lin:
+    """y = act(x @ Wt + b) with everything foldable already inside Wt / b."""
+
+    def __init__(self, w: Tensor, b: Tensor, dtype, relu: bool, s_in=None, t_in=None, s_out=None, t_out=None,
+                 pad_in: int = 0):
+        w, b = w.double(), b.double()
+        if w.dim() == 3:
+            w = w.squeeze(-1)
+        if s_in is not None:                     # input was (x*s_in + t_in) on its leading len(s_in) columns
+            k = s_in.numel()
+            b = b + w[:, :k] @ t_in
+            w = torch.cat([w[:, :k] * s_in[None, :], w[:, k:]], dim=1)
+        if s_out is not None:
+            w = w * s_out[:, None]
+            b = b * s_out + t_out
+        if pad_in:
+            w = torch.cat([w, w.new_zeros(w.size(0), pad_in)], dim=1)
+        self.wt = w.t().contiguous().to(dtype)
+        self.b = b.to(dtype).contiguous()
+        self.relu = relu
+
+    def __call__(self, x: Tensor) -> Tensor:
+        if self.relu:
+            return torch._addmm_activation(self.b, x, self.wt, use_gelu=False)
+        return torch.addmm(self.b, x, self.wt)
+
+
+class _Residual:
+    """InvertedResidualBlock (src/model.py:46-85), shortcut = identity (in == out channels)."""
+
+    def __init__(self, blk, dtype):
+        assert len(blk.shortcut) == 0, "the reference builds InvertedResidualBlock(C, C)"
+        f32 = lambda t: t.float().contiguous()
+        self.expand = _Lin(blk.expand[0].weight, blk.expand[0].bias, dtype, True, None, None, *_affine(blk.expand[1]))
+        ds0, ds3 = blk.conv[0], blk.conv[3]
+
+        def dw(ds):        # depthwise(k=1) -> BN : one per-channel affine
+            s, t = _affine(ds.depthwise_bn)
+            return ds.depthwise_conv.weight.double().view(-1) * s, ds.depthwise_conv.bias.double() * s + t
+
+        a0, c0 = dw(ds0)
+        self.a0, self.c0 = f32(a0), f32(c0)
+        self.pw0 = _Lin(ds0.pointwise_conv.weight, ds0.pointwise_conv.bias, dtype, True, None, None,
+                        *_affine(ds0.pointwise_bn))
+        s1, t1 = _affine(blk.conv[1])
+        a3, c3 = dw(ds3)
+        self.s1, self.t1, self.a3, self.c3 = f32(s1), f32(t1), f32(a3), f32(c3)
+        self.pw3 = _Lin(ds3.pointwise_conv.weight, ds3.pointwise_conv.bias, dtype, True, None, None,
+                        *_affine(ds3.pointwise_bn))
+        s4, t4 = _affine(blk.conv[4])
+        self.project = _Lin(blk.project[0].weight, blk.project[0].bias, dtype, False, s4, t4, *_affine(blk.project[1]))
+
+    def __call__(self, x: Tensor) -> Tensor:
+        h = self.expand(x)
+        h = self.pw0(ops.affine_relu_(h, self.a0, self.c0))
+        h = self.pw3(ops.affine_relu_(h, self.s1, self.t1, self.a3, self.c3))
+        h = self.project(h)
+        return torch.relu_(h.add_(x))
+
+
+class InferenceEngine:
+    def __init__(self, net: nn.Module, dtype=torch.float32, conv_mode: Optional[int] = None):
+        assert dtype in (torch.float32, torch.bfloat16)
+        self.dtype = dtype
+        self.conv_mode = conv_mode if conv_mode is not None else (
+            ops.CONV_BF16_TC if dtype == torch.bfloat16 else ops.CONV_FP32)
+        if dtype == torch.bfloat16 and self.conv_mode != ops.CONV_BF16_TC:
+            raise ValueError("bf16 activations need the tensor-core PointNetConv")
+        self.fold(net)
+
+    # ------------------------------------------------------------------ folding (once per weights)
+    @torch.no_grad()
+    def fold(self, net: nn.Module) -> None:
+        dt = self.dtype
+        dev = next(net.parameters()).device
+        f32 = lambda t: t.float().contiguous()
+        stem = net.stem_mlp[0][0]
+        self.stem = _Lin(stem.weight, stem.bias, torch.float32, True)
+        self.sa = []
+        for mod in (net.sa1_module, net.sa2_module, net.sa3_module):
+            lin1, lin2, bn = mod.conv.local_nn[0][0], mod.conv.local_nn[1][0], mod.conv.local_nn[1][2]
+            s, t = _affine(bn)
+            w = [f32(lin1.weight), f32(lin1.bias), f32(lin2.weight), f32(lin2.bias), f32(s), f32(t)]
+            H, K1 = lin1.weight.shape
+            self.sa.append(dict(res=mod.resolution, k=mod.k, w=w, packed=False,
+                                ws=ops.pointnet_conv_ws(K1 - 4, H, lin2.weight.size(0), self.conv_mode, dev),
+                                residual=_Residual(mod.residual_block, dt)))
+        g = net.sa4_module.NN
+        k_in = g[0][0].weight.size(1)                                  # 515 = 512 features + xyz
+        self.g_pad = (-k_in) % 8
+        self.g1 = _Lin(g[0][0].weight, g[0][0].bias, dt, True, pad_in=self.g_pad)
+        self.g2 = _Lin(g[1][0].weight, g[1][0].bias, dt, True)
+        gs, gt = _affine(g[1][2])
+        self.g_s, self.g_t = f32(gs), f32(gt)
+        # FP modules: the trailing BN affine of each MLP is folded into the consumer of its output
+        self.fp = []
+        pend = None                                                    # (s, t) owed by the previous MLP's output
+        for mod in (net.fp4_module, net.fp3_module, net.fp2_module, net.fp1_module):
+            nn_ = mod.NN
+            l1 = _Lin(nn_[0][0].weight, nn_[0][0].bias, dt, True, *(pend if pend else (None, None)))
+            l2 = _Lin(nn_[1][0].weight, nn_[1][0].bias, dt, True)
+            self.fp.append(dict(k=mod.k, l1=l1, l2=l2))
+            pend = _affine(nn_[1][2])
+        self.head1 = _Lin(net.conv1.weight, net.conv1.bias, dt, True, pend[0], pend[1], *_affine(net.norm))
+        self.head2 = _Lin(net.conv2.weight, net.conv2.bias, dt, False)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def __call__(self, pos: Tensor, reflectance: Tensor, batch: Tensor, sf: Tensor, ptr: Optional[Tensor] = None,
+                 group_ptr: Optional[Tensor] = None) -> Tensor:
+        """pos [N,3] (tile-mean-shifted), reflectance [N], batch [N] int64 sorted, sf [T]; ptr [T+1] CSR of
+        the tiles; group_ptr [G+1] CSR of the reference batches over tiles (None: one batch).
+        Returns logits [N] fp32."""
+        dt = self.dtype
+        T = sf.numel()
+        pos = pos[:, :3].contiguous()
+        if ptr is None:
+            ptr = ops.batch_to_ptr(batch, T)
+        if group_ptr is None:
+            group_ptr = torch.tensor([0, T], device=pos.device, dtype=torch.int64)
+        x = self.stem(pos)                                             # [N0,32] fp32
+        skips = [(x, pos, ptr)]
+        refl = reflectance
+        for lvl in self.sa:
+            idx = ops.voxel_sample(pos, lvl["res"], batch, ptr=ptr, group_ptr=group_ptr)
+            batch_t = batch[idx]
+            ptr_t = ops.batch_to_ptr(batch_t, T)
+            if lvl["res"] == 0.04:                                     # src/model.py:117-118
+                nbr, _ = ops.radius_table(pos, pos[idx], lvl["res"] * 2, ptr, ptr_t, lvl["k"])
+            else:
+                nbr = ops.knn_table(pos, pos[idx], lvl["k"], ptr, ptr_t)
+            pos4, back = ops.sa_prepare(pos, refl, ptr, sf)
+            h = ops.pointnet_conv_max(x, pos4, pos4[idx], nbr, *lvl["w"], mode=self.conv_mode, ws=lvl["ws"],
+                                      packed=lvl["packed"], out_dtype=dt)
+            lvl["packed"] = lvl["packed"] or idx.numel() > 0          # an empty call returns before packing
+            x = lvl["residual"](h)
+            pos, batch, refl, ptr = back[idx], batch_t, refl[idx], ptr_t
+            skips.append((x, pos, ptr))
+        # ---- GlobalSAModule (src/model.py:134-140)
+        n3 = x.size(0)
+        buf = torch.zeros((n3, x.size(1) + 3 + self.g_pad), device=x.device, dtype=dt)
+        buf[:, : x.size(1)] = x
+        buf[:, x.size(1): x.size(1) + 3] = pos
+        h = self.g2(self.g1(buf)).float()
+        h = h * self.g_s + self.g_t
+        x = ops.global_max_pool(h, batch, ptr=ptr)                     # [T,512] fp32
+        pos_c = pos.new_zeros((T, 3))
+        ptr_c = torch.arange(T + 1, device=pos.device, dtype=torch.int64)
+        # ---- FPModules (src/model.py:148-153), coarse -> fine
+        for fp, (x_skip, pos_skip, ptr_skip) in zip(self.fp, reversed(skips)):
+            c, cs = x.size(1), x_skip.size(1)
+            buf = torch.empty((pos_skip.size(0), c + cs), device=x.device, dtype=dt)
+            ops.knn_interpolate(x, pos_c, pos_skip, k=fp["k"], ptr_x=ptr_c, ptr_y=ptr_skip, out=buf)
+            buf[:, c:] = x_skip
+            x = fp["l2"](fp["l1"](buf))
+            pos_c, ptr_c = pos_skip, ptr_skip
+        x = self.head2(self.head1(x))
+        return x.reshape(-1).float()

@@ -243,14 +243,41 @@ class Net(nn.Module):
         self.conv2 = nn.Conv1d(C * 16, num_classes, 1)
         self.norm = nn.BatchNorm1d(C * 16)
         initialize_weights(self)
+        self.conv_mode = conv_mode
+        self.inference_dtype = torch.float32
+        self.use_engine = True          # eval mode runs through engine.InferenceEngine (folded BN, super-batches)
+        self._engine = None
 
     def set_conv_mode(self, mode: int) -> "Net":
         for m in self.modules():
             if isinstance(m, PointNetConv):
                 m.conv_mode = mode
+        self.conv_mode = mode
         return self
 
+    def set_precision(self, precision: str) -> "Net":
+        """'fp32': FP32 everywhere (parity mode, |dp| <= 1e-3).  'bf16': bf16 activations / weights with FP32
+        accumulation, PointNetConv on tcgen05 (|dp| <= 1e-2).  'bf16-conv': only the PointNetConv in bf16."""
+        if precision not in ("fp32", "bf16", "bf16-conv"):
+            raise ValueError(precision)
+        self.set_conv_mode(ops.CONV_FP32 if precision == "fp32" else ops.CONV_BF16_TC)
+        self.inference_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        return self
+
+    def engine(self):
+        """The eval-mode executor for the current weights / precision (re-folded when either changes)."""
+        from .engine import InferenceEngine
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = (self.inference_dtype, self.conv_mode, tensors[0].device, sum(t._version for t in tensors),
+               tuple(t.data_ptr() for t in tensors[:4]))
+        if self._engine is None or self._engine[0] != key:
+            self._engine = (key, InferenceEngine(self, self.inference_dtype, self.conv_mode))
+        return self._engine[1]
+
     def forward(self, data):
+        if not self.training and self.use_engine:
+            return self.engine()(data.pos, data.reflectance, data.batch, data.sf, getattr(data, "ptr", None),
+                                 getattr(data, "group_ptr", None))
         B = data.sf.numel()
         pos = data.pos[:, :3].contiguous()
         data.x = self.stem_mlp(pos)

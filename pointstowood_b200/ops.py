@@ -27,7 +27,7 @@ __all__ = [
     "batch_to_ptr", "knn", "radius", "fps", "grid_cluster", "voxel_grid", "consecutive_cluster",
     "knn_interpolate", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
     "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback",
-    "sort_pairs", "CONV_FP32", "CONV_BF16_TC",
+    "sort_pairs", "affine_relu_", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
 ]
 
 CONV_FP32 = 0
@@ -297,9 +297,17 @@ def consecutive_cluster(src: Tensor) -> Tuple[Tensor, Tensor]:
     return inv, perm[: int(cnt.item())]
 
 
-def voxel_sample(pos: Tensor, size: float, batch: Tensor, key_bits: int = 40) -> Tensor:
+def voxel_sample(pos: Tensor, size: float, batch: Optional[Tensor], key_bits: int = 40, ptr: Optional[Tensor] = None,
+                 group_ptr: Optional[Tensor] = None, spatial_bits: int = 24) -> Tensor:
     """SAModule.voxelsample (src/model.py:103-106): one representative row per occupied voxel,
-    voxels ascending by id (batch-major).  One host sync (the number of voxels)."""
+    voxels ascending by id (batch-major).  One host sync (the number of voxels).
+
+    With `ptr` (CSR of tiles over rows) and `group_ptr` (CSR of reference batches over tiles) the
+    rows of SEVERAL reference batches are sampled in one pass, each batch on its own grid origin
+    (the reference's voxel_grid takes start/end over one batch), which is what lets the predicter
+    run many batches of `batch_size` tiles per launch with unchanged results."""
+    if group_ptr is not None:
+        return _voxel_sample_grouped(pos, size, ptr, group_ptr, spatial_bits)
     ids = _voxel_ids(pos, size, batch)
     if ids.numel() == 0:
         return ids
@@ -312,6 +320,32 @@ def voxel_sample(pos: Tensor, size: float, batch: Tensor, key_bits: int = 40) ->
         perm, _, cnt = _unique_last(keys, idx, False)
         n_unique = int(cnt.item())
     return perm[:n_unique]
+
+
+def _voxel_sample_grouped(pos: Tensor, size: float, ptr: Tensor, group_ptr: Tensor, spatial_bits: int) -> Tensor:
+    pos = _req(pos, torch.float32, "pos", 2)
+    ptr, group_ptr = _req(ptr, torch.int64, "ptr", 1), _req(group_ptr, torch.int64, "group_ptr", 1)
+    n, T, G = pos.size(0), ptr.numel() - 1, group_ptr.numel() - 1
+    dev = pos.device
+    if n == 0:
+        return torch.empty(0, device=dev, dtype=torch.int64)
+    L = _lib.lib()
+    tile_bits = max(1, int(T - 1).bit_length())
+    gmn = torch.empty((G, 3), device=dev, dtype=torch.float32)
+    gmx = torch.empty((G, 3), device=dev, dtype=torch.float32)
+    keys = torch.empty(n, device=dev, dtype=torch.int64)
+    flag = torch.empty(1, device=dev, dtype=torch.int32)        # raised when an id needs > spatial_bits bits
+    while True:
+        _lib.check(L.p2w_voxel_keys_grouped(_dp(pos), n, pos.stride(0), _dp(ptr), T, _dp(group_ptr), G, float(size),
+                                            spatial_bits, _dp(gmn), _dp(gmx), _dp(keys), _dp(flag), _stream()))
+        skeys, idx = sort_pairs(keys, spatial_bits + tile_bits)
+        perm, _, cnt = _unique_last(skeys, idx, False)
+        over, n_unique = torch.cat([flag.to(torch.int64), cnt]).tolist()
+        if not over:
+            return perm[:n_unique]
+        if spatial_bits >= 48:
+            raise _lib.P2WError("voxel_sample: the voxel grid of one batch has more than 2^48 cells")
+        spatial_bits = 48                              # rare: a batch wider than 2^24 voxels
 
 
 # --------------------------------------------------------------------------- reductions
@@ -362,24 +396,43 @@ def knn_interpolate(x: Tensor, pos_x: Tensor, pos_y: Tensor, batch_x: Optional[T
                     ptr_x: Optional[Tensor] = None, ptr_y: Optional[Tensor] = None,
                     out: Optional[Tensor] = None) -> Tensor:
     """torch_geometric.nn.knn_interpolate (src/model.py:149).  `out` may be a wider
-    [Ny, >=C] buffer whose leading C columns are filled (fuses the skip concatenation)."""
-    x = _req(x, torch.float32, "x", 2)
+    [Ny, >=C] buffer whose leading C columns are filled (fuses the skip concatenation); x and
+    out may be float32 or bfloat16 (weights and positions are always FP32)."""
+    if x.dtype not in _DT:
+        raise _lib.P2WError("knn_interpolate: x must be float32 or bfloat16")
+    x = _req(x, x.dtype, "x", 2)
     pos_x, pos_y = _req(pos_x, torch.float32, "pos_x", 2), _req(pos_y, torch.float32, "pos_y", 2)
     if ptr_x is None:
         ptr_x, ptr_y, _ = _ptrs(pos_x, pos_y, batch_x, batch_y, None)
     nbr = knn_table(pos_x, pos_y, k, ptr_x, ptr_y)
     if out is None:
-        out = torch.empty((pos_y.size(0), x.size(1)), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().p2w_knn_interpolate(_dp(x), _dp(pos_x), _dp(pos_y), _dp(nbr), pos_y.size(0), k, x.size(1),
-                                              out.stride(0), _dp(out), _stream()))
+        out = torch.empty((pos_y.size(0), x.size(1)), device=x.device, dtype=x.dtype)
+    if out.dtype not in _DT or out.stride(1) != 1:
+        raise _lib.P2WError("knn_interpolate: out must be a row-major float32 / bfloat16 buffer")
+    _lib.check(_lib.lib().p2w_knn_interpolate_ex(_dp(x), _DT[x.dtype], _dp(pos_x), _dp(pos_y), _dp(nbr), pos_y.size(0), k,
+                                                 x.size(1), out.stride(0), _dp(out), _DT[out.dtype], _stream()))
     return out
 
 
 # --------------------------------------------------------------------------- fused conv and glue
+def pointnet_conv_ws(c_in: int, hidden: int, c_out: int, mode: int, device) -> Tensor:
+    """Workspace that receives the re-laid-out weights of one PointNetConv (reusable across calls)."""
+    nbytes = int(_lib.lib().p2w_pointnet_conv_ws_bytes(c_in, hidden, c_out, mode))
+    return torch.empty(nbytes, device=device, dtype=torch.uint8)
+
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}       # P2W_F32 / P2W_BF16
+
+
 def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, w1: Tensor, b1: Tensor, w2: Tensor,
-                      b2: Tensor, bn_scale: Tensor, bn_shift: Tensor, mode: int = CONV_FP32) -> Tensor:
-    """Fused PointNetConv.message + local_nn + max aggregation (src/pointnet.py:108-132)."""
-    x = _req(x, torch.float32, "x", 2)
+                      b2: Tensor, bn_scale: Tensor, bn_shift: Tensor, mode: int = CONV_FP32,
+                      ws: Optional[Tensor] = None, packed: bool = False, out_dtype=torch.float32) -> Tensor:
+    """Fused PointNetConv.message + local_nn + max aggregation (src/pointnet.py:108-132).
+    `ws` (from pointnet_conv_ws) with packed=True re-uses the weights laid out by an earlier call.
+    In the tensor-core mode x may be bf16 and `out_dtype` may be torch.bfloat16."""
+    if x.dtype not in _DT or out_dtype not in _DT:
+        raise _lib.P2WError("pointnet_conv_max: feature rows must be float32 or bfloat16")
+    x = _req(x, x.dtype, "x", 2)
     pos_src, pos_tgt = _req(pos_src, torch.float32, "pos_src", 2), _req(pos_tgt, torch.float32, "pos_tgt", 2)
     nbr = _req(nbr, torch.int32, "nbr", 2)
     if pos_src.size(1) != 4 or pos_tgt.size(1) != 4:
@@ -390,15 +443,31 @@ def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, 
     if K1 != C + 4 or w2.size(1) != H or nbr.size(0) != pos_tgt.size(0):
         raise _lib.P2WError("pointnet_conv_max: inconsistent shapes")
     L = _lib.lib()
-    nbytes = int(L.p2w_pointnet_conv_ws_bytes(C, H, Co, mode))
-    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
-    out = torch.empty((pos_tgt.size(0), Co), device=x.device, dtype=torch.float32)
+    if ws is None:
+        if packed:
+            raise _lib.P2WError("pointnet_conv_max: packed=True needs the workspace of the packing call")
+        ws = pointnet_conv_ws(C, H, Co, mode, x.device)
+    out = torch.empty((pos_tgt.size(0), Co), device=x.device, dtype=out_dtype)
     args = [_req(t, torch.float32, "weights") for t in (w1, b1, w2, b2, bn_scale, bn_shift)]
     flops = float(pos_tgt.size(0)) * 32.0 * (2.0 * (C + 4) * H + 2.0 * H * Co)
-    _lib.check(KERNEL_TIMER.call("p2w_pointnet_conv_max", flops, L.p2w_pointnet_conv_max, _dp(x), _dp(pos_src),
-                                 _dp(pos_tgt), _dp(nbr), x.size(0), pos_tgt.size(0), nbr.size(1), C, H, Co,
-                                 *[_dp(a) for a in args], _dp(out), mode, _dp(ws), nbytes, _stream()))
+    _lib.check(KERNEL_TIMER.call("p2w_pointnet_conv_max", flops, L.p2w_pointnet_conv_max_ex, _dp(x), _DT[x.dtype],
+                                 _dp(pos_src), _dp(pos_tgt), _dp(nbr), x.size(0), pos_tgt.size(0), nbr.size(1), C, H, Co,
+                                 *[_dp(a) for a in args], _dp(out), _DT[out_dtype], mode, _dp(ws), ws.numel(),
+                                 1 if packed else 0, _stream()))
     return out
+
+
+def affine_relu_(x: Tensor, s1: Tensor, t1: Tensor, s2: Optional[Tensor] = None, t2: Optional[Tensor] = None) -> Tensor:
+    """In place y = relu(x*s1 + t1) [then relu(y*s2 + t2)] per channel of [N, C] fp32 / bf16 rows: what is
+    left between two k=1 convolutions of InvertedResidualBlock (src/model.py:18-85) after BN folding."""
+    if x.dtype not in _DT:
+        raise _lib.P2WError("affine_relu_: rows must be float32 or bfloat16")
+    x = _req(x, x.dtype, "x", 2)
+    cs = [_req(t, torch.float32, "constants", 1) for t in (s1, t1)]
+    cs += [None, None] if s2 is None else [_req(t, torch.float32, "constants", 1) for t in (s2, t2)]
+    _lib.check(_lib.lib().p2w_affine_relu(_dp(x), _dp(x), x.size(0), x.size(1), *[_dp(c) for c in cs], _DT[x.dtype],
+                                          _stream()))
+    return x
 
 
 def sa_prepare(pos: Tensor, refl: Tensor, ptr: Tensor, sf: Tensor) -> Tuple[Tensor, Tensor]:

@@ -25,7 +25,7 @@ from . import model as M
 from . import ops
 from .preprocessing import TileStore
 
-__all__ = ["plan_batches", "shard_batches", "classify_tiles", "gather_rows", "SemanticSegmentation"]
+__all__ = ["plan_batches", "plan_launches", "shard_batches", "classify_tiles", "gather_rows", "SemanticSegmentation"]
 
 
 def plan_batches(num_tiles: int, batch_size: int) -> List[Tuple[int, int]]:
@@ -46,28 +46,49 @@ def shard_batches(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, world_siz
     return [i for i in range(len(batches)) if owner[i] == rank]
 
 
+def plan_launches(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, batch_ids: Sequence[int],
+                  max_points: int) -> List[List[int]]:
+    """Groups CONSECUTIVE reference batches into super-batches of at most `max_points` points (always
+    at least one batch): one set of kernel launches serves a whole group, each batch keeping its own
+    voxel-grid origin (engine.InferenceEngine)."""
+    out: List[List[int]] = []
+    cur: List[int] = []
+    pts = 0
+    for bi in batch_ids:
+        a, b = batches[bi]
+        n = int(ptr[b] - ptr[a])
+        if cur and (bi != cur[-1] + 1 or pts + n > max_points):
+            out.append(cur)
+            cur, pts = [], 0
+        cur.append(bi)
+        pts += n
+    if cur:
+        out.append(cur)
+    return out
+
+
 @torch.no_grad()
 def classify_tiles(net: torch.nn.Module, tiles: TileStore, batch_size: int = 8, is_wood: float = 0.5,
-                   batch_ids: Optional[Iterable[int]] = None, want_rows: bool = False, autocast_bf16: bool = False):
+                   batch_ids: Optional[Iterable[int]] = None, want_rows: bool = False,
+                   max_points_per_launch: int = 1 << 20):
     """Runs the network over the tiles.  Returns (prob float32 [M'], pred uint8 [M'], rows float64
-    [M',5] or None, row_offsets) on the device, in batch order; M' covers the selected batches."""
+    [M',5] or None, spans) on the device, in batch order; M' covers the selected batches.
+    Batches of `batch_size` tiles are the reference's unit (their composition fixes the voxel-grid
+    origin); up to `max_points_per_launch` points of consecutive batches share one launch set."""
     dev = tiles.feat.device
     batches = plan_batches(tiles.num_tiles, batch_size)
-    if batch_ids is None:
-        batch_ids = range(len(batches))
+    batch_ids = list(range(len(batches)) if batch_ids is None else batch_ids)
     ptr_dev = torch.as_tensor(tiles.ptr, device=dev)
     probs, preds, rows, spans = [], [], [], []
-    for bi in batch_ids:
-        t0, t1 = batches[bi]
+    for group in plan_launches(batches, tiles.ptr, batch_ids, max_points_per_launch):
+        t0, t1 = batches[group[0]][0], batches[group[-1]][1]
         lo, hi = int(tiles.ptr[t0]), int(tiles.ptr[t1])
         bptr = ptr_dev[t0: t1 + 1] - lo
+        gptr = torch.tensor([batches[b][0] - t0 for b in group] + [t1 - t0], device=dev, dtype=torch.int64)
         pos, refl, batch, shift, sf = ops.pack_tiles(tiles.feat, tiles.members[lo:hi], bptr)
-        data = M.make_data(pos, refl, batch, sf, local_shift=shift.reshape(-1), ptr=bptr)
-        if autocast_bf16:
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                logits = net(data)
-        else:
-            logits = net(data)
+        data = M.make_data(pos, refl, batch, sf, local_shift=shift.reshape(-1), ptr=bptr,
+                           group_ptr=gptr if len(group) > 1 else None)
+        logits = net(data)
         out = ops.writeback(logits.float().reshape(-1), pos, bptr, shift, is_wood, want_rows=want_rows)
         probs.append(out[0])
         preds.append(out[1])

@@ -83,3 +83,15 @@ def test_oracle_pipeline_invariants():
     # reflectance ranks are stable: equal inputs keep their order
     r = ref_pipeline.quantile_normalize_reflectance(np.array([3, 1, 1, 2, 1], np.float32))
     assert r[1] < r[2] < r[4] < r[3] < r[0]
+
+
+def test_plan_launches_groups_consecutive_batches_under_a_point_budget():
+    from pointstowood_b200.predicter import plan_batches, plan_launches
+    sizes = np.array([100] * 20)
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    batches = plan_batches(20, 8)                       # (0,8) (8,16) (16,20): 800, 800, 400 points
+    assert plan_launches(batches, ptr, [0, 1, 2], 1 << 30) == [[0, 1, 2]]
+    assert plan_launches(batches, ptr, [0, 1, 2], 1600) == [[0, 1], [2]]
+    assert plan_launches(batches, ptr, [0, 1, 2], 1) == [[0], [1], [2]]      # a batch is never split
+    assert plan_launches(batches, ptr, [0, 2], 1 << 30) == [[0], [2]]        # only consecutive batches merge
+    assert plan_launches(batches, ptr, [], 10) == []
