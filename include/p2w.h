@@ -60,6 +60,21 @@ int p2w_radius(const float *x, const float *y, const int64_t *ptr_x, const int64
                int32_t num_tiles, int64_t nx, int64_t ny, double r, int32_t max_nbr,
                int32_t *nbr, int32_t *cnt, p2w_stream_t stream);
 
+/* ---- K1 / K2 with a per-tile cell list ----------------------------------------------------
+ * Same contracts and bit-identical results as p2w_knn / p2w_radius, but every query examines only
+ * the cells of its tile's uniform grid that can hold a result (growing Chebyshev shells, exact
+ * stopping bound), i.e. a few hundred candidates instead of the whole tile.  The grid is built per
+ * call from the sources (bounding box + occupancy pyramid per tile, one radix sort) in `ws`
+ * (p2w_grid_search_ws_bytes(nx, num_tiles) bytes, 16-byte aligned).  Pays off from a few hundred
+ * sources per tile; the brute-force sweep remains the better choice for tiny tiles. */
+size_t p2w_grid_search_ws_bytes(int64_t nx, int32_t num_tiles);
+int p2w_knn_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
+                 int32_t num_tiles, int64_t nx, int64_t ny, int32_t k,
+                 int32_t *nbr, float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream);
+int p2w_radius_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
+                    int32_t num_tiles, int64_t nx, int64_t ny, double r, int32_t max_nbr,
+                    int32_t *nbr, int32_t *cnt, void *ws, size_t ws_bytes, p2w_stream_t stream);
+
 /* Compaction of a -1 padded [ny,k] table into upstream's [2,E] int64 edge list
  * (row 0 = query index, row 1 = source index, query-major).  edge_offset [ny+1] is a
  * caller workspace that receives the exclusive prefix sum of the per-query counts;

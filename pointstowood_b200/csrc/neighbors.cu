@@ -14,6 +14,7 @@
 // shuffle insertion only when it beats the current k-th entry lexicographically -- so the
 // result is independent of the scan order and bit-identical to the serial insertion sort.
 #include "common.cuh"
+#include "topk.cuh"
 
 namespace p2w {
 namespace {
@@ -21,49 +22,6 @@ namespace {
 constexpr int CH = 2048;   // sources per staged chunk (multiple of 4 keeps 16-byte alignment)
 constexpr int NW = 16;     // warps per CTA
 constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ bool key_less(float d, int i, float td, int ti) {
-    return d < td || (d == td && i < ti);
-}
-
-template <int S>
-struct TopK {
-    float d[S];
-    int i[S];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int s = 0; s < S; s++) { d[s] = 1e10f; i[s] = -1; }
-    }
-    // insert (cd, ci) keeping ascending (d, i) order; entry e lives in slot e/32, lane e%32
-    __device__ __forceinline__ void insert(float cd, int ci, int lane) {
-        int pos = 0;
-#pragma unroll
-        for (int s = 0; s < S; s++) pos += __popc(__ballot_sync(FULL, key_less(d[s], i[s], cd, ci)));
-#pragma unroll
-        for (int s = S - 1; s >= 0; s--) {
-            float ud = __shfl_up_sync(FULL, d[s], 1);
-            int ui = __shfl_up_sync(FULL, i[s], 1);
-            if (s > 0) {
-                float wd = __shfl_sync(FULL, d[s - 1], 31);
-                int wi = __shfl_sync(FULL, i[s - 1], 31);
-                if (lane == 0) { ud = wd; ui = wi; }
-            }
-            const int e = s * 32 + lane;
-            if (e == pos) { d[s] = cd; i[s] = ci; }
-            else if (e > pos) { d[s] = ud; i[s] = ui; }
-        }
-    }
-    __device__ __forceinline__ void kth(int k, float &td, int &ti) const {
-        const int e = k - 1;
-        float vd = d[0];
-        int vi = i[0];
-#pragma unroll
-        for (int s = 1; s < S; s++)
-            if ((e >> 5) == s) { vd = d[s]; vi = i[s]; }
-        td = __shfl_sync(FULL, vd, e & 31);
-        ti = __shfl_sync(FULL, vi, e & 31);
-    }
-};
 
 struct SweepSmem {
     float buf[2][CH * 3];

@@ -100,9 +100,26 @@ def _ptrs(x, y, batch_x, batch_y, batch_size):
 
 
 # --------------------------------------------------------------------------- neighbour tables
-def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return_d2: bool = False):
+GRID_MIN_SOURCES_PER_TILE = 192      # below this average the brute-force sweep wins (identical results)
+
+
+def _use_grid(method: Optional[str], nx: int, tiles: int) -> bool:
+    if method not in (None, "grid", "sweep"):
+        raise _lib.P2WError("method must be None, 'grid' or 'sweep'")
+    if method is None:
+        return nx >= GRID_MIN_SOURCES_PER_TILE * max(tiles, 1)
+    return method == "grid"
+
+
+def _grid_ws(nx: int, tiles: int, dev) -> Tensor:
+    return torch.empty(int(_lib.lib().p2w_grid_search_ws_bytes(nx, tiles)), device=dev, dtype=torch.uint8)
+
+
+def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return_d2: bool = False,
+              method: Optional[str] = None):
     """[Ny, k] int32 table of the k nearest x rows of every y row inside its tile, ordered by
-    (FP32 squared distance, index); -1 padded.  No host sync."""
+    (FP32 squared distance, index); -1 padded.  No host sync.  method: 'sweep' (tile-resident brute
+    force), 'grid' (per-tile cell list) or None (pick by sources per tile); same result either way."""
     x = _req(x, torch.float32, "x", 2)
     y = _req(y, torch.float32, "y", 2)
     if x.size(1) != 3 or y.size(1) != 3:
@@ -110,25 +127,40 @@ def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return
     ptr_x, ptr_y = _req(ptr_x, torch.int64, "ptr_x", 1), _req(ptr_y, torch.int64, "ptr_y", 1)
     if ptr_x.numel() != ptr_y.numel():
         raise _lib.P2WError("ptr_x and ptr_y must describe the same number of examples")
+    T = ptr_x.numel() - 1
     nbr = torch.empty((y.size(0), k), device=x.device, dtype=torch.int32)
     d2 = torch.empty((y.size(0), k), device=x.device, dtype=torch.float32) if return_d2 else None
     work = 12.0 * (x.size(0) + y.size(0)) + 16.0 * y.size(0) * k + 16.0 * ptr_x.numel()
-    _lib.check(KERNEL_TIMER.call("p2w_knn", work, _lib.lib().p2w_knn, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y),
-                                 ptr_x.numel() - 1, x.size(0), y.size(0), k, _dp(nbr), _dp(d2), _stream()))
+    L = _lib.lib()
+    if _use_grid(method, x.size(0), T):
+        ws = _grid_ws(x.size(0), T, x.device)
+        _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn_grid, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T,
+                                     x.size(0), y.size(0), k, _dp(nbr), _dp(d2), _dp(ws), ws.numel(), _stream()))
+    else:
+        _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T, x.size(0),
+                                     y.size(0), k, _dp(nbr), _dp(d2), _stream()))
     return (nbr, d2) if return_d2 else nbr
 
 
-def radius_table(x: Tensor, y: Tensor, r: float, ptr_x: Tensor, ptr_y: Tensor, max_num_neighbors: int = 32):
+def radius_table(x: Tensor, y: Tensor, r: float, ptr_x: Tensor, ptr_y: Tensor, max_num_neighbors: int = 32,
+                 method: Optional[str] = None):
     """([Ny, max] int32 -1 padded, cnt [Ny] int32): the lowest-index x rows with d2 < (float)(r*r)."""
     x = _req(x, torch.float32, "x", 2)
     y = _req(y, torch.float32, "y", 2)
     if x.size(1) != 3 or y.size(1) != 3:
         raise _lib.P2WError("radius: only 3-D coordinates are supported")
     ptr_x, ptr_y = _req(ptr_x, torch.int64, "ptr_x", 1), _req(ptr_y, torch.int64, "ptr_y", 1)
+    T = ptr_x.numel() - 1
     nbr = torch.empty((y.size(0), max_num_neighbors), device=x.device, dtype=torch.int32)
     cnt = torch.empty((y.size(0),), device=x.device, dtype=torch.int32)
-    _lib.check(_lib.lib().p2w_radius(_dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), ptr_x.numel() - 1, x.size(0),
-                                     y.size(0), float(r), max_num_neighbors, _dp(nbr), _dp(cnt), _stream()))
+    L = _lib.lib()
+    if _use_grid(method, x.size(0), T) and max_num_neighbors <= 128:
+        ws = _grid_ws(x.size(0), T, x.device)
+        _lib.check(L.p2w_radius_grid(_dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T, x.size(0), y.size(0), float(r),
+                                     max_num_neighbors, _dp(nbr), _dp(cnt), _dp(ws), ws.numel(), _stream()))
+    else:
+        _lib.check(L.p2w_radius(_dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T, x.size(0), y.size(0), float(r),
+                                max_num_neighbors, _dp(nbr), _dp(cnt), _stream()))
     return nbr, cnt
 
 

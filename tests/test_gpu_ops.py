@@ -49,12 +49,13 @@ KNN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("method", ["sweep", "grid"])
 @pytest.mark.parametrize("case", KNN_CASES)
-def test_knn_table_bit_exact(ops, case):
+def test_knn_table_bit_exact(ops, case, method):
     rng = np.random.default_rng(hash(str(case)) % 2**32)
     x, y, px, py = _tiles(rng, case["sx"], case["sy"], case.get("dup", False), case.get("lattice", False))
     ref, ref_d = O.knn(x, y, case["k"], px, py, return_d2=True)
-    nbr, d2 = ops.knn_table(_dev(x), _dev(y), case["k"], _dev(px), _dev(py), return_d2=True)
+    nbr, d2 = ops.knn_table(_dev(x), _dev(y), case["k"], _dev(px), _dev(py), return_d2=True, method=method)
     assert np.array_equal(nbr.cpu().numpy().astype(np.int64), ref)
     assert np.array_equal(d2.cpu().numpy(), ref_d)
 
@@ -85,11 +86,12 @@ def test_knn_edge_index_matches_upstream_layout(ops):
     dict(sx=[2048 * 3 + 5], sy=[777], r=0.05, m=8),
     dict(sx=[4000], sy=[1000], r=0.25, m=64, lattice=True),
 ])
-def test_radius_table_bit_exact(ops, case):
+@pytest.mark.parametrize("method", ["sweep", "grid"])
+def test_radius_table_bit_exact(ops, case, method):
     rng = np.random.default_rng(hash(str(case)) % 2**32)
     x, y, px, py = _tiles(rng, case["sx"], case["sy"], lattice=case.get("lattice", False))
     ref, ref_cnt = O.radius(x, y, case["r"], px, py, case["m"])
-    nbr, cnt = ops.radius_table(_dev(x), _dev(y), case["r"], _dev(px), _dev(py), case["m"])
+    nbr, cnt = ops.radius_table(_dev(x), _dev(y), case["r"], _dev(px), _dev(py), case["m"], method=method)
     assert np.array_equal(cnt.cpu().numpy(), ref_cnt)
     assert np.array_equal(nbr.cpu().numpy().astype(np.int64), ref)
     bx = np.repeat(np.arange(len(px) - 1), np.diff(px))
@@ -98,7 +100,8 @@ def test_radius_table_bit_exact(ops, case):
     assert np.array_equal(e.cpu().numpy(), O.table_to_edges(ref))
 
 
-def test_radius_sa1_subset_queries(ops):
+@pytest.mark.parametrize("method", ["sweep", "grid"])
+def test_radius_sa1_subset_queries(ops, method):
     """The SA1 call shape: y = x[idx], r = 0.08, max 32 on a dense cloud (src/model.py:118)."""
     from pointstowood_b200.synthetic import tls_plot
     p, _ = tls_plot(40000, 21, side=4.0)
@@ -106,9 +109,76 @@ def test_radius_sa1_subset_queries(ops):
     idx = np.sort(np.random.default_rng(1).choice(len(x), 9000, replace=False))
     px, py = np.array([0, len(x)]), np.array([0, len(idx)])
     ref, ref_cnt = O.radius(x, x[idx], 0.08, px, py, 32)
-    nbr, cnt = ops.radius_table(_dev(x), _dev(x[idx]), 0.08, _dev(px), _dev(py), 32)
+    nbr, cnt = ops.radius_table(_dev(x), _dev(x[idx]), 0.08, _dev(px), _dev(py), 32, method=method)
     assert np.array_equal(nbr.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(cnt.cpu().numpy(), ref_cnt)
     assert (ref_cnt == 32).mean() > 0.1          # truncation really happens
+
+
+def _tls_tiles(n, seed, side, n_side):
+    from pointstowood_b200.synthetic import tls_plot
+    p, _ = tls_plot(n, seed, side=side)
+    cell = side / n_side
+    tid = np.minimum((p[:, 0] / cell).astype(int), n_side - 1) * n_side + np.minimum((p[:, 1] / cell).astype(int),
+                                                                                     n_side - 1)
+    order = np.argsort(tid, kind="stable")
+    x = np.ascontiguousarray(p[order, :3])
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(tid, minlength=n_side * n_side))]).astype(np.int64)
+    return x, ptr
+
+
+@pytest.mark.parametrize("k", [2, 16, 32])
+def test_grid_knn_on_tls_tiles_matches_sweep_and_oracle(ops, k):
+    """Surface-like, strongly non-uniform tiles (the data the cell size is planned for); queries are a
+    subset of the sources (SA levels) or a superset (FP levels)."""
+    x, ptr = _tls_tiles(70000, 3, 6.0, 3)
+    rng = np.random.default_rng(k)
+    keep = np.sort(rng.choice(len(x), len(x) // 3, replace=False))
+    sub = x[keep]
+    ptr_sub = np.searchsorted(keep, ptr).astype(np.int64)
+    for (src, psrc, qry, pqry) in ((x, ptr, sub, ptr_sub), (sub, ptr_sub, x, ptr)):
+        grid, gd = ops.knn_table(_dev(src), _dev(qry), k, _dev(psrc), _dev(pqry), return_d2=True, method="grid")
+        sweep, sd = ops.knn_table(_dev(src), _dev(qry), k, _dev(psrc), _dev(pqry), return_d2=True, method="sweep")
+        assert torch.equal(grid, sweep) and torch.equal(gd, sd)
+    ref = O.knn(sub, x[:5000], k, ptr_sub, np.array([0] + [5000] * 9))         # first tile against the oracle
+    got = ops.knn_table(_dev(sub), _dev(x[:5000]), k, _dev(ptr_sub), _dev(np.array([0] + [5000] * 9)), method="grid")
+    assert np.array_equal(got.cpu().numpy().astype(np.int64), ref)
+
+
+def test_grid_knn_queries_far_outside_and_sparse_outliers(ops):
+    """Queries outside the sources' bounding box and isolated sources many empty cells away force
+    the shell expansion well past the first ring."""
+    rng = np.random.default_rng(11)
+    core = rng.normal(0, 0.05, (6000, 3)).astype(np.float32)
+    far = (rng.random((40, 3), dtype=np.float32) * 8 - 4).astype(np.float32)
+    x = np.concatenate([core, far]).astype(np.float32)
+    y = np.concatenate([far[:20] + 0.01, rng.random((300, 3), dtype=np.float32) * 30 - 15,
+                        core[:200]]).astype(np.float32)
+    px, py = np.array([0, len(x)]), np.array([0, len(y)])
+    for k in (1, 8, 32):
+        ref, ref_d = O.knn(x, y, k, px, py, return_d2=True)
+        nbr, d2 = ops.knn_table(_dev(x), _dev(y), k, _dev(px), _dev(py), return_d2=True, method="grid")
+        assert np.array_equal(nbr.cpu().numpy().astype(np.int64), ref)
+        assert np.array_equal(d2.cpu().numpy(), ref_d)
+    ref, ref_cnt = O.radius(x, y, 0.6, px, py, 32)
+    nbr, cnt = ops.radius_table(_dev(x), _dev(y), 0.6, _dev(px), _dev(py), 32, method="grid")
+    assert np.array_equal(nbr.cpu().numpy().astype(np.int64), ref) and np.array_equal(cnt.cpu().numpy(), ref_cnt)
+
+
+def test_grid_knn_degenerate_tiles(ops):
+    """All sources identical / collinear / k larger than the tile."""
+    same = np.full((500, 3), 0.25, np.float32)
+    line = np.zeros((700, 3), np.float32)
+    line[:, 0] = np.linspace(0, 1, 700, dtype=np.float32)
+    few = np.random.default_rng(2).random((40, 3), dtype=np.float32)
+    x = np.concatenate([same, line, few]).astype(np.float32)
+    px = np.array([0, 500, 1200, 1240])
+    y = np.random.default_rng(3).random((90, 3), dtype=np.float32)
+    py = np.array([0, 30, 60, 90])
+    for k in (4, 64):
+        ref = O.knn(x, y, k, px, py)
+        nbr = ops.knn_table(_dev(x), _dev(y), k, _dev(px), _dev(py), method="grid")
+        assert np.array_equal(nbr.cpu().numpy().astype(np.int64), ref)
 
 
 @pytest.mark.parametrize("sizes,ratio", [([3000], 0.05), ([1000, 1, 17000, 250], 0.01), ([64], 1.0)])

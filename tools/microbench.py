@@ -31,18 +31,33 @@ def main():
         pos, ptr = uniform_tiles(B, 16384, 2.0, 3)
         x = torch.from_numpy(pos).cuda()
         p = torch.from_numpy(ptr).cuda()
-        for k in (16, 32):
-            ms = timeit(lambda: ops.knn_table(x, x, k, p, p))
-            byt = 12 * 2 * x.size(0) + 16 * x.size(0) * k + 16 * (B + 1)
-            out.append(dict(op="knn", tiles=B, k=k, ms=ms, pairs_per_s=B * 16384.0 ** 2 / ms * 1e3,
-                            alg_GBs=byt / ms / 1e6))
-        ms = timeit(lambda: ops.radius_table(x, x, 0.08, p, p, 32))
-        out.append(dict(op="radius", tiles=B, ms=ms))
-        ms = timeit(lambda: ops.knn_table(x, x, 2, p, p))
-        out.append(dict(op="knn", tiles=B, k=2, ms=ms))
+        for method in ("sweep", "grid"):
+            for k in (16, 32):
+                ms = timeit(lambda: ops.knn_table(x, x, k, p, p, method=method))
+                byt = 12 * 2 * x.size(0) + 16 * x.size(0) * k + 16 * (B + 1)
+                out.append(dict(op="knn", method=method, tiles=B, k=k, ms=ms, us_per_tile=ms * 1e3 / B,
+                                alg_GBs=byt / ms / 1e6, frac_hbm=byt / ms / 1e6 / 6542.7))
+            ms = timeit(lambda: ops.radius_table(x, x, 0.08, p, p, 32, method=method))
+            out.append(dict(op="radius", method=method, tiles=B, ms=ms))
+            ms = timeit(lambda: ops.knn_table(x, x, 2, p, p, method=method))
+            out.append(dict(op="knn", method=method, tiles=B, k=2, ms=ms))
         batch = torch.repeat_interleave(torch.arange(B, device="cuda"), 16384)
         ms = timeit(lambda: ops.voxel_sample(x, 0.04, batch))
         out.append(dict(op="voxel_sample", tiles=B, ms=ms))
+    # TLS-like tiles (surfaces): 16 tiles of ~16k points cut from a synthetic plot
+    cloud, _ = tls_plot(16 * 16384, 7, side=8.0)
+    tid = np.minimum((cloud[:, 0] / 2.0).astype(int), 3) * 4 + np.minimum((cloud[:, 1] / 2.0).astype(int), 3)
+    order = np.argsort(tid, kind="stable")
+    xt = torch.from_numpy(np.ascontiguousarray(cloud[order, :3])).cuda()
+    pt = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(tid, minlength=16))]).astype(np.int64)).cuda()
+    for method in ("sweep", "grid"):
+        for k in (2, 32):
+            ms = timeit(lambda: ops.knn_table(xt, xt, k, pt, pt, method=method))
+            byt = 12 * 2 * xt.size(0) + 16 * xt.size(0) * k + 16 * 17
+            out.append(dict(op="knn_tls", method=method, tiles=16, k=k, ms=ms, alg_GBs=byt / ms / 1e6,
+                            frac_hbm=byt / ms / 1e6 / 6542.7))
+        ms = timeit(lambda: ops.radius_table(xt, xt, 0.08, pt, pt, 32, method=method))
+        out.append(dict(op="radius_tls", method=method, tiles=16, ms=ms))
     pos, ptr = uniform_tiles(8, 16384, 2.0, 3)
     x = torch.from_numpy(pos).cuda()
     p = torch.from_numpy(ptr).cuda()
