@@ -180,6 +180,14 @@ int p2w_knn_interpolate_ex(const void *x, int32_t x_dtype, const float *pos_x, c
                            const int32_t *nbr, int64_t ny, int32_t k, int32_t c, int32_t ld_out,
                            void *out, int32_t out_dtype, p2w_stream_t stream);
 
+/* FPModule.forward up to its MLP (src/model.py:149-151): out[q] = [knn_interpolate(x)[q], skip[q]], the
+ * interpolation and torch.cat([x, x_skip], dim=1) in one pass over 16-byte channel groups.
+ * c, c_skip and ld_out (>= c + c_skip) are multiples of 8; any mix of FP32 / BF16 rows. */
+int p2w_knn_interpolate_cat(const void *x, int32_t x_dtype, const float *pos_x, const float *pos_y,
+                            const int32_t *nbr, int64_t ny, int32_t k, int32_t c,
+                            const void *skip, int32_t skip_dtype, int32_t c_skip, int32_t ld_out,
+                            void *out, int32_t out_dtype, p2w_stream_t stream);
+
 /* ---- dense-block epilogues (src/model.py:18-85, InvertedResidualBlock in eval mode) ------------
  * What remains between two k=1 convolutions once every BatchNorm that follows a convolution is
  * folded into its weights: y = relu(x*s1 + t1), and if s2 != NULL y = relu(y*s2 + t2), per channel,

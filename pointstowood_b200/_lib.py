@@ -43,6 +43,8 @@ SIGNATURES = {
     "p2w_pointnet_conv_ws_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "p2w_knn_interpolate": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "p2w_knn_interpolate_ex": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, c_int32, _P]),
+    "p2w_knn_interpolate_cat": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int32, c_int32, c_int32,
+                                          _P, c_int32, _P]),
     "p2w_affine_relu": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, _P]),
     "p2w_segment_max": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "p2w_scatter_minmax": (c_int32, [_P, _P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),

@@ -166,6 +166,83 @@ __global__ void __launch_bounds__(256) interp_kernel(const TI *__restrict__ x, c
     }
 }
 
+// FPModule.forward (src/model.py:148-153) up to its MLP: out[q] = [knn_interpolate(x)[q], x_skip[q]] in one
+// pass.  Warp per query row; a lane owns groups of 8 channels (16-byte accesses on bf16 rows), so the
+// k source rows stream through full sectors and the concatenated row is written once.
+__device__ __forceinline__ void ld8(const float *p, float v[8]) {
+    *reinterpret_cast<float4 *>(v) = __ldg(reinterpret_cast<const float4 *>(p));
+    *reinterpret_cast<float4 *>(v + 4) = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16 *p, float v[8]) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p));
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const float2 f = __bfloat1622float2(h[u]);
+        v[2 * u] = f.x;
+        v[2 * u + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void st8(float *p, const float v[8]) {
+    reinterpret_cast<float4 *>(p)[0] = *reinterpret_cast<const float4 *>(v);
+    reinterpret_cast<float4 *>(p)[1] = *reinterpret_cast<const float4 *>(v + 4);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16 *p, const float v[8]) {
+    uint4 raw;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&raw);
+#pragma unroll
+    for (int u = 0; u < 4; u++) h[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+    *reinterpret_cast<uint4 *>(p) = raw;
+}
+
+template <typename TI, typename TS, typename TO>
+__global__ void __launch_bounds__(256) interp_cat_kernel(const TI *__restrict__ x, const float *__restrict__ pos_x,
+                                                         const float *__restrict__ pos_y,
+                                                         const int32_t *__restrict__ nbr, int64_t ny, int k, int c,
+                                                         const TS *__restrict__ skip, int cs, int ld_out,
+                                                         TO *__restrict__ out) {
+    const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= ny) return;
+    int j = -1;
+    float w = 0.f;
+    if (lane < k) {
+        j = nbr[q * k + lane];
+        if (j >= 0) {
+            const float dx = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 0], pos_y[q * 3 + 0]);
+            const float dy = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 1], pos_y[q * 3 + 1]);
+            const float dz = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 2], pos_y[q * 3 + 2]);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            w = __fdiv_rn(1.0f, fmaxf(d2, 1e-16f));
+        }
+    }
+    float den = 0.f;
+    for (int e = 0; e < k; e++) den = __fadd_rn(den, __shfl_sync(FULL, w, e));
+    const int groups = (c + cs) >> 3, gi = c >> 3;
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+        const int g = g0 + lane;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int e = 0; e < k; e++) {          // warp-uniform trip count: the shuffles stay converged
+            const int je = __shfl_sync(FULL, j, e);
+            const float we = __shfl_sync(FULL, w, e);
+            if (je >= 0 && g < gi) {
+                float v[8];
+                ld8(x + static_cast<int64_t>(je) * c + g * 8, v);
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] = __fadd_rn(acc[u], __fmul_rn(v[u], we));
+            }
+        }
+        if (g < gi) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc[u] = __fdiv_rn(acc[u], den);
+            st8(out + q * ld_out + g * 8, acc);
+        } else if (g < groups) {
+            ld8(skip + q * cs + (g - gi) * 8, acc);
+            st8(out + q * ld_out + g * 8, acc);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ segment max (global_max_pool)
 __global__ void __launch_bounds__(128) segment_max_kernel(const float *__restrict__ x, const int64_t *__restrict__ ptr,
                                                           int c, float *__restrict__ out) {
@@ -329,6 +406,41 @@ extern "C" int p2w_knn_interpolate(const float *x, const float *pos_x, const flo
                                    int64_t ny, int32_t k, int32_t c, int32_t ld_out, float *out,
                                    p2w_stream_t stream) {
     return p2w_knn_interpolate_ex(x, P2W_F32, pos_x, pos_y, nbr, ny, k, c, ld_out, out, P2W_F32, stream);
+}
+
+extern "C" int p2w_knn_interpolate_cat(const void *x, int32_t x_dtype, const float *pos_x, const float *pos_y,
+                                       const int32_t *nbr, int64_t ny, int32_t k, int32_t c, const void *skip,
+                                       int32_t skip_dtype, int32_t c_skip, int32_t ld_out, void *out,
+                                       int32_t out_dtype, p2w_stream_t stream) {
+    P2W_REQUIRE(k >= 1 && k <= 32, "p2w_knn_interpolate_cat: k=%d outside [1,32]", k);
+    P2W_REQUIRE(c >= 8 && c % 8 == 0 && c_skip >= 0 && c_skip % 8 == 0 && ld_out >= c + c_skip && ld_out % 8 == 0,
+                "p2w_knn_interpolate_cat: channel counts and the row stride must be multiples of 8");
+    P2W_REQUIRE((c_skip == 0) || skip != nullptr, "p2w_knn_interpolate_cat: skip rows missing");
+    auto okdt = [](int d) { return d == P2W_F32 || d == P2W_BF16; };
+    P2W_REQUIRE(okdt(x_dtype) && okdt(skip_dtype) && okdt(out_dtype), "p2w_knn_interpolate_cat: unknown dtype");
+    P2W_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                "p2w_knn_interpolate_cat: rows must be 16-byte aligned");
+    if (ny == 0) return P2W_OK;
+    cudaStream_t st = as_stream(stream);
+    const unsigned blocks = (unsigned)((ny * 32 + 255) / 256);
+    typedef __nv_bfloat16 bf;
+#define P2W_IC(TI, TS, TO)                                                                                       \
+    P2W_LAUNCH((interp_cat_kernel<TI, TS, TO>), blocks, 256, 0, st)(static_cast<const TI *>(x), pos_x, pos_y, nbr, ny, k, c, \
+                                                                    static_cast<const TS *>(skip), c_skip, ld_out,   \
+                                                                    static_cast<TO *>(out))
+    const int sel = x_dtype * 4 + skip_dtype * 2 + out_dtype;
+    switch (sel) {
+        case 0: P2W_IC(float, float, float); break;
+        case 1: P2W_IC(float, float, bf); break;
+        case 2: P2W_IC(float, bf, float); break;
+        case 3: P2W_IC(float, bf, bf); break;
+        case 4: P2W_IC(bf, float, float); break;
+        case 5: P2W_IC(bf, float, bf); break;
+        case 6: P2W_IC(bf, bf, float); break;
+        default: P2W_IC(bf, bf, bf); break;
+    }
+#undef P2W_IC
+    return check_launch("p2w_knn_interpolate_cat");
 }
 
 extern "C" int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_segments, int32_t c, float *out,

@@ -10,15 +10,17 @@
 //
 // An accumulator block is 128 channels (TMEM lanes) x 128 edges (TMEM columns = 4 targets x 32
 // edges).  An epilogue thread owns one channel: bias / ReLU / BatchNorm are per-thread constants
-// and the segment max is a 32-long register reduction.  Per CTA (persistent, one edge tile at a
-// time):
-//   warps 0-7  workers: gather x_j rows + geometry into the msg tile (bf16, canonical no-swizzle
-//              K-major layout), epilogue 1 (TMEM -> ReLU -> bf16 hid tile in shared memory),
+// and the segment max is a 32-long register reduction.  Per CTA (persistent), four roles run as a
+// pipeline over the edge tiles:
+//   warps 0-3  epilogue: epilogue 1 (TMEM -> ReLU -> bf16 hid tile in shared memory) and
 //              epilogue 2 (TMEM -> ReLU -> BN -> max -> out[t, c], coalesced over c);
+//   warps 4-7  gather: neighbour rows + geometry of the NEXT tile into the msg tile (bf16, canonical
+//              no-swizzle K-major layout) as soon as layer 1 of the current tile has consumed it;
 //   warp 8     one thread issues tcgen05.mma and tcgen05.commit;
 //   warp 9     one thread streams the pre-packed bf16 weights through a 4-stage ring of 8 KB
 //              slices with 1-D TMA bulk copies (the weights stay L2 resident).
-// Two 128-column accumulators alternate, so the MMAs of block j+1 overlap the epilogue of block j.
+// Two 128-column accumulators alternate, so the MMAs of block j+1 overlap the epilogue of block j,
+// and the gather of tile i+1 overlaps layer 2 and both epilogues of tile i.
 // The [E, C+4], [E, H] and [E, C'] edge tensors of the reference never exist in HBM.
 #include <cuda_bf16.h>
 
@@ -32,8 +34,11 @@ constexpr int TPT = NT / 32;                   // targets per tile
 constexpr int SLICE_K = 32;                    // k extent of one ring slice (two K=16 MMAs)
 constexpr int SLICE_BYTES = 128 * SLICE_K * 2; // 8 KB: [4 k-chunks][128 rows][8 bf16]
 constexpr int STAGES = 4;
-constexpr int WORKERS = 256;
-constexpr int THREADS = WORKERS + 64;
+constexpr int EPI_THREADS = 128;                // warps 0-3 (one TMEM lane quarter each)
+constexpr int GATHER_WARPS = 4;                 // warps 4-7
+constexpr int GATHER_THREADS = GATHER_WARPS * 32;
+constexpr int THREADS = EPI_THREADS + GATHER_THREADS + 64;
+constexpr int VALID_SLOTS = 4;                  // per-target validity flags of the tiles in flight
 constexpr int LBO1 = NT * 16 + 16;             // k-chunk stride of the msg tile, padded against bank conflicts
 constexpr int TMEM_COLS = 2 * NT;
 constexpr unsigned FULL = 0xffffffffu;
@@ -90,7 +95,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
+__device__ __forceinline__ void gather_bar() { asm volatile("bar.sync 1, %0;" ::"n"(GATHER_THREADS) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // .x (low half) = a
@@ -108,7 +113,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K1p, int H) {
     L.b2 = (L.b2 + 127u) & ~127u;
     L.sj = L.b2 + (NT / 8) * (H * 16);
     L.svalid = L.sj + NT * 4;
-    L.bars = (L.svalid + TPT * 4 + 7u) & ~7u;
+    L.bars = (L.svalid + VALID_SLOTS * TPT * 4 + 7u) & ~7u;
     L.tmem = L.bars + 8 * (2 * STAGES + 8);
     L.total = L.tmem + 16;
     return L;
@@ -133,10 +138,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], WORKERS); }
-        mbar_init(b1_full, WORKERS);
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_THREADS); }
+        mbar_init(b1_full, GATHER_THREADS);
         mbar_init(b1_empty, 1);
-        mbar_init(b2_full, WORKERS);
+        mbar_init(b2_full, EPI_THREADS);
         mbar_init(b2_empty, 1);
         fence_barrier_init();
     }
@@ -222,30 +227,28 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             }
             tph ^= 1;
         }
-    } else {
-        // ------------------------------------------------ workers: gather + epilogues
-        int acc = 0;
-        uint32_t tph = 0, use0 = 0, use1 = 0;
-        const int q = warp & 3, ch = warp >> 2;
+    } else if (warp >= 4) {
+        // ------------------------------------------------ gather warps: one tile ahead of the MMAs
+        uint32_t tph = 0;
+        const int gw = warp - 4;
         const int CPR = p.C >> 3;
         const int cpr_c = CPR < 32 ? CPR : 32;
         const int rpw = 32 / cpr_c;
         const int ck = lane % cpr_c, ri = lane / cpr_c;
-        const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
         for (int it = 0; it < my_tiles; it++) {
             const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
             const int64_t t0 = static_cast<int64_t>(tile) * TPT;
-            worker_bar();                          // everyone is done with s_j / s_valid of the previous tile
-            mbar_wait(b1_empty, tph ^ 1);          // MMA1 of the previous tile no longer reads the msg tile
-            if (warp < TPT) {
-                const int64_t t = t0 + warp;
+            gather_bar();                          // every gather warp is done with s_j of the previous tile
+            mbar_wait(b1_empty, tph ^ 1);          // layer 1 of the previous tile no longer reads the msg tile
+            for (int tw = gw; tw < TPT; tw += GATHER_WARPS) {
+                const int64_t t = t0 + tw;
                 int j = (t < p.n_tgt && lane < p.K) ? p.nbr[t * p.K + lane] : -1;
                 const unsigned m = __ballot_sync(FULL, j >= 0);
                 const int jf = m ? __shfl_sync(FULL, j, __ffs(m) - 1) : 0;
                 if (j < 0) j = jf;                 // padded slot: duplicate a valid edge (max unchanged)
-                const int n = warp * 32 + lane;
+                const int n = tw * 32 + lane;
                 s_j[n] = j;
-                if (lane == 0) s_valid[warp] = m ? 1 : 0;
+                if (lane == 0) s_valid[(it & (VALID_SLOTS - 1)) * TPT + tw] = m ? 1 : 0;
                 const float4 ps = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j);
                 const float4 pt = __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + (t < p.n_tgt ? t : 0));
                 const float dx = ps.x - pt.x, dy = ps.y - pt.y, dz = ps.z - pt.z;
@@ -259,31 +262,31 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 g.w = 0;
                 *reinterpret_cast<uint4 *>(b1 + CPR * LBO1 + n * 16) = g;
             }
-            worker_bar();
+            gather_bar();
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
             if (p.x_bf16) {
                 const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16 *>(p.x);
-                for (int r0 = warp * rpw; r0 < NT; r0 += 8 * rpw * 4) {
+                for (int r0 = gw * rpw; r0 < NT; r0 += GATHER_WARPS * rpw * 4) {
                     uint4 v[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const int n = r0 + u * 8 * rpw + ri;
+                        const int n = r0 + u * GATHER_WARPS * rpw + ri;
                         if (n < NT && ck < CPR)
                             v[u] = __ldg(reinterpret_cast<const uint4 *>(xb + static_cast<int64_t>(s_j[n]) * p.C + ck * 8));
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const int n = r0 + u * 8 * rpw + ri;
+                        const int n = r0 + u * GATHER_WARPS * rpw + ri;
                         if (n < NT && ck < CPR) *reinterpret_cast<uint4 *>(b1 + ck * LBO1 + n * 16) = v[u];
                     }
                 }
             } else {
                 const float *xf = static_cast<const float *>(p.x);
-                for (int r0 = warp * rpw; r0 < NT; r0 += 8 * rpw * 4) {
+                for (int r0 = gw * rpw; r0 < NT; r0 += GATHER_WARPS * rpw * 4) {
                     float4 lo[4], hi[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const int n = r0 + u * 8 * rpw + ri;
+                        const int n = r0 + u * GATHER_WARPS * rpw + ri;
                         if (n < NT && ck < CPR) {
                             const float4 *src =
                                 reinterpret_cast<const float4 *>(xf + static_cast<int64_t>(s_j[n]) * p.C + ck * 8);
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const int n = r0 + u * 8 * rpw + ri;
+                        const int n = r0 + u * GATHER_WARPS * rpw + ri;
                         if (n < NT && ck < CPR) {
                             uint4 v;
                             v.x = pack_bf16(lo[u].x, lo[u].y);
@@ -307,17 +310,27 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             }
             fence_proxy_async();
             mbar_arrive(b1_full);
-
+            tph ^= 1;
+        }
+    } else {
+        // ------------------------------------------------ epilogue warps (TMEM lane quarter q = warp)
+        int acc = 0;
+        uint32_t tph = 0, use0 = 0, use1 = 0;
+        const int q = warp;
+        const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int64_t t0 = static_cast<int64_t>(tile) * TPT;
             // ---- epilogue 1: hid[e, h] = relu(D1^T[h, e] + b1[h]) as the MN-major B operand of layer 2
             for (int blk = 0; blk < p.NB1; blk++) {
                 mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
-                if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // MMA2 of the previous tile is done with hid
+                if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // layer 2 of the previous tile is done with hid
                 const int h = blk * 128 + 32 * q + lane;
                 const float bias = p.b1p[h];
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int n0 = ch * 64 + c * 32;
+                for (int c = 0; c < NT / 32; c++) {
+                    const int n0 = c * 32;
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + n0, r);
                     if (h < p.H) {
@@ -346,14 +359,14 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             mbar_arrive(b2_full);
 
             // ---- epilogue 2: out[t, c] = max_e BN(relu(D2^T[c, e] + b2[c]))
+            const int *valid = s_valid + (it & (VALID_SLOTS - 1)) * TPT;
             for (int blk = 0; blk < p.NB2; blk++) {
                 mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
                 const int co = blk * 128 + 32 * q + lane;
                 const float bias = p.b2p[co], sc = p.scale[co], sh = p.shift[co];
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int tt = ch * 2 + c;
+                for (int tt = 0; tt < TPT; tt++) {
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + tt * 32, r);
                     float m = __int_as_float(0xff800000);
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                         m = fmaxf(m, fmaf(fmaxf(__uint_as_float(r[e]) + bias, 0.f), sc, sh));
                     const int64_t t = t0 + tt;
                     if (t < p.n_tgt && co < p.Co) {
-                        const float v = s_valid[tt] ? m : 0.f;
+                        const float v = valid[tt] ? m : 0.f;
                         if (p.out_bf16) static_cast<__nv_bfloat16 *>(p.out)[t * p.Co + co] = __float2bfloat16(v);
                         else static_cast<float *>(p.out)[t * p.Co + co] = v;
                     }
@@ -437,7 +450,8 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
                        const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
                        bool packed) {
     (void)n_src;
-    P2W_REQUIRE(c_in % 8 == 0 && c_in >= 8, "p2w_pointnet_conv_max(bf16): c_in=%d must be a multiple of 8", c_in);
+    P2W_REQUIRE(c_in % 8 == 0 && c_in >= 8 && c_in <= 256,
+                "p2w_pointnet_conv_max(bf16): c_in=%d must be a multiple of 8 in [8, 256]", c_in);
     P2W_REQUIRE(hidden % SLICE_K == 0, "p2w_pointnet_conv_max(bf16): hidden=%d must be a multiple of 32", hidden);
     P2W_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(pos_src) & 15u) == 0 &&
                     (reinterpret_cast<uintptr_t>(pos_tgt) & 15u) == 0 && (reinterpret_cast<uintptr_t>(ws) & 127u) == 0,

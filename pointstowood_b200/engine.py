@@ -184,10 +184,7 @@ class InferenceEngine:
         ptr_c = torch.arange(T + 1, device=pos.device, dtype=torch.int64)
         # ---- FPModules (src/model.py:148-153), coarse -> fine
         for fp, (x_skip, pos_skip, ptr_skip) in zip(self.fp, reversed(skips)):
-            c, cs = x.size(1), x_skip.size(1)
-            buf = torch.empty((pos_skip.size(0), c + cs), device=x.device, dtype=dt)
-            ops.knn_interpolate(x, pos_c, pos_skip, k=fp["k"], ptr_x=ptr_c, ptr_y=ptr_skip, out=buf)
-            buf[:, c:] = x_skip
+            buf = ops.knn_interpolate_cat(x, pos_c, pos_skip, x_skip, fp["k"], ptr_c, ptr_skip, out_dtype=dt)
             x = fp["l2"](fp["l1"](buf))
             pos_c, ptr_c = pos_skip, ptr_skip
         x = self.head2(self.head1(x))

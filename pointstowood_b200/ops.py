@@ -25,7 +25,7 @@ from . import _lib
 
 __all__ = [
     "batch_to_ptr", "knn", "radius", "fps", "grid_cluster", "voxel_grid", "consecutive_cluster",
-    "knn_interpolate", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
+    "knn_interpolate", "knn_interpolate_cat", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
     "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback",
     "sort_pairs", "affine_relu_", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
 ]
@@ -443,6 +443,28 @@ def knn_interpolate(x: Tensor, pos_x: Tensor, pos_y: Tensor, batch_x: Optional[T
         raise _lib.P2WError("knn_interpolate: out must be a row-major float32 / bfloat16 buffer")
     _lib.check(_lib.lib().p2w_knn_interpolate_ex(_dp(x), _DT[x.dtype], _dp(pos_x), _dp(pos_y), _dp(nbr), pos_y.size(0), k,
                                                  x.size(1), out.stride(0), _dp(out), _DT[out.dtype], _stream()))
+    return out
+
+
+def knn_interpolate_cat(x: Tensor, pos_x: Tensor, pos_y: Tensor, x_skip: Optional[Tensor], k: int, ptr_x: Tensor,
+                        ptr_y: Tensor, out_dtype=None) -> Tensor:
+    """FPModule.forward before its MLP (src/model.py:149-151): torch.cat([knn_interpolate(x, pos_x, pos_y, k),
+    x_skip], dim=1) written in one pass.  Rows may be float32 or bfloat16; channel counts multiples of 8."""
+    if x.dtype not in _DT or (x_skip is not None and x_skip.dtype not in _DT):
+        raise _lib.P2WError("knn_interpolate_cat: rows must be float32 or bfloat16")
+    x = _req(x, x.dtype, "x", 2)
+    pos_x, pos_y = _req(pos_x, torch.float32, "pos_x", 2), _req(pos_y, torch.float32, "pos_y", 2)
+    nbr = knn_table(pos_x, pos_y, k, ptr_x, ptr_y)
+    c = x.size(1)
+    cs = 0 if x_skip is None else x_skip.size(1)
+    if x_skip is not None:
+        x_skip = _req(x_skip, x_skip.dtype, "x_skip", 2)
+        if x_skip.size(0) != pos_y.size(0):
+            raise _lib.P2WError("knn_interpolate_cat: x_skip must have one row per target")
+    out = torch.empty((pos_y.size(0), c + cs), device=x.device, dtype=out_dtype or x.dtype)
+    _lib.check(_lib.lib().p2w_knn_interpolate_cat(_dp(x), _DT[x.dtype], _dp(pos_x), _dp(pos_y), _dp(nbr), pos_y.size(0), k,
+                                                  c, _dp(x_skip), _DT[x_skip.dtype] if cs else 0, cs, c + cs, _dp(out),
+                                                  _DT[out.dtype], _stream()))
     return out
 
 

@@ -170,3 +170,21 @@ def test_knn_interpolate_bf16_rows(p2w):
     ops.knn_interpolate(x.bfloat16(), px, py, k=2, ptr_x=ptr_x, ptr_y=ptr_y, out=buf)
     assert (buf[:, :64].float() - want).abs().max().item() <= 3e-2
     assert (buf[:, 64:] == 0).all()
+
+
+def test_knn_interpolate_cat_equals_interpolate_then_cat(p2w):
+    """FPModule front half in one pass: same arithmetic as knn_interpolate + torch.cat (bit-exact in fp32)."""
+    _, ops = p2w
+    rng = np.random.default_rng(8)
+    px = torch.from_numpy(rng.random((700, 3), dtype=np.float32)).cuda()
+    py = torch.from_numpy(rng.random((3000, 3), dtype=np.float32)).cuda()
+    x = torch.from_numpy(rng.normal(size=(700, 64)).astype(np.float32)).cuda()
+    skip = torch.from_numpy(rng.normal(size=(3000, 32)).astype(np.float32)).cuda()
+    ptr_x, ptr_y = torch.tensor([0, 300, 700]).cuda(), torch.tensor([0, 1000, 3000]).cuda()
+    want = torch.cat([ops.knn_interpolate(x, px, py, k=2, ptr_x=ptr_x, ptr_y=ptr_y), skip], dim=1)
+    got = ops.knn_interpolate_cat(x, px, py, skip, 2, ptr_x, ptr_y)
+    assert torch.equal(got, want)
+    got_bf = ops.knn_interpolate_cat(x.bfloat16(), px, py, skip, 2, ptr_x, ptr_y, out_dtype=torch.bfloat16)
+    assert got_bf.dtype == torch.bfloat16 and (got_bf.float() - want).abs().max().item() <= 3e-2
+    none = ops.knn_interpolate_cat(x, px, py, None, 2, ptr_x, ptr_y)
+    assert torch.equal(none, want[:, :64])
