@@ -23,6 +23,7 @@
 // and the gather of tile i+1 overlaps layer 2 and both epilogues of tile i.
 // The [E, C+4], [E, H] and [E, C'] edge tensors of the reference never exist in HBM.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,7 +34,7 @@ constexpr int NT = 128;                        // edges per tile (MMA N)
 constexpr int TPT = NT / 32;                   // targets per tile
 constexpr int SLICE_K = 32;                    // k extent of one ring slice (two K=16 MMAs)
 constexpr int SLICE_BYTES = 128 * SLICE_K * 2; // 8 KB: [4 k-chunks][128 rows][8 bf16]
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 16;                  // weight-ring depth is chosen per layer shape (tc_stages)
 constexpr int EPI_THREADS = 128;                // warps 0-3 (one TMEM lane quarter each)
 constexpr int GATHER_WARPS = 4;                 // warps 4-7
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
@@ -43,12 +44,17 @@ constexpr int LBO1 = NT * 16 + 16;             // k-chunk stride of the msg tile
 constexpr int TMEM_COLS = 2 * NT;
 constexpr unsigned FULL = 0xffffffffu;
 
+// timing experiments only (P2W_CONV_DEBUG & 16): clock64 timeline of the MMA thread of CTA 0
+__device__ long long g_timeline[8192];
+
 struct ConvTcParams {
     const void *x;                 // [n_src, C] FP32 or BF16 (x_bf16)
     const float *pos_src, *pos_tgt;
     const int32_t *nbr;
     int64_t n_tgt;
     int K, C, H, Co, K1p, NB1, NB2, num_tiles, x_bf16, out_bf16;
+    int stages, resident;          // ring depth; resident: the ring holds ALL weight slices, loaded once
+    int debug;                     // timing experiments only (P2W_CONV_DEBUG): 1 no weight re-streaming, 2 no feature gather
     const unsigned char *wpack;
     const float *b1p, *b2p, *scale, *shift;
     void *out;                     // [n_tgt, Co] FP32 or BF16 (out_bf16)
@@ -95,6 +101,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// one lane of a converged warp (the warp-uniform issue pattern ptxas keeps in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void gather_bar() { asm volatile("bar.sync 1, %0;" ::"n"(GATHER_THREADS) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -105,35 +117,37 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 struct SmemLayout {
     uint32_t ring, b1, b2, sj, svalid, bars, tmem, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int K1p, int H) {
+__host__ __device__ inline SmemLayout smem_layout(int K1p, int H, int stages) {
     SmemLayout L;
     L.ring = 0;
-    L.b1 = L.ring + STAGES * SLICE_BYTES;
+    L.b1 = L.ring + stages * SLICE_BYTES;
     L.b2 = L.b1 + (K1p / 8) * LBO1;
     L.b2 = (L.b2 + 127u) & ~127u;
     L.sj = L.b2 + (NT / 8) * (H * 16);
     L.svalid = L.sj + NT * 4;
     L.bars = (L.svalid + VALID_SLOTS * TPT * 4 + 7u) & ~7u;
-    L.tmem = L.bars + 8 * (2 * STAGES + 8);
+    L.tmem = L.bars + 8 * (2 * MAX_STAGES + 8);
     L.total = L.tmem + 16;
     return L;
 }
 
 __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const SmemLayout L = smem_layout(p.K1p, p.H);
+    const SmemLayout L = smem_layout(p.K1p, p.H, p.stages);
+    const int STAGES = p.stages;
     unsigned char *ring = smem + L.ring;
     unsigned char *b1 = smem + L.b1;
     unsigned char *b2 = smem + L.b2;
     int *s_j = reinterpret_cast<int *>(smem + L.sj);
     int *s_valid = reinterpret_cast<int *>(smem + L.svalid);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
-    uint64_t *ring_full = bars, *ring_empty = bars + STAGES;
-    uint64_t *acc_full = bars + 2 * STAGES, *acc_empty = acc_full + 2;
+    uint64_t *ring_full = bars, *ring_empty = bars + MAX_STAGES;
+    uint64_t *acc_full = bars + 2 * MAX_STAGES, *acc_empty = acc_full + 2;
     uint64_t *b1_full = acc_empty + 2, *b1_empty = b1_full + 1, *b2_full = b1_full + 2, *b2_empty = b1_full + 3;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L.tmem);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(FULL, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+    const int lane = threadIdx.x & 31;
     const int kchunks = p.K1p >> 3;
 
     if (threadIdx.x == 0) {
@@ -168,65 +182,82 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 
     if (warp == 9) {
         // ------------------------------------------------ weight producer
-        // (the whole warp walks the loop so that it reaches the final barrier converged; lane 0 issues)
+        // The whole warp walks the (warp-uniform) loop, one elected lane issues: addresses and counters stay
+        // in uniform registers, so the loop body is a wait, an expect_tx and a bulk copy.
         int slot = 0;
         uint32_t ph = 0;
         const int per_tile = p.NB1 * n1 + p.NB2 * n2;
-        for (int it = 0; it < my_tiles; it++) {
+        const int passes = (p.debug & 1) ? 0 : (p.resident ? (my_tiles > 0 ? 1 : 0) : my_tiles);
+        for (int it = 0; it < passes; it++) {
+            const unsigned char *src = p.wpack;
             for (int s = 0; s < per_tile; s++) {
                 mbar_wait(&ring_empty[slot], ph ^ 1);
-                if (lane == 0) {
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&ring_full[slot], SLICE_BYTES);
-                    bulk_g2s(ring + slot * SLICE_BYTES, p.wpack + static_cast<size_t>(s) * SLICE_BYTES, SLICE_BYTES,
-                             &ring_full[slot]);
+                    bulk_g2s(ring + slot * SLICE_BYTES, src, SLICE_BYTES, &ring_full[slot]);
                 }
-                __syncwarp();
+                src += SLICE_BYTES;
                 if (++slot == STAGES) { slot = 0; ph ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp == 8) {
-        // ------------------------------------------------ MMA issuer (lane 0 issues, the warp stays converged)
+        // ------------------------------------------------ MMA issuer: warp-uniform loop, one elected lane
+        // issues; descriptors advance by increments (a lone issuing warp is latency-bound on every
+        // dependent instruction, so the per-slice body must stay a few instructions long).
         int slot = 0, acc = 0;
         uint32_t ph = 0, tph = 0, use0 = 0, use1 = 0;
-        const uint32_t ring_a = smem_u32(ring), b1_a = smem_u32(b1), b2_a = smem_u32(b2);
+        const uint64_t a_desc0 = smem_desc(smem_u32(ring), 2048, 128);            // + slot * 512 (+ 256 for kk = 1)
+        const uint64_t b1_desc0 = smem_desc(smem_u32(b1), LBO1, 128);             // + s * 4 LBO1/16 (+ 2 LBO1/16)
+        const uint64_t b2_desc0 = smem_desc(smem_u32(b2), 128, p.H * 16);         // + s * 32 (+ 16)
         constexpr uint32_t ID1 = instr_desc(false), ID2 = instr_desc(true);
+        const bool stream = !(p.resident || (p.debug & 1));
+        const bool rec = (p.debug & 16) && blockIdx.x == 0;
+        int nrec = 0;
+#define P2W_TS(tag) do { if (rec && lane == 0 && nrec < 4090) { g_timeline[2 + nrec++] = (clock64() << 8) | (tag); } } while (0)
         for (int it = 0; it < my_tiles; it++) {
+#pragma unroll 1
             for (int layer = 0; layer < 2; layer++) {
+                P2W_TS(1 + layer);
                 mbar_wait(layer == 0 ? b1_full : b2_full, tph);
                 tc_fence_after();
+                P2W_TS(3 + layer);
                 const int nb = layer == 0 ? p.NB1 : p.NB2, ns = layer == 0 ? n1 : n2;
+                const uint64_t b_desc0 = layer == 0 ? b1_desc0 : b2_desc0;
+                const uint32_t b_step = layer == 0 ? 4u * (LBO1 >> 4) : 32u, b_half = b_step >> 1;
+                const uint32_t idesc = layer == 0 ? ID1 : ID2;
                 for (int blk = 0; blk < nb; blk++) {
-                    const uint32_t use = acc ? use1 : use0;
-                    mbar_wait(&acc_empty[acc], (use & 1) ^ 1);
+                    P2W_TS(5);
+                    mbar_wait(&acc_empty[acc], ((acc ? use1 : use0) & 1) ^ 1);
                     tc_fence_after();
+                    P2W_TS(6);
                     const uint32_t d_addr = tmem_base + acc * NT;
+                    uint64_t bd = b_desc0;
                     for (int s = 0; s < ns; s++) {
-                        mbar_wait(&ring_full[slot], ph);
-                        tc_fence_after();
-                        if (lane == 0) {
-#pragma unroll
-                            for (int kk = 0; kk < 2; kk++) {
-                                const uint64_t ad = smem_desc(ring_a + slot * SLICE_BYTES + kk * 4096, 2048, 128);
-                                const uint64_t bd =
-                                    layer == 0 ? smem_desc(b1_a + (s * 4 + kk * 2) * LBO1, LBO1, 128)
-                                               : smem_desc(b2_a + (s * 2 + kk) * 256, 128, p.H * 16);
-                                umma(d_addr, ad, bd, layer == 0 ? ID1 : ID2, (s | kk) ? 1u : 0u);
+                        if (stream || (it == 0 && !(p.debug & 1))) mbar_wait(&ring_full[slot], ph);
+                        const uint64_t ad = a_desc0 + static_cast<uint32_t>(slot) * (SLICE_BYTES >> 4);
+                        if (elect_one()) {
+                            if (!(p.debug & 8)) {
+                                umma(d_addr, ad, bd, idesc, s ? 1u : 0u);
+                                umma(d_addr, ad + 256u, bd + b_half, idesc, 1u);
                             }
-                            umma_commit(&ring_empty[slot]);
+                            if (stream) umma_commit(&ring_empty[slot]);
                         }
-                        __syncwarp();
+                        bd += b_step;
                         if (++slot == STAGES) { slot = 0; ph ^= 1; }
                     }
-                    if (lane == 0) umma_commit(&acc_full[acc]);
-                    __syncwarp();
+                    P2W_TS(7);
+                    if (elect_one()) umma_commit(&acc_full[acc]);
                     if (acc) use1++; else use0++;
                     acc ^= 1;
                 }
-                if (lane == 0) umma_commit(layer == 0 ? b1_empty : b2_empty);
-                __syncwarp();
+                if (elect_one()) umma_commit(layer == 0 ? b1_empty : b2_empty);
             }
             tph ^= 1;
         }
+        if (rec && lane == 0) g_timeline[0] = nrec;
+#undef P2W_TS
+        __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------ gather warps: one tile ahead of the MMAs
         uint32_t tph = 0;
@@ -264,7 +295,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             }
             gather_bar();
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
-            if (p.x_bf16) {
+            if (p.debug & 2) {
+            } else if (p.x_bf16) {
                 const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16 *>(p.x);
                 for (int r0 = gw * rpw; r0 < NT; r0 += GATHER_WARPS * rpw * 4) {
                     uint4 v[4];
@@ -329,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 const int h = blk * 128 + 32 * q + lane;
                 const float bias = p.b1p[h];
 #pragma unroll
-                for (int c = 0; c < NT / 32; c++) {
+                for (int c = 0; c < ((p.debug & 4) ? 0 : NT / 32); c++) {
                     const int n0 = c * 32;
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + n0, r);
@@ -366,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 const int co = blk * 128 + 32 * q + lane;
                 const float bias = p.b2p[co], sc = p.scale[co], sh = p.shift[co];
 #pragma unroll
-                for (int tt = 0; tt < TPT; tt++) {
+                for (int tt = 0; tt < ((p.debug & 4) ? 0 : TPT); tt++) {
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + tt * 32, r);
                     float m = __int_as_float(0xff800000);
@@ -442,6 +474,10 @@ inline TcPlan tc_plan(int c_in, int hidden, int c_out) {
 
 using namespace p2w;
 
+extern "C" int p2wdbg_conv_timeline(long long *dst_host, int n) {
+    return (int)cudaMemcpyFromSymbol(dst_host, g_timeline, sizeof(long long) * n);
+}
+
 size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out) { return tc_plan(c_in, hidden, c_out).total; }
 
 int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
@@ -458,7 +494,20 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
                 "p2w_pointnet_conv_max(bf16): x / pos / workspace must be 16-byte aligned");
     const TcPlan t = tc_plan(c_in, hidden, c_out);
     P2W_REQUIRE(ws_bytes >= t.total, "p2w_pointnet_conv_max(bf16): workspace too small");
-    const SmemLayout L = smem_layout(t.K1p, hidden);
+    // Weight-ring depth.  The ring must keep (L2 latency x consumption rate) bytes in flight, so it takes
+    // whatever shared memory the tiles leave: all of it when one CTA per SM is the only option, up to
+    // the two-CTAs-per-SM budget otherwise.  A layer whose slices all fit (SA1) keeps them resident.
+    const int per_tile = t.NB1 * (t.K1p / SLICE_K) + t.NB2 * (hidden / SLICE_K);
+    const unsigned fixed = smem_layout(t.K1p, hidden, 0).total;
+    const unsigned budget2 = 113u * 1024u, budget1 = 227u * 1024u;
+    int stages;
+    if (fixed + 4u * SLICE_BYTES <= budget2) stages = static_cast<int>((budget2 - fixed) / SLICE_BYTES);
+    else stages = fixed + 2u * SLICE_BYTES <= budget1 ? static_cast<int>((budget1 - fixed) / SLICE_BYTES) : 0;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    const int resident = per_tile <= stages ? 1 : 0;
+    if (resident) stages = per_tile;
+    P2W_REQUIRE(stages >= 2, "p2w_pointnet_conv_max(bf16): layer too wide for one CTA (%u bytes of tiles)", fixed);
+    const SmemLayout L = smem_layout(t.K1p, hidden, stages);
     P2W_REQUIRE(L.total <= 227 * 1024, "p2w_pointnet_conv_max(bf16): layer too wide for one CTA (%u bytes smem)",
                 L.total);
     unsigned char *base = static_cast<unsigned char *>(ws);
@@ -479,6 +528,12 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     }
     ConvTcParams p;
     p.x_bf16 = x_bf16; p.out_bf16 = out_bf16;
+    p.stages = stages; p.resident = resident;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("P2W_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+        p.debug = dbg;
+    }
     p.x = x; p.pos_src = pos_src; p.pos_tgt = pos_tgt; p.nbr = nbr;
     p.n_tgt = n_tgt; p.K = k; p.C = c_in; p.H = hidden; p.Co = c_out;
     p.K1p = t.K1p; p.NB1 = t.NB1; p.NB2 = t.NB2;
@@ -496,7 +551,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
         smem_set = L.total;
     }
-    const int per_sm = (L.total <= 110 * 1024) ? 2 : 1;     // TMEM: 2 x 256 columns fit one SM
+    const int per_sm = (L.total <= 113 * 1024) ? 2 : 1;     // TMEM: 2 x 256 columns fit one SM
     int grid = sm_count * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
     P2W_LAUNCH(conv_tc_kernel, grid, THREADS, L.total, st)(p);
