@@ -21,6 +21,12 @@
 //              slices with 1-D TMA bulk copies (the weights stay L2 resident).
 // Two 128-column accumulators alternate, so the MMAs of block j+1 overlap the epilogue of block j,
 // and the gather of tile i+1 overlaps layer 2 and both epilogues of tile i.
+// Epilogue algebra (the epilogue warps share the SM's issue slots with everything else, so every
+// per-edge instruction counts): b1 rides in the contraction as a constant-one message column, so
+// epilogue 1 is one cvt.rn.relu.bf16x2 per two values; y -> BN(ReLU(y + b2)) is monotone (increasing
+// for a non-negative BN scale, decreasing otherwise), so rows of W2 whose BN scale is negative are
+// negated when packed and epilogue 2 is a plain running max per edge, with bias / ReLU / BN applied
+// once per (channel, target) to the extremal value -- bit-identical to applying them per edge.
 // The [E, C+4], [E, H] and [E, C'] edge tensors of the reference never exist in HBM.
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -112,6 +118,12 @@ __device__ __forceinline__ void gather_bar() { asm volatile("bar.sync 1, %0;" ::
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // .x (low half) = a
     return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {   // low half = relu(a), high half = relu(b)
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
 }
 
 struct SmemLayout {
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 uint4 g;
                 g.x = pack_bf16(dx / den, dy / den);
                 g.y = pack_bf16(dz / den, ps.w);
-                g.z = 0;
+                g.z = 0x00003F80u;                 // column C+4 = 1.0: carries b1 through the contraction
                 g.w = 0;
                 *reinterpret_cast<uint4 *>(b1 + CPR * LBO1 + n * 16) = g;
             }
@@ -359,7 +371,6 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 tc_fence_after();
                 if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // layer 2 of the previous tile is done with hid
                 const int h = blk * 128 + 32 * q + lane;
-                const float bias = p.b1p[h];
 #pragma unroll
                 for (int c = 0; c < ((p.debug & 4) ? 0 : NT / 32); c++) {
                     const int n0 = c * 32;
@@ -370,14 +381,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 #pragma unroll
                         for (int g = 0; g < 4; g++) {
                             uint4 v;
-                            v.x = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 0]) + bias, 0.f),
-                                            fmaxf(__uint_as_float(r[8 * g + 1]) + bias, 0.f));
-                            v.y = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 2]) + bias, 0.f),
-                                            fmaxf(__uint_as_float(r[8 * g + 3]) + bias, 0.f));
-                            v.z = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 4]) + bias, 0.f),
-                                            fmaxf(__uint_as_float(r[8 * g + 5]) + bias, 0.f));
-                            v.w = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 6]) + bias, 0.f),
-                                            fmaxf(__uint_as_float(r[8 * g + 7]) + bias, 0.f));
+                            v.x = pack_bf16_relu(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+                            v.y = pack_bf16_relu(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+                            v.z = pack_bf16_relu(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+                            v.w = pack_bf16_relu(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
                             *reinterpret_cast<uint4 *>(dst + g * (p.H * 16)) = v;
                         }
                     }
@@ -397,14 +404,22 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 tc_fence_after();
                 const int co = blk * 128 + 32 * q + lane;
                 const float bias = p.b2p[co], sc = p.scale[co], sh = p.shift[co];
+                const float sgn = sc < 0.f ? -1.f : 1.f;      // rows with a negative BN scale were packed negated
 #pragma unroll
                 for (int tt = 0; tt < ((p.debug & 4) ? 0 : TPT); tt++) {
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + tt * 32, r);
-                    float m = __int_as_float(0xff800000);
+                    float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]),
+                          m3 = __uint_as_float(r[3]);
 #pragma unroll
-                    for (int e = 0; e < 32; e++)
-                        m = fmaxf(m, fmaf(fmaxf(__uint_as_float(r[e]) + bias, 0.f), sc, sh));
+                    for (int e = 4; e < 32; e += 4) {
+                        m0 = fmaxf(m0, __uint_as_float(r[e]));
+                        m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
+                    }
+                    const float ext = sgn * fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));   // the edge value that maximises BN(ReLU(.))
+                    const float m = fmaf(fmaxf(ext + bias, 0.f), sc, sh);
                     const int64_t t = t0 + tt;
                     if (t < p.n_tgt && co < p.Co) {
                         const float v = valid[tt] ? m : 0.f;
@@ -430,7 +445,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 }
 
 // w [R, Kreal] fp32 row-major -> bf16 [NB][Kp/8][128][8] (zero padded): every ring slice contiguous
+// bias_col (may be NULL): an extra column Kreal holding bias[row] (b1 rides in the contraction);
+// neg_if (may be NULL): rows with neg_if[row] < 0 are stored negated (W2 rows of negative BN scale).
 __global__ void prepack_kernel(const float *__restrict__ w, int R, int Kreal, int NB, int Kp,
+                               const float *__restrict__ bias_col, const float *__restrict__ neg_if,
                                __nv_bfloat16 *__restrict__ out) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = static_cast<int64_t>(NB) * Kp * 128;
@@ -440,7 +458,13 @@ __global__ void prepack_kernel(const float *__restrict__ w, int R, int Kreal, in
     const int kc = static_cast<int>((idx >> 10) % (Kp >> 3));
     const int blk = static_cast<int>((idx >> 10) / (Kp >> 3));
     const int row = blk * 128 + r, k = kc * 8 + e;
-    out[idx] = __float2bfloat16((row < R && k < Kreal) ? w[static_cast<int64_t>(row) * Kreal + k] : 0.f);
+    float v = 0.f;
+    if (row < R) {
+        if (k < Kreal) v = w[static_cast<int64_t>(row) * Kreal + k];
+        else if (k == Kreal && bias_col) v = bias_col[row];
+        if (neg_if && neg_if[row] < 0.f) v = -v;
+    }
+    out[idx] = __float2bfloat16(v);
 }
 
 __global__ void padvec_kernel(const float *__restrict__ v, int n, int np, float *__restrict__ out) {
@@ -456,7 +480,7 @@ struct TcPlan {
 };
 inline TcPlan tc_plan(int c_in, int hidden, int c_out) {
     TcPlan t;
-    t.K1p = round_up(c_in + 4, SLICE_K);
+    t.K1p = round_up(c_in + 5, SLICE_K);       // + the constant-one column that carries b1
     t.NB1 = (hidden + 127) / 128;
     t.NB2 = (c_out + 127) / 128;
     t.w1_bytes = static_cast<size_t>(t.NB1) * t.K1p * 128 * 2;
@@ -519,8 +543,8 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     float *shp = reinterpret_cast<float *>(base + t.off_shift);
     if (!packed) {
         const int64_t n1 = static_cast<int64_t>(t.NB1) * t.K1p * 128, n2 = static_cast<int64_t>(t.NB2) * hidden * 128;
-        P2W_LAUNCH(prepack_kernel, (unsigned)((n1 + 255) / 256), 256, 0, st)(w1, hidden, c_in + 4, t.NB1, t.K1p, w1p);
-        P2W_LAUNCH(prepack_kernel, (unsigned)((n2 + 255) / 256), 256, 0, st)(w2, c_out, hidden, t.NB2, hidden, w2p);
+        P2W_LAUNCH(prepack_kernel, (unsigned)((n1 + 255) / 256), 256, 0, st)(w1, hidden, c_in + 4, t.NB1, t.K1p, b1, nullptr, w1p);
+        P2W_LAUNCH(prepack_kernel, (unsigned)((n2 + 255) / 256), 256, 0, st)(w2, c_out, hidden, t.NB2, hidden, nullptr, bn_scale, w2p);
         P2W_LAUNCH(padvec_kernel, (t.NB1 * 128 + 255) / 256, 256, 0, st)(b1, hidden, t.NB1 * 128, b1p);
         P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(b2, c_out, t.NB2 * 128, b2p);
         P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(bn_scale, c_out, t.NB2 * 128, scp);
