@@ -45,7 +45,8 @@ constexpr int EPI_THREADS = 128;                // warps 0-3 (one TMEM lane quar
 constexpr int GATHER_WARPS = 4;                 // warps 4-7
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
 constexpr int THREADS = EPI_THREADS + GATHER_THREADS + 64;
-constexpr int VALID_SLOTS = 4;                  // per-target validity flags of the tiles in flight
+constexpr int VALID_SLOTS = 8;                  // per-target validity flags of the tiles in flight
+constexpr int MAX_MSG_BUFS = 3;                 // msg tiles the gather warps may run ahead of layer 1
 constexpr int LBO1 = NT * 16 + 16;             // k-chunk stride of the msg tile, padded against bank conflicts
 constexpr int TMEM_COLS = 2 * NT;
 constexpr unsigned FULL = 0xffffffffu;
@@ -59,6 +60,7 @@ struct ConvTcParams {
     const int32_t *nbr;
     int64_t n_tgt;
     int K, C, H, Co, K1p, NB1, NB2, num_tiles, x_bf16, out_bf16;
+    int msg_bufs;                  // msg tiles in shared memory (the gather runs msg_bufs - 1 tiles ahead)
     int stages, resident;          // ring depth; resident: the ring holds ALL weight slices, loaded once
     int debug;                     // timing experiments only (P2W_CONV_DEBUG): 1 no weight re-streaming, 2 no feature gather
     const unsigned char *wpack;
@@ -129,23 +131,25 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {   // low 
 struct SmemLayout {
     uint32_t ring, b1, b2, sj, svalid, bars, tmem, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int K1p, int H, int stages) {
+__host__ __device__ inline uint32_t msg_tile_bytes(int K1p) { return ((K1p / 8) * LBO1 + 127u) & ~127u; }
+__host__ __device__ inline SmemLayout smem_layout(int K1p, int H, int stages, int msg_bufs) {
     SmemLayout L;
     L.ring = 0;
     L.b1 = L.ring + stages * SLICE_BYTES;
-    L.b2 = L.b1 + (K1p / 8) * LBO1;
-    L.b2 = (L.b2 + 127u) & ~127u;
+    L.b2 = L.b1 + msg_bufs * msg_tile_bytes(K1p);
     L.sj = L.b2 + (NT / 8) * (H * 16);
-    L.svalid = L.sj + NT * 4;
+    L.svalid = L.sj + 2 * NT * 4;
     L.bars = (L.svalid + VALID_SLOTS * TPT * 4 + 7u) & ~7u;
-    L.tmem = L.bars + 8 * (2 * MAX_STAGES + 8);
+    L.tmem = L.bars + 8 * (2 * MAX_STAGES + 6 + 2 * MAX_MSG_BUFS);
     L.total = L.tmem + 16;
     return L;
 }
 
 __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const SmemLayout L = smem_layout(p.K1p, p.H, p.stages);
+    const SmemLayout L = smem_layout(p.K1p, p.H, p.stages, p.msg_bufs);
+    const int MB = p.msg_bufs;
+    const uint32_t msg_bytes = msg_tile_bytes(p.K1p);
     const int STAGES = p.stages;
     unsigned char *ring = smem + L.ring;
     unsigned char *b1 = smem + L.b1;
@@ -155,7 +159,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     uint64_t *ring_full = bars, *ring_empty = bars + MAX_STAGES;
     uint64_t *acc_full = bars + 2 * MAX_STAGES, *acc_empty = acc_full + 2;
-    uint64_t *b1_full = acc_empty + 2, *b1_empty = b1_full + 1, *b2_full = b1_full + 2, *b2_empty = b1_full + 3;
+    uint64_t *b2_full = acc_empty + 2, *b2_empty = b2_full + 1;
+    uint64_t *b1_full = b2_empty + 1, *b1_empty = b1_full + MAX_MSG_BUFS;      // one pair per msg buffer
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L.tmem);
 
     const int warp = __shfl_sync(FULL, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
@@ -165,8 +170,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_THREADS); }
-        mbar_init(b1_full, GATHER_THREADS);
-        mbar_init(b1_empty, 1);
+        for (int m = 0; m < MAX_MSG_BUFS; m++) { mbar_init(&b1_full[m], GATHER_THREADS); mbar_init(&b1_empty[m], 1); }
         mbar_init(b2_full, EPI_THREADS);
         mbar_init(b2_empty, 1);
         fence_barrier_init();
@@ -178,9 +182,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // K padding of the msg tile (chunks after the geometry chunk) is zero for the whole kernel
-    for (int i = threadIdx.x; i < (kchunks - (p.C >> 3) - 1) * NT; i += THREADS) {
-        const int kc = (p.C >> 3) + 1 + i / NT, n = i % NT;
-        *reinterpret_cast<uint4 *>(b1 + kc * LBO1 + n * 16) = make_uint4(0, 0, 0, 0);
+    for (int m = 0; m < MB; m++) {
+        for (int i = threadIdx.x; i < (kchunks - (p.C >> 3) - 1) * NT; i += THREADS) {
+            const int kc = (p.C >> 3) + 1 + i / NT, n = i % NT;
+            *reinterpret_cast<uint4 *>(b1 + m * msg_bytes + kc * LBO1 + n * 16) = make_uint4(0, 0, 0, 0);
+        }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -217,8 +223,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         // ------------------------------------------------ MMA issuer: warp-uniform loop, one elected lane
         // issues; descriptors advance by increments (a lone issuing warp is latency-bound on every
         // dependent instruction, so the per-slice body must stay a few instructions long).
-        int slot = 0, acc = 0;
-        uint32_t ph = 0, tph = 0, use0 = 0, use1 = 0;
+        int slot = 0, acc = 0, mbuf = 0;
+        uint32_t ph = 0, tph = 0, mph = 0, use0 = 0, use1 = 0;
         const uint64_t a_desc0 = smem_desc(smem_u32(ring), 2048, 128);            // + slot * 512 (+ 256 for kk = 1)
         const uint64_t b1_desc0 = smem_desc(smem_u32(b1), LBO1, 128);             // + s * 4 LBO1/16 (+ 2 LBO1/16)
         const uint64_t b2_desc0 = smem_desc(smem_u32(b2), 128, p.H * 16);         // + s * 32 (+ 16)
@@ -231,11 +237,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 #pragma unroll 1
             for (int layer = 0; layer < 2; layer++) {
                 P2W_TS(1 + layer);
-                mbar_wait(layer == 0 ? b1_full : b2_full, tph);
+                mbar_wait(layer == 0 ? &b1_full[mbuf] : b2_full, layer == 0 ? mph : tph);
                 tc_fence_after();
                 P2W_TS(3 + layer);
                 const int nb = layer == 0 ? p.NB1 : p.NB2, ns = layer == 0 ? n1 : n2;
-                const uint64_t b_desc0 = layer == 0 ? b1_desc0 : b2_desc0;
+                const uint64_t b_desc0 = layer == 0 ? b1_desc0 + static_cast<uint32_t>(mbuf) * (msg_bytes >> 4) : b2_desc0;
                 const uint32_t b_step = layer == 0 ? 4u * (LBO1 >> 4) : 32u, b_half = b_step >> 1;
                 const uint32_t idesc = layer == 0 ? ID1 : ID2;
                 for (int blk = 0; blk < nb; blk++) {
@@ -263,48 +269,73 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                     if (acc) use1++; else use0++;
                     acc ^= 1;
                 }
-                if (elect_one()) umma_commit(layer == 0 ? b1_empty : b2_empty);
+                if (elect_one()) umma_commit(layer == 0 ? &b1_empty[mbuf] : b2_empty);
             }
             tph ^= 1;
+            if (++mbuf == MB) { mbuf = 0; mph ^= 1; }
         }
         if (rec && lane == 0) g_timeline[0] = nrec;
 #undef P2W_TS
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------ gather warps: one tile ahead of the MMAs
-        uint32_t tph = 0;
+        uint32_t mph = 0;
+        int mbuf = 0;
         const int gw = warp - 4;
         const int CPR = p.C >> 3;
         const int cpr_c = CPR < 32 ? CPR : 32;
         const int rpw = 32 / cpr_c;
         const int ck = lane % cpr_c, ri = lane / cpr_c;
+        // Software pipeline over tiles (this warp owns target gw of every tile): the neighbour row of tile
+        // it+2 and the source positions of tile it+1 are in flight while the features of tile it are fetched,
+        // so a tile costs one global-load latency instead of a chain of three.
+        static_assert(TPT == GATHER_WARPS, "one gather warp per target of a tile");
+        auto load_row = [&](int it, int &j, unsigned &m, float4 &pt) {
+            j = -1;
+            pt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < my_tiles) {
+                const int64_t t = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x) * TPT + gw;
+                if (t < p.n_tgt) {
+                    if (lane < p.K) j = p.nbr[t * p.K + lane];
+                    pt = __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + t);
+                }
+            }
+            m = __ballot_sync(FULL, j >= 0);
+            const int jf = m ? __shfl_sync(FULL, j, __ffs(m) - 1) : 0;
+            if (j < 0) j = jf;                     // padded slot: duplicate a valid edge (max unchanged)
+        };
+        int j0, j1, j2;
+        unsigned m0, m1, m2;
+        float4 pt0, pt1, pt2, ps0, ps1;
+        load_row(0, j0, m0, pt0);
+        load_row(1, j1, m1, pt1);
+        ps0 = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j0);
         for (int it = 0; it < my_tiles; it++) {
             const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
             const int64_t t0 = static_cast<int64_t>(tile) * TPT;
-            gather_bar();                          // every gather warp is done with s_j of the previous tile
-            mbar_wait(b1_empty, tph ^ 1);          // layer 1 of the previous tile no longer reads the msg tile
-            for (int tw = gw; tw < TPT; tw += GATHER_WARPS) {
-                const int64_t t = t0 + tw;
-                int j = (t < p.n_tgt && lane < p.K) ? p.nbr[t * p.K + lane] : -1;
-                const unsigned m = __ballot_sync(FULL, j >= 0);
-                const int jf = m ? __shfl_sync(FULL, j, __ffs(m) - 1) : 0;
-                if (j < 0) j = jf;                 // padded slot: duplicate a valid edge (max unchanged)
-                const int n = tw * 32 + lane;
-                s_j[n] = j;
-                if (lane == 0) s_valid[(it & (VALID_SLOTS - 1)) * TPT + tw] = m ? 1 : 0;
-                const float4 ps = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j);
-                const float4 pt = __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + (t < p.n_tgt ? t : 0));
-                const float dx = ps.x - pt.x, dy = ps.y - pt.y, dz = ps.z - pt.z;
+            (void)t0;
+            unsigned char *msg = b1 + mbuf * msg_bytes;
+            int *sj = s_j + (it & 1) * NT;
+            ps1 = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j1);     // tile it+1
+            load_row(it + 2, j2, m2, pt2);                                      // tile it+2
+            const int n = gw * 32 + lane;
+            sj[n] = j0;
+            if (lane == 0) s_valid[(it & (VALID_SLOTS - 1)) * TPT + gw] = m0 ? 1 : 0;
+            mbar_wait(&b1_empty[mbuf], mph ^ 1);   // layer 1 of the tile that last used this buffer is done
+            {
+                const float dx = ps0.x - pt0.x, dy = ps0.y - pt0.y, dz = ps0.z - pt0.z;
                 float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
                 for (int o = 16; o; o >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(FULL, nrm, o));
                 const float den = nrm + 1e-8f;
                 uint4 g;
                 g.x = pack_bf16(dx / den, dy / den);
-                g.y = pack_bf16(dz / den, ps.w);
+                g.y = pack_bf16(dz / den, ps0.w);
                 g.z = 0x00003F80u;                 // column C+4 = 1.0: carries b1 through the contraction
                 g.w = 0;
-                *reinterpret_cast<uint4 *>(b1 + CPR * LBO1 + n * 16) = g;
+                *reinterpret_cast<uint4 *>(msg + CPR * LBO1 + n * 16) = g;
             }
+            j0 = j1; m0 = m1; pt0 = pt1; ps0 = ps1;
+            j1 = j2; m1 = m2; pt1 = pt2;
             gather_bar();
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
             if (p.debug & 2) {
@@ -316,12 +347,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                     for (int u = 0; u < 4; u++) {
                         const int n = r0 + u * GATHER_WARPS * rpw + ri;
                         if (n < NT && ck < CPR)
-                            v[u] = __ldg(reinterpret_cast<const uint4 *>(xb + static_cast<int64_t>(s_j[n]) * p.C + ck * 8));
+                            v[u] = __ldg(reinterpret_cast<const uint4 *>(xb + static_cast<int64_t>(sj[n]) * p.C + ck * 8));
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const int n = r0 + u * GATHER_WARPS * rpw + ri;
-                        if (n < NT && ck < CPR) *reinterpret_cast<uint4 *>(b1 + ck * LBO1 + n * 16) = v[u];
+                        if (n < NT && ck < CPR) *reinterpret_cast<uint4 *>(msg + ck * LBO1 + n * 16) = v[u];
                     }
                 }
             } else {
@@ -333,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                         const int n = r0 + u * GATHER_WARPS * rpw + ri;
                         if (n < NT && ck < CPR) {
                             const float4 *src =
-                                reinterpret_cast<const float4 *>(xf + static_cast<int64_t>(s_j[n]) * p.C + ck * 8);
+                                reinterpret_cast<const float4 *>(xf + static_cast<int64_t>(sj[n]) * p.C + ck * 8);
                             lo[u] = __ldg(src);
                             hi[u] = __ldg(src + 1);
                         }
@@ -347,14 +378,14 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                             v.y = pack_bf16(lo[u].z, lo[u].w);
                             v.z = pack_bf16(hi[u].x, hi[u].y);
                             v.w = pack_bf16(hi[u].z, hi[u].w);
-                            *reinterpret_cast<uint4 *>(b1 + ck * LBO1 + n * 16) = v;
+                            *reinterpret_cast<uint4 *>(msg + ck * LBO1 + n * 16) = v;
                         }
                     }
                 }
             }
             fence_proxy_async();
-            mbar_arrive(b1_full);
-            tph ^= 1;
+            mbar_arrive(&b1_full[mbuf]);
+            if (++mbuf == MB) { mbuf = 0; mph ^= 1; }
         }
     } else {
         // ------------------------------------------------ epilogue warps (TMEM lane quarter q = warp)
@@ -522,16 +553,26 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     // whatever shared memory the tiles leave: all of it when one CTA per SM is the only option, up to
     // the two-CTAs-per-SM budget otherwise.  A layer whose slices all fit (SA1) keeps them resident.
     const int per_tile = t.NB1 * (t.K1p / SLICE_K) + t.NB2 * (hidden / SLICE_K);
-    const unsigned fixed = smem_layout(t.K1p, hidden, 0).total;
     const unsigned budget2 = 113u * 1024u, budget1 = 227u * 1024u;
-    int stages;
-    if (fixed + 4u * SLICE_BYTES <= budget2) stages = static_cast<int>((budget2 - fixed) / SLICE_BYTES);
-    else stages = fixed + 2u * SLICE_BYTES <= budget1 ? static_cast<int>((budget1 - fixed) / SLICE_BYTES) : 0;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    const int resident = per_tile <= stages ? 1 : 0;
-    if (resident) stages = per_tile;
-    P2W_REQUIRE(stages >= 2, "p2w_pointnet_conv_max(bf16): layer too wide for one CTA (%u bytes of tiles)", fixed);
-    const SmemLayout L = smem_layout(t.K1p, hidden, stages);
+    // msg buffers: the gather (three dependent global loads per tile) runs ahead of layer 1 when the tiles
+    // leave room for a second / third msg tile next to a weight ring of useful depth.
+    int msg_bufs = 1, stages = 0, resident = 0;
+    for (int mb = MAX_MSG_BUFS; mb >= 1; mb--) {
+        const unsigned fixed = smem_layout(t.K1p, hidden, 0, mb).total;
+        int st;
+        if (fixed + 4u * SLICE_BYTES <= budget2) st = static_cast<int>((budget2 - fixed) / SLICE_BYTES);
+        else st = fixed + 2u * SLICE_BYTES <= budget1 ? static_cast<int>((budget1 - fixed) / SLICE_BYTES) : 0;
+        if (st > MAX_STAGES) st = MAX_STAGES;
+        const int res = per_tile <= st ? 1 : 0;
+        if (res || st >= 8 || mb == 1) {
+            msg_bufs = mb;
+            stages = res ? per_tile : st;
+            resident = res;
+            break;
+        }
+    }
+    P2W_REQUIRE(stages >= 2, "p2w_pointnet_conv_max(bf16): layer too wide for one CTA");
+    const SmemLayout L = smem_layout(t.K1p, hidden, stages, msg_bufs);
     P2W_REQUIRE(L.total <= 227 * 1024, "p2w_pointnet_conv_max(bf16): layer too wide for one CTA (%u bytes smem)",
                 L.total);
     unsigned char *base = static_cast<unsigned char *>(ws);
@@ -552,7 +593,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     }
     ConvTcParams p;
     p.x_bf16 = x_bf16; p.out_bf16 = out_bf16;
-    p.stages = stages; p.resident = resident;
+    p.stages = stages; p.resident = resident; p.msg_bufs = msg_bufs;
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("P2W_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
