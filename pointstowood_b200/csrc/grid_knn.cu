@@ -605,6 +605,128 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
     }
 }
 
+// ---- k <= 4 (the k = 2 search inside knn_interpolate, src/model.py:149): one THREAD per query.
+// With ~one source per occupied cell the warp-per-query machinery (scan, flatten, ballots) costs far
+// more than the handful of distances a query needs; here a thread walks the 27 cells of its first ring
+// in the same nearest-first order, skips cells that cannot beat its current k-th distance, and keeps
+// its k best keys in registers.  Same keys, same stopping bound, same results.
+__host__ __device__ constexpr int nb_d(unsigned long long lut, int s) { return static_cast<int>((lut >> (2 * s)) & 3ull) - 1; }
+
+template <int K>
+__device__ __forceinline__ void small_insert(key_t (&best)[K], key_t ck) {
+    if (ck < best[K - 1]) {
+        best[K - 1] = ck;
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) {
+            if (best[i] < best[i - 1]) {
+                const key_t t = best[i];
+                best[i] = best[i - 1];
+                best[i - 1] = t;
+            }
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void small_scan(const float4 *__restrict__ spts, uint32_t a, uint32_t e, float qx, float qy,
+                                           float qz, key_t (&best)[K]) {
+    for (uint32_t i = a; i < e; i++) {
+        const float4 c = __ldg(spts + i);
+        const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
+        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        if (d < 1e10f) small_insert<K>(best, (static_cast<key_t>(__float_as_uint(d)) << 32) | __float_as_uint(c.w));
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__restrict__ spts,
+                                                               const uint32_t *__restrict__ cell_start,
+                                                               const GridTile *__restrict__ grid,
+                                                               const float *__restrict__ y,
+                                                               const int64_t *__restrict__ ptr_x,
+                                                               const int64_t *__restrict__ ptr_y, int T, int64_t ny,
+                                                               int32_t *__restrict__ nbr, float *__restrict__ d2out) {
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= ny) return;
+    const int b = find_tile(ptr_y, T, q);
+    const int64_t s0 = ptr_x[b], s1 = ptr_x[b + 1];
+    const float qx = y[q * 3 + 0], qy = y[q * 3 + 1], qz = y[q * 3 + 2];
+    key_t best[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) best[i] = key_sentinel();
+    if (s1 > s0) {
+        const GridTile g = grid[b];
+        const int cx = axis_cell(qx, g.ox, g.inv_h, g.nx);
+        const int cy = axis_cell(qy, g.oy, g.inv_h, g.ny);
+        const int cz = axis_cell(qz, g.oz, g.inv_h, g.nz);
+        const int nmax = max(g.nx, max(g.ny, g.nz));
+        const float margin = 1e-5f * g.h * static_cast<float>(nmax) +
+                             4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz));
+        // safe gaps from the query to the six faces of its own cell
+        const float fx = g.ox + static_cast<float>(cx) * g.h, fy = g.oy + static_cast<float>(cy) * g.h,
+                    fz = g.oz + static_cast<float>(cz) * g.h;
+        const float k1 = 1.f - 1e-4f;
+        const float lox = fmaxf((qx - fx) * k1 - margin, 0.f), hix = fmaxf((fx + g.h - qx) * k1 - margin, 0.f);
+        const float loy = fmaxf((qy - fy) * k1 - margin, 0.f), hiy = fmaxf((fy + g.h - qy) * k1 - margin, 0.f);
+        const float loz = fmaxf((qz - fz) * k1 - margin, 0.f), hiz = fmaxf((fz + g.h - qz) * k1 - margin, 0.f);
+#pragma unroll
+        for (int s = 0; s < 27; s++) {
+            const int ddx = nb_d(NB_DX, s), ddy = nb_d(NB_DY, s), ddz = nb_d(NB_DZ, s);
+            const int xx = cx + ddx, yy = cy + ddy, zz = cz + ddz;
+            if (xx < 0 || xx >= g.nx || yy < 0 || yy >= g.ny || zz < 0 || zz >= g.nz) continue;
+            const float sx = ddx < 0 ? lox : (ddx > 0 ? hix : 0.f);
+            const float sy = ddy < 0 ? loy : (ddy > 0 ? hiy : 0.f);
+            const float sz = ddz < 0 ? loz : (ddz > 0 ? hiz : 0.f);
+            if (sx * sx + sy * sy + sz * sz > __uint_as_float(static_cast<unsigned>(best[K - 1] >> 32))) continue;
+            const int64_t c = g.base + xx + g.nx * (yy + g.ny * zz);
+            small_scan<K>(spts, __ldg(cell_start + c), __ldg(cell_start + c + 1), qx, qy, qz, best);
+        }
+        for (int r = 1;; r++) {
+            if (r > 1) {                               // rare: shells beyond the first ring, row by row
+                for (int dz = -r; dz <= r; dz++) {
+                    const int zz = cz + dz;
+                    if (zz < 0 || zz >= g.nz) continue;
+                    for (int dy = -r; dy <= r; dy++) {
+                        const int yy = cy + dy;
+                        if (yy < 0 || yy >= g.ny) continue;
+                        const bool rim = (dz == -r || dz == r || dy == -r || dy == r);
+                        const int64_t row = g.base + g.nx * (yy + g.ny * zz);
+                        if (rim) {
+                            const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+                            if (x0 <= x1)
+                                small_scan<K>(spts, __ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1), qx, qy,
+                                              qz, best);
+                        } else {
+                            if (cx - r >= 0)
+                                small_scan<K>(spts, __ldg(cell_start + row + cx - r), __ldg(cell_start + row + cx - r + 1),
+                                              qx, qy, qz, best);
+                            if (cx + r < g.nx)
+                                small_scan<K>(spts, __ldg(cell_start + row + cx + r), __ldg(cell_start + row + cx + r + 1),
+                                              qx, qy, qz, best);
+                        }
+                    }
+                }
+            }
+            const int bx0 = cx - r, bx1 = cx + r, by0 = cy - r, by1 = cy + r, bz0 = cz - r, bz1 = cz + r;
+            if (bx0 <= 0 && bx1 >= g.nx - 1 && by0 <= 0 && by1 >= g.ny - 1 && bz0 <= 0 && bz1 >= g.nz - 1) break;
+            float bd = 3.0e38f;
+            if (bx0 > 0) bd = fminf(bd, qx - (g.ox + static_cast<float>(bx0) * g.h));
+            if (bx1 < g.nx - 1) bd = fminf(bd, (g.ox + static_cast<float>(bx1 + 1) * g.h) - qx);
+            if (by0 > 0) bd = fminf(bd, qy - (g.oy + static_cast<float>(by0) * g.h));
+            if (by1 < g.ny - 1) bd = fminf(bd, (g.oy + static_cast<float>(by1 + 1) * g.h) - qy);
+            if (bz0 > 0) bd = fminf(bd, qz - (g.oz + static_cast<float>(bz0) * g.h));
+            if (bz1 < g.nz - 1) bd = fminf(bd, (g.oz + static_cast<float>(bz1 + 1) * g.h) - qz);
+            const float bs = bd * (1.f - 1e-4f) - margin;
+            if (bs > 0.f && __uint_as_float(static_cast<unsigned>(best[K - 1] >> 32)) < bs * bs) break;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        nbr[q * K + i] = static_cast<int32_t>(static_cast<uint32_t>(best[i]));
+        if (d2out) d2out[q * K + i] = __uint_as_float(static_cast<unsigned>(best[i] >> 32));
+    }
+}
+
 struct GridWs {
     GridTile *grid;
     uint32_t *slot, *cell_start, *fill, *bsum;
@@ -659,6 +781,13 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
         P2W_LAUNCH(scan32_single_kernel, 1, 1024, 0, st)(w.bsum, nb);
         P2W_LAUNCH(scan32_apply_kernel, (unsigned)nb, SC_T, 0, st)(w.cell_start, w.table, w.bsum, w.cell_start);
         P2W_LAUNCH(grid_scatter_kernel, blocks, 256, 0, st)(x, nx, w.slot, w.cell_start, w.fill, w.spts);
+    }
+    if (!radius && k <= 4) {                              // thread per query
+        const unsigned gs = static_cast<unsigned>((ny + 255) / 256);
+#define P2W_GS(KK) P2W_LAUNCH((grid_query_small_kernel<KK>), gs, 256, 0, st)(w.spts, w.cell_start, w.grid, y, ptr_x, ptr_y, T, ny, nbr, d2)
+        if (k == 1) P2W_GS(1); else if (k == 2) P2W_GS(2); else if (k == 3) P2W_GS(3); else P2W_GS(4);
+#undef P2W_GS
+        return check_launch(what);
     }
     int64_t blocks = ((ny + 31) / 32 + 7) / 8;          // a warp takes 32 queries at a time
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
