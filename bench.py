@@ -42,6 +42,16 @@ N_POINTS = 1_000_000
 CFG = dict(grid_size=(2.0, 4.0), min_pts=128, max_pts=16384, batch_size=8, is_wood=0.5)
 
 
+def load_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernels, from the
+    committed `ncu --set full` capture of this workload (profiles/traffic.json; null if absent)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -213,7 +223,7 @@ def main():
     out_pred = torch.empty(tile_points, dtype=torch.uint8).pin_memory()
 
     # ---- device-resident steps, dominant kernel timed live with CUDA events
-    ops.KERNEL_TIMER.reset("p2w_pointnet_conv_max" if bf16 else "p2w_knn")
+    ops.KERNEL_TIMER.reset("p2w_pointnet_conv_max", "p2w_knn")
     barrier()
     launches0 = L.p2w_launch_count()
     with ClockSampler(local) as clk:
@@ -225,8 +235,8 @@ def main():
         barrier()
     launches = L.p2w_launch_count() - launches0
     ms = ev0.elapsed_time(ev1) / args.steps
-    kt = ops.KERNEL_TIMER.summary()
-    ops.KERNEL_TIMER.reset(None)
+    kt_conv, kt_knn = ops.KERNEL_TIMER.summary("p2w_pointnet_conv_max"), ops.KERNEL_TIMER.summary("p2w_knn")
+    ops.KERNEL_TIMER.reset()
 
     # ---- end to end through the host-facing API (pinned host in, host out)
     barrier()
@@ -247,31 +257,42 @@ def main():
     ms, ms_e2e = t.tolist()
 
     if rank == 0:
-        roof = None
-        if kt["launches"]:
-            per_launch_ms = kt["ms"] / kt["launches"]
-            if bf16:
-                achieved = kt["work"] / kt["launches"] / per_launch_ms / 1e9          # TFLOP/s
-                roof = dict(kernel="conv_tc_kernel (fused gather-MLP-max, tcgen05)", bound="tensor", achieved=achieved,
-                            peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
-                            peak_source=f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
-                            traffic=None, launches=kt["launches"], avg_launch_ms=per_launch_ms)
-            else:
-                achieved = kt["work"] / kt["launches"] / per_launch_ms / 1e6          # GB/s
-                roof = dict(kernel="sweep_kernel (kNN)", bound="hbm", achieved=achieved, peak=peaks["hbm"],
-                            unit="GB/s", frac=achieved / peaks["hbm"], peak_source=peaks["src"], traffic=None,
-                            launches=kt["launches"], avg_launch_ms=per_launch_ms)
+        traffic = load_traffic()
+        roof_conv = roof_knn = None
+        if kt_conv["launches"]:
+            per_launch_ms = kt_conv["ms"] / kt_conv["launches"]
+            achieved = kt_conv["work"] / kt_conv["launches"] / per_launch_ms / 1e9              # TFLOP/s
+            peak = peaks["bf16_sustained"] if bf16 else None
+            roof_conv = dict(kernel="conv_tc_kernel (fused gather-MLP-max, tcgen05)" if bf16 else
+                             "conv_simt_kernel (fused gather-MLP-max, FP32 parity mode)",
+                             bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s",
+                             frac=achieved / peak if peak else None,
+                             peak_source=f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
+                             traffic=traffic.get("conv_tc_kernel") if bf16 else None,
+                             work="FLOPs = 32 n_tgt (2 (C+4) H + 2 H C') per launch, unpadded (SURVEY.md 8d)",
+                             launches=kt_conv["launches"], avg_launch_ms=per_launch_ms)
+        if kt_knn["launches"]:
+            per_launch_ms = kt_knn["ms"] / kt_knn["launches"]
+            achieved = kt_knn["work"] / kt_knn["launches"] / per_launch_ms / 1e6                # GB/s
+            roof_knn = dict(kernel="p2w_knn (cell-list / sweep kNN, build + query)", bound="hbm", achieved=achieved,
+                            peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"], peak_source=peaks["src"],
+                            traffic=traffic.get("grid_query_kernel"),
+                            work="bytes = 12 (Nx + Ny) + 16 Ny k + 16 (B+1) per call (SURVEY.md 8d)",
+                            launches=kt_knn["launches"], avg_launch_ms=per_launch_ms)
+        roof = roof_conv if bf16 else roof_knn
         line = dict(metric="points classified/sec", value=world * n_points / (ms / 1e3), unit="points/s", n_gpus=world,
                     steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="bf16" if bf16 else "f32", data="synthetic",
                     config=dict(workload=f"predict {n_points}-point synthetic TLS plot per GPU, grid 2/4 m, min_pts 128, "
                                          "max_pts 16384, batch_size 8, seeded weights",
                                 tile_points=tile_points, tiles=int(store.num_tiles),
-                                l2="inputs larger than L2 are not guaranteed: every step re-tiles and re-packs the "
-                                   "whole plot (writes > 126 MB of intermediates) between kernel repeats"),
+                                launch_points=args.launch_points,
+                                l2="no flush needed: a step streams > 4 GB of activations (e.g. the [N0, 544] and "
+                                   "[N0, 512] FP buffers) between two launches of any kernel, 30x the 126 MB L2"),
                     e2e=dict(value=world * n_points / (ms_e2e / 1e3), unit="points/s", h2d_bytes_per_step=int(host.numel() * 4),
                              d2h_bytes_per_step=int(tile_points * 5)),
-                    gpu_launches=int(launches), clocks=clk.summary(), roofline=roof)
+                    gpu_launches=int(launches), clocks=clk.summary(), roofline=roof,
+                    roofline_knn=roof_knn if bf16 else roof_conv)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_arm(n_points, 1, budget_s=15.0)
         print(json.dumps(line))

@@ -40,28 +40,30 @@ def _stream() -> int:
 
 class _KernelTimer:
     """bench.py's live roofline probe: CUDA-event pairs on the launching stream around every call
-    of ONE chosen C-ABI entry point, with the algorithmic work (bytes or FLOPs) of each call."""
+    of the chosen C-ABI entry points, with the algorithmic work (bytes or FLOPs) of each call."""
 
     def __init__(self):
-        self.target, self.pairs, self.work = None, [], 0.0
+        self.targets = {}
 
-    def reset(self, target):
-        self.target, self.pairs, self.work = target, [], 0.0
+    def reset(self, *targets):
+        self.targets = {t: dict(pairs=[], work=0.0) for t in targets if t}
 
     def call(self, name, work, fn, *args):
-        if self.target != name:
+        rec = self.targets.get(name)
+        if rec is None:
             return fn(*args)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        self.pairs.append((e0, e1))
-        self.work += work
+        rec["pairs"].append((e0, e1))
+        rec["work"] += work
         return rc
 
-    def summary(self):
+    def summary(self, name):
         torch.cuda.synchronize()
-        return dict(launches=len(self.pairs), ms=sum(a.elapsed_time(b) for a, b in self.pairs), work=self.work)
+        rec = self.targets.get(name, dict(pairs=[], work=0.0))
+        return dict(launches=len(rec["pairs"]), ms=sum(a.elapsed_time(b) for a, b in rec["pairs"]), work=rec["work"])
 
 
 KERNEL_TIMER = _KernelTimer()
