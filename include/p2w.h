@@ -71,6 +71,12 @@ size_t p2w_grid_search_ws_bytes(int64_t nx, int32_t num_tiles);
 int p2w_knn_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
                  int32_t num_tiles, int64_t nx, int64_t ny, int32_t k,
                  int32_t *nbr, float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream);
+/* Same with the cell size given by the caller (cell_size > 0, enlarged until the cell table fits 4 cells
+ * per source, at most 1024 cells per axis): plot-wide searches such as the spatial vote, where one
+ * "tile" holds millions of points and the occupancy pyramid's 64 cells per axis are too coarse. */
+int p2w_knn_grid_ex(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
+                    int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, float cell_size,
+                    int32_t *nbr, float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream);
 int p2w_radius_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
                     int32_t num_tiles, int64_t nx, int64_t ny, double r, int32_t max_nbr,
                     int32_t *nbr, int32_t *cnt, void *ws, size_t ws_bytes, p2w_stream_t stream);
@@ -226,6 +232,14 @@ int p2w_pack(const float *cloud, int32_t ld, const int64_t *index, const int64_t
 int p2w_writeback(const float *logits, const float *pos, const int64_t *ptr,
                   const float *local_shift, int32_t num_tiles, int64_t m, float is_wood,
                   double *out64, float *prob, uint8_t *pred, p2w_stream_t stream);
+
+/* ---- spatial vote (src/predicter.py:113-142, PointCloudClassifier.compute_labels) -------------
+ * For every original point q and its k nearest CLASSIFIED points nbr[q, :] (from p2w_knn_grid_ex
+ * over the whole plot; -1 = missing): pwood[q] = median of prob[nbr] (np.median, float64);
+ * label[q] = (any_wood == 1) ? (sum of prob over pred == 1) > (sum over pred == 0)
+ *                            : any(pred[nbr] > any_wood).   k <= 128. */
+int p2w_spatial_vote(const int32_t *nbr, int64_t n, int32_t k, const float *prob, const uint8_t *pred,
+                     float any_wood, uint8_t *label, double *pwood, p2w_stream_t stream);
 
 /* ---- K6: tiling front end (src/preprocessing.py:18-64, 116-120) ---------------------------
  * p2w_ground_normalize (gpu_ground, :37-53): 5 m XY cells with edges x_min + 5 i (bucketize:

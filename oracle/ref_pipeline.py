@@ -143,3 +143,24 @@ def classify(sd, feat5, tiles, batch_size=8, is_wood=0.5, max_batches=None):
         out.append(np.concatenate([xyz, pred[:, None], prob.astype(np.float64)[:, None]], 1))
         nb += 1
     return np.concatenate(out) if out else np.zeros((0, 5))
+
+
+def collect_predictions(classification, original_xyz, any_wood=1):
+    """PointCloudClassifier.collect_predictions + compute_labels (src/predicter.py:113-142): float64 KD-tree
+    over the classified rows (pykdtree in the reference, scipy's cKDTree here: same exact k nearest
+    neighbours up to ties), k = 64 (32 if any_wood != 1); pwood = np.median of the neighbours'
+    probabilities; label = argmax over the class votes sum_{pred == c} prob (any_wood == 1), else
+    any(pred > any_wood).  Returns (label float64 [N], pwood float64 [N])."""
+    from scipy.spatial import cKDTree
+    k = 32 if any_wood != 1 else 64
+    tree = cKDTree(classification[:, :3])
+    _, idx = tree.query(np.asarray(original_xyz, dtype=np.float64)[:, :3], k=k)
+    nb = classification[idx]                                   # [N, k, 5]
+    pwood = np.median(nb[:, :, -1], axis=1)
+    if any_wood != 1:
+        label = (nb[:, :, -2] > any_wood).any(axis=1).astype(np.float64)
+    else:
+        votes = np.stack([((nb[:, :, -2] == c) * nb[:, :, -1]).sum(axis=1) for c in (0, 1)], axis=1)
+        # the reference sizes class_votes by k (SURVEY.md Appendix C.10): classes >= 2 never occur, argmax = first max
+        label = np.argmax(votes, axis=1).astype(np.float64)
+    return label, pwood

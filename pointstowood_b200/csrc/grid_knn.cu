@@ -33,7 +33,8 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int GL_MAX = 6;        // finest planning level: 64 cells along the longest axis
-constexpr int GDIM_MAX = 64;
+constexpr int GDIM_MAX = 64;        // cells per axis when the cell size is planned from the occupancy pyramid
+constexpr int GDIM_HINT_MAX = 1024; // ... and when the caller gives the cell size (plot-wide searches)
 constexpr int MERGE_MIN = 5;      // survivors per step above which the step is sorted and merged at once
 
 struct __align__(16) GridTile {
@@ -59,7 +60,7 @@ __device__ __forceinline__ unsigned spread6(unsigned v) {   // 6 bits -> every t
 
 // ------------------------------------------------------------------ plan: one CTA per tile
 __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict__ x,
-                                                        const int64_t *__restrict__ ptr_x, float tau,
+                                                        const int64_t *__restrict__ ptr_x, float tau, float cell_hint,
                                                         GridTile *__restrict__ grid) {
     __shared__ unsigned bits[8192];          // 64^3 occupancy bits, Morton order
     __shared__ float s_lo[16][3], s_hi[16][3];
@@ -110,6 +111,22 @@ __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict_
         g.ox = g.oy = g.oz = 0.f;
     } else if (n <= 32 || !(maxext > 0.f) || !(maxext < 1e30f)) {
         g.h = (maxext > 0.f && maxext < 1e30f) ? maxext * 1.0001f : 1.f;      // one cell: brute force inside the tile
+    } else if (cell_hint > 0.f) {
+        // the caller knows the scale (plot-wide searches): start from its cell size, respect the table cap
+        float h = cell_hint;
+        const int64_t cap = n * 4 > 64 ? n * 4 : 64;
+        for (;;) {
+            const float fx = ex / h, fy = ey / h, fz = ez / h;
+            if (fx < static_cast<float>(GDIM_HINT_MAX) && fy < static_cast<float>(GDIM_HINT_MAX) &&
+                fz < static_cast<float>(GDIM_HINT_MAX)) {
+                g.nx = static_cast<int>(fx) + 1;
+                g.ny = static_cast<int>(fy) + 1;
+                g.nz = static_cast<int>(fz) + 1;
+                if (static_cast<int64_t>(g.nx) * g.ny * g.nz <= cap) break;
+            }
+            h *= 1.26f;
+        }
+        g.h = h;
     } else {
         const float scale = 64.f / maxext;
         for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
@@ -758,8 +775,8 @@ inline GridWs grid_ws(void *base, int64_t nx, int T) {
 }
 
 int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y, int T, int64_t nx,
-                int64_t ny, int k, float r2, bool radius, int32_t *nbr, float *d2, int32_t *cnt, void *ws,
-                size_t ws_bytes, cudaStream_t st, const char *what) {
+                int64_t ny, int k, float r2, bool radius, float cell_hint, int32_t *nbr, float *d2, int32_t *cnt,
+                void *ws, size_t ws_bytes, cudaStream_t st, const char *what) {
     P2W_REQUIRE(T >= 1 && nx >= 0 && ny >= 0, "%s: bad sizes", what);
     P2W_REQUIRE(nx < (int64_t(1) << 29), "%s: nx must stay below 2^29 sources per call", what);
     P2W_REQUIRE(T < (1 << 24), "%s: too many tiles", what);
@@ -768,7 +785,8 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
     P2W_REQUIRE(ws != nullptr && ws_bytes >= w.total && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0,
                 "%s: workspace too small or misaligned (%zu bytes needed)", what, w.total);
     const float tau = fmaxf(1.f, 0.45f * static_cast<float>(k));
-    P2W_LAUNCH(grid_plan_kernel, T, 512, 0, st)(x, ptr_x, tau, w.grid);
+    P2W_REQUIRE(cell_hint >= 0.f && cell_hint < 1e30f, "%s: bad cell size", what);
+    P2W_LAUNCH(grid_plan_kernel, T, 512, 0, st)(x, ptr_x, tau, cell_hint, w.grid);
     P2W_LAUNCH(grid_base_kernel, 1, 1024, 0, st)(w.grid, T);
     // cell_start and fill are adjacent: one memset clears both
     cudaMemsetAsync(w.cell_start, 0, reinterpret_cast<unsigned char *>(w.fill + w.table) -
@@ -811,12 +829,18 @@ extern "C" size_t p2w_grid_search_ws_bytes(int64_t nx, int32_t num_tiles) {
     return grid_ws(nullptr, nx < 0 ? 0 : nx, num_tiles < 1 ? 1 : num_tiles).total;
 }
 
+extern "C" int p2w_knn_grid_ex(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
+                               int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, float cell_size, int32_t *nbr,
+                               float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream) {
+    P2W_REQUIRE(k >= 1 && k <= P2W_MAX_K, "p2w_knn_grid: k=%d outside [1,%d]", k, P2W_MAX_K);
+    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, false, cell_size, nbr, d2, nullptr, ws, ws_bytes,
+                       as_stream(stream), "p2w_knn_grid");
+}
+
 extern "C" int p2w_knn_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
                             int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, int32_t *nbr, float *d2, void *ws,
                             size_t ws_bytes, p2w_stream_t stream) {
-    P2W_REQUIRE(k >= 1 && k <= P2W_MAX_K, "p2w_knn_grid: k=%d outside [1,%d]", k, P2W_MAX_K);
-    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, false, nbr, d2, nullptr, ws, ws_bytes,
-                       as_stream(stream), "p2w_knn_grid");
+    return p2w_knn_grid_ex(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, nbr, d2, ws, ws_bytes, stream);
 }
 
 extern "C" int p2w_radius_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
@@ -825,6 +849,6 @@ extern "C" int p2w_radius_grid(const float *x, const float *y, const int64_t *pt
     P2W_REQUIRE(max_nbr >= 1 && max_nbr <= P2W_MAX_K, "p2w_radius_grid: max_num_neighbors=%d outside [1,%d]", max_nbr,
                 P2W_MAX_K);
     const float r2 = static_cast<float>(r * r);   // upstream passes r*r (double) into a float argument
-    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, max_nbr, r2, true, nbr, nullptr, cnt, ws, ws_bytes,
+    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, max_nbr, r2, true, 0.f, nbr, nullptr, cnt, ws, ws_bytes,
                        as_stream(stream), "p2w_radius_grid");
 }

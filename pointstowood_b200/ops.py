@@ -26,7 +26,7 @@ from . import _lib
 __all__ = [
     "batch_to_ptr", "knn", "radius", "fps", "grid_cluster", "voxel_grid", "consecutive_cluster",
     "knn_interpolate", "knn_interpolate_cat", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
-    "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback",
+    "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback", "spatial_vote",
     "sort_pairs", "affine_relu_", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
 ]
 
@@ -118,7 +118,7 @@ def _grid_ws(nx: int, tiles: int, dev) -> Tensor:
 
 
 def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return_d2: bool = False,
-              method: Optional[str] = None):
+              method: Optional[str] = None, cell_size: float = 0.0):
     """[Ny, k] int32 table of the k nearest x rows of every y row inside its tile, ordered by
     (FP32 squared distance, index); -1 padded.  No host sync.  method: 'sweep' (tile-resident brute
     force), 'grid' (per-tile cell list) or None (pick by sources per tile); same result either way."""
@@ -136,8 +136,9 @@ def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return
     L = _lib.lib()
     if _use_grid(method, x.size(0), T):
         ws = _grid_ws(x.size(0), T, x.device)
-        _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn_grid, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T,
-                                     x.size(0), y.size(0), k, _dp(nbr), _dp(d2), _dp(ws), ws.numel(), _stream()))
+        _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn_grid_ex, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T,
+                                     x.size(0), y.size(0), k, float(cell_size), _dp(nbr), _dp(d2), _dp(ws), ws.numel(),
+                                     _stream()))
     else:
         _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T, x.size(0),
                                      y.size(0), k, _dp(nbr), _dp(d2), _stream()))
@@ -555,6 +556,27 @@ def pack_tiles(cloud: Tensor, index: Optional[Tensor], ptr: Tensor):
     _lib.check(_lib.lib().p2w_pack(_dp(cloud), cloud.stride(0), _dp(index), _dp(ptr), B, m, _dp(pos), _dp(refl),
                                    _dp(batch), _dp(shift), _dp(sf), _stream()))
     return pos, refl, batch, shift, sf
+
+
+def spatial_vote(classified_xyz: Tensor, prob: Tensor, pred: Tensor, original_xyz: Tensor, k: int = 64,
+                 any_wood: float = 1.0, cell_size: float = 0.05):
+    """PointCloudClassifier.collect_predictions (src/predicter.py:129-142) on the device: the k nearest
+    classified points of every original point (one plot-wide cell-list search, FP32 distances) and
+    compute_labels (:113-127).  Returns (label uint8 [N], pwood float64 [N])."""
+    xyz = _req(classified_xyz, torch.float32, "classified_xyz", 2)
+    org = _req(original_xyz, torch.float32, "original_xyz", 2)
+    prob, pred = _req(prob, torch.float32, "prob", 1), _req(pred, torch.uint8, "pred", 1)
+    if xyz.size(1) != 3 or org.size(1) != 3 or prob.numel() != xyz.size(0) or pred.numel() != xyz.size(0):
+        raise _lib.P2WError("spatial_vote: inconsistent shapes")
+    dev = xyz.device
+    px = torch.tensor([0, xyz.size(0)], device=dev, dtype=torch.int64)
+    py = torch.tensor([0, org.size(0)], device=dev, dtype=torch.int64)
+    nbr = knn_table(xyz, org, k, px, py, method="grid", cell_size=cell_size)
+    label = torch.empty(org.size(0), device=dev, dtype=torch.uint8)
+    pwood = torch.empty(org.size(0), device=dev, dtype=torch.float64)
+    _lib.check(_lib.lib().p2w_spatial_vote(_dp(nbr), org.size(0), k, _dp(prob), _dp(pred), float(any_wood), _dp(label),
+                                           _dp(pwood), _stream()))
+    return label, pwood
 
 
 def writeback(logits: Tensor, pos: Tensor, ptr: Tensor, local_shift: Tensor, is_wood: float = 0.5,

@@ -25,7 +25,7 @@ from . import model as M
 from . import ops
 from .preprocessing import TileStore
 
-__all__ = ["plan_batches", "plan_launches", "shard_batches", "classify_tiles", "gather_rows", "SemanticSegmentation"]
+__all__ = ["plan_batches", "plan_launches", "shard_batches", "classify_tiles", "PointCloudClassifier", "gather_rows", "SemanticSegmentation"]
 
 
 def plan_batches(num_tiles: int, batch_size: int) -> List[Tuple[int, int]]:
@@ -119,11 +119,47 @@ def gather_rows(rows: torch.Tensor, batch_ids: Sequence[int], dst: int = 0):
     return [(meta[r][0], bucket[r][: meta[r][1]]) for r in range(world)]
 
 
+class PointCloudClassifier:
+    """src/predicter.py:107-142: the spatial vote that turns the per-tile classifications (every point is
+    classified once per tile that holds it) into one label / pwood per ORIGINAL point."""
+
+    def __init__(self, is_wood, any_wood):
+        self.is_wood = is_wood
+        self.any_wood = any_wood
+
+    def collect_predictions(self, classification, original, cell_size: float = 0.05):
+        """classification: float64 [M,5] device rows (x, y, z, pred, prob) or a tuple
+        (xyz float32 [M,3], pred uint8 [M], prob float32 [M]); original: [N, >=3] device array or a pandas
+        DataFrame (x, y, z first).  Returns (label uint8 [N], pwood float64 [N]) on the device and, for a
+        DataFrame, also stores them in its 'label' / 'pwood' columns as the reference does (:141)."""
+        if isinstance(classification, tuple):
+            xyz, pred, prob = classification
+        else:
+            xyz = classification[:, :3].to(torch.float32).contiguous()
+            pred = classification[:, 3].to(torch.uint8)
+            prob = classification[:, 4].to(torch.float32)
+        frame = original if hasattr(original, "columns") else None
+        if frame is not None:
+            frame = frame.drop(columns=[c for c in frame.columns if c in ("label", "pwood", "pleaf")])
+            org = torch.as_tensor(np.ascontiguousarray(frame.values[:, :3], dtype=np.float32)).to(xyz.device)
+        else:
+            org = original[:, :3].to(torch.float32).contiguous()
+        k = 32 if self.any_wood != 1 else 64                            # :137
+        label, pwood = ops.spatial_vote(xyz, prob.contiguous(), pred.contiguous(), org, k, float(self.any_wood),
+                                        cell_size)
+        if frame is not None:
+            frame.loc[:, "label"] = label.cpu().numpy().astype(np.float64)
+            frame.loc[:, "pwood"] = pwood.cpu().numpy()
+            return frame
+        return label, pwood
+
+
 def SemanticSegmentation(args):
-    """src/predicter.py:148-236 up to `classified_pc` (:217).  Expects args.tiles (from
-    preprocessing.preprocess) and the reference's flags (batch_size, is_wood, model, wdir).
-    Sets args.classified_pc (float64 [M,5] numpy: x, y, z, pred, prob) and returns args.
-    The spatial vote (collect_predictions, :107-142) is the next row of SURVEY.md §8(f)."""
+    """src/predicter.py:148-236 without the file output (:233-234, src/io.py).  Expects args.tiles (from
+    preprocessing.preprocess), args.pc (the original cloud: DataFrame or [N, >=3] array) and the
+    reference's flags (batch_size, is_wood, any_wood, model, wdir).  Sets args.classified_pc (float64
+    [M,5] numpy: x, y, z, pred, prob, :217) and the voted per-point result: args.pc gains 'label' /
+    'pwood' columns when it is a DataFrame, else args.label / args.pwood hold device tensors."""
     device = torch.device("cuda")
     net = getattr(args, "net", None)
     if net is None:
@@ -136,4 +172,12 @@ def SemanticSegmentation(args):
     net.eval()
     _, _, rows, _ = classify_tiles(net, args.tiles, args.batch_size, args.is_wood, want_rows=True)
     args.classified_pc = rows.cpu().numpy()
+    classifier = PointCloudClassifier(args.is_wood, any_wood=getattr(args, "any_wood", 1))
+    pc = getattr(args, "pc", None)
+    if pc is not None:
+        if hasattr(pc, "columns"):
+            args.pc = classifier.collect_predictions(rows, pc)
+        else:
+            cloud = torch.as_tensor(pc)
+            args.label, args.pwood = classifier.collect_predictions(rows, cloud.to(device))
     return args
