@@ -4,12 +4,13 @@
 
 Workload (BASELINE.json configs[1]): the predict.py path on a synthetic 1 M-point TLS plot
 (xyz + reflectance), grid_size 2.0 4.0, min_pts 128, max_pts 16384, batch_size 8, seeded random
-weights (the checkpoint is not shipped).  One STEP = one complete pass over the plot: height /
-reflectance normalisation and 5-D voxel tiling (K6), then for every batch of 8 tiles packing (K7),
-the network (voxel sampling K4, radius / kNN K1-K2, fused PointNetConv K5, kNN interpolation,
-torch/cuBLAS dense blocks) and write-back (K8), up to the `classified_pc` rows of
-src/predicter.py:217.  The spatial vote after it is outside the region on
-both arms.
+weights (the checkpoint is not shipped).  One STEP = one complete pass over the plot, from the
+in-memory [N,4] cloud to one (label, pwood) per ORIGINAL point: height / reflectance normalisation
+and 5-D voxel tiling (K6), then for every batch of 8 tiles packing (K7), the network (voxel
+sampling K4, radius / kNN K1-K2, fused PointNetConv K5, kNN interpolation, cuBLASLt dense blocks)
+and write-back (K8) -- the `classified_pc` rows of src/predicter.py:217 -- and the spatial vote
+over them (src/predicter.py:107-142; 64-NN of every original point among all classified points,
+median pwood, class votes).  File I/O (src/io.py) is outside the region on both arms.
 
 `value`   : N_points * steps / device time, cloud resident in HBM when the clock starts.
 `e2e`     : the same through the host-facing API: pinned host cloud -> H2D -> pipeline -> D2H of the
@@ -18,7 +19,9 @@ both arms.
 `cpu_baseline` / `--impl reference`: the reference's host + model code cannot be imported on the
             GPU box (torch_geometric, torch_cluster, torch_scatter absent), so the CPU arm is the
             oracle's restatement (oracle/ref_pipeline.py + ref_model.py, kind "port") on all host
-            threads, on a bounded sample of the same plot, extrapolated to the whole plot.
+            threads: full tiling, a bounded sample of the batches extrapolated by tile points to the
+            whole plot, and the full spatial vote (scipy cKDTree on all cores) on a plot-sized stand-in
+            for the classified rows.
 N > 1 (torchrun): every rank classifies its own 1 M-point plot (seed 1 + rank): weak scaling, no
 collective on the data path; time = max over ranks.
 """
@@ -129,10 +132,20 @@ def cpu_arm(n_points: int, seed: int, budget_s: float = 20.0):
         used += 1
         if t_cls > budget_s:
             break
-    est = t_pre + t_cls * total_pts / max(done_pts, 1)
+    # spatial vote on a plot-sized stand-in for the classified rows: every tile point at its own
+    # coordinates with a synthetic probability (the KD-tree cost does not depend on the values)
+    members = np.concatenate(tiles)
+    rng = np.random.default_rng(0)
+    prob = rng.random(len(members))
+    rows = np.concatenate([feat5[members, :3].astype(np.float64), (prob >= 0.5)[:, None].astype(np.float64),
+                           prob[:, None]], axis=1)
+    t2 = time.perf_counter()
+    ref_pipeline.collect_predictions(rows, cloud[:, :3], 1, workers=cores)
+    t_vote = time.perf_counter() - t2
+    est = t_pre + t_cls * total_pts / max(done_pts, 1) + t_vote
     return dict(value=n_points / est, unit="points/s", cores=cores, kind="port",
                 sample=f"full tiling ({t_pre:.2f} s) + {used} of {nb} batches ({done_pts} of {total_pts} tile points, "
-                       f"{t_cls:.1f} s), extrapolated by tile points"), est
+                       f"{t_cls:.1f} s), extrapolated by tile points + full spatial vote ({t_vote:.1f} s)"), est
 
 
 def run_reference(args):
@@ -152,7 +165,8 @@ def run_reference(args):
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload="predict 1M-point synthetic TLS plot, grid 2/4 m, min_pts 128, max_pts 16384, "
-                                     "batch_size 8 (CPU: reference pipeline restated on oracle ops, bounded sample)"),
+                                     "batch_size 8; cloud -> tiles -> network -> spatial vote (CPU: reference pipeline "
+                                     "restated on oracle ops, bounded sample)"),
                 cpu_baseline=base,
                 e2e=dict(value=value, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -206,9 +220,10 @@ def main():
 
     def step(cloud):
         store = Voxelise(cloud, minpoints=CFG["min_pts"], maxpoints=CFG["max_pts"], gridsize=CFG["grid_size"]).write_voxels()
-        prob, pred, _, _ = classify_tiles(net, store, CFG["batch_size"], CFG["is_wood"],
-                                          max_points_per_launch=args.launch_points)
-        return store, prob, pred
+        prob, pred, xyz, _ = classify_tiles(net, store, CFG["batch_size"], CFG["is_wood"],
+                                            max_points_per_launch=args.launch_points, want_xyz=True)
+        label, pwood = ops.spatial_vote(xyz, prob, pred, cloud[:, :3].contiguous(), 64, 1.0)
+        return store, label, pwood
 
     def barrier():
         torch.cuda.synchronize()
@@ -217,10 +232,10 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        store, prob, pred = step(dev_cloud)
+        store, label, pwood = step(dev_cloud)
     tile_points = int(store.ptr[-1])
-    out_prob = torch.empty(tile_points, dtype=torch.float32).pin_memory()
-    out_pred = torch.empty(tile_points, dtype=torch.uint8).pin_memory()
+    out_label = torch.empty(n_points, dtype=torch.uint8).pin_memory()
+    out_pwood = torch.empty(n_points, dtype=torch.float64).pin_memory()
 
     # ---- device-resident steps, dominant kernel timed live with CUDA events
     ops.KERNEL_TIMER.reset("p2w_pointnet_conv_max", "p2w_knn")
@@ -244,9 +259,9 @@ def main():
     e0.record()
     for _ in range(args.steps):
         cloud = host.cuda(non_blocking=True)
-        _, prob, pred = step(cloud)
-        out_prob.copy_(prob, non_blocking=True)
-        out_pred.copy_(pred, non_blocking=True)
+        _, label, pwood = step(cloud)
+        out_label.copy_(label, non_blocking=True)
+        out_pwood.copy_(pwood, non_blocking=True)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
@@ -284,13 +299,14 @@ def main():
                     steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="bf16" if bf16 else "f32", data="synthetic",
                     config=dict(workload=f"predict {n_points}-point synthetic TLS plot per GPU, grid 2/4 m, min_pts 128, "
-                                         "max_pts 16384, batch_size 8, seeded weights",
+                                         "max_pts 16384, batch_size 8, seeded weights; cloud -> tiles -> network -> spatial vote "
+                                         "-> (label, pwood) per point",
                                 tile_points=tile_points, tiles=int(store.num_tiles),
                                 launch_points=args.launch_points,
                                 l2="no flush needed: a step streams > 4 GB of activations (e.g. the [N0, 544] and "
                                    "[N0, 512] FP buffers) between two launches of any kernel, 30x the 126 MB L2"),
                     e2e=dict(value=world * n_points / (ms_e2e / 1e3), unit="points/s", h2d_bytes_per_step=int(host.numel() * 4),
-                             d2h_bytes_per_step=int(tile_points * 5)),
+                             d2h_bytes_per_step=int(n_points * 9)),
                     gpu_launches=int(launches), clocks=clk.summary(), roofline=roof,
                     roofline_knn=roof_knn if bf16 else roof_conv)
         if world == 1 and not args.no_cpu_baseline:

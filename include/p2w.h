@@ -222,7 +222,8 @@ int p2w_scatter_minmax(const float *src, const int64_t *index, int64_t n, int32_
  * (local_shift [B,3]) and returns sf[b] = max |pos|; pos [m,3], refl [m], batch [m].
  * p2w_writeback (src/predicter.py:199-214): prob = sigmoid(nan_to_num(logit)),
  * pred = prob >= is_wood, xyz = pos + local_shift[tile]; rows (x,y,z,pred,prob) as
- * float64 [m,5] (out64) and/or compact prob [m] / pred [m]. */
+ * float64 [m,5] (out64) and/or compact prob [m] / pred [m] / xyz32 [m,3] (the un-shifted coordinates
+ * rounded to FP32, what the spatial vote searches); every output may be NULL. */
 int p2w_sa_prepare(const float *pos, int32_t ld_pos, const float *refl, const int64_t *ptr,
                    const float *sf, int32_t num_tiles, int64_t n, float *pos4, float *pos_back,
                    p2w_stream_t stream);
@@ -231,7 +232,7 @@ int p2w_pack(const float *cloud, int32_t ld, const int64_t *index, const int64_t
              float *local_shift, float *sf, p2w_stream_t stream);
 int p2w_writeback(const float *logits, const float *pos, const int64_t *ptr,
                   const float *local_shift, int32_t num_tiles, int64_t m, float is_wood,
-                  double *out64, float *prob, uint8_t *pred, p2w_stream_t stream);
+                  double *out64, float *prob, uint8_t *pred, float *xyz32, p2w_stream_t stream);
 
 /* ---- spatial vote (src/predicter.py:113-142, PointCloudClassifier.compute_labels) -------------
  * For every original point q and its k nearest CLASSIFIED points nbr[q, :] (from p2w_knn_grid_ex

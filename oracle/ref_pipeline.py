@@ -145,7 +145,7 @@ def classify(sd, feat5, tiles, batch_size=8, is_wood=0.5, max_batches=None):
     return np.concatenate(out) if out else np.zeros((0, 5))
 
 
-def collect_predictions(classification, original_xyz, any_wood=1):
+def collect_predictions(classification, original_xyz, any_wood=1, workers=1):
     """PointCloudClassifier.collect_predictions + compute_labels (src/predicter.py:113-142): float64 KD-tree
     over the classified rows (pykdtree in the reference, scipy's cKDTree here: same exact k nearest
     neighbours up to ties), k = 64 (32 if any_wood != 1); pwood = np.median of the neighbours'
@@ -154,7 +154,7 @@ def collect_predictions(classification, original_xyz, any_wood=1):
     from scipy.spatial import cKDTree
     k = 32 if any_wood != 1 else 64
     tree = cKDTree(classification[:, :3])
-    _, idx = tree.query(np.asarray(original_xyz, dtype=np.float64)[:, :3], k=k)
+    _, idx = tree.query(np.asarray(original_xyz, dtype=np.float64)[:, :3], k=k, workers=workers)
     nb = classification[idx]                                   # [N, k, 5]
     pwood = np.median(nb[:, :, -1], axis=1)
     if any_wood != 1:

@@ -57,7 +57,7 @@ SIGNATURES = {
     "p2w_reflectance_normalize": (c_int32, [_P, c_int64, _P, _P, _P, _P]),
     "p2w_assemble5": (c_int32, [_P, c_int32, _P, _P, c_int64, _P, _P]),
     "p2w_priority_keys": (c_int32, [_P, _P, _P, c_int64, c_float, ctypes.c_uint32, _P, _P]),
-    "p2w_writeback": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_float, _P, _P, _P, _P]),
+    "p2w_writeback": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_float, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -34,7 +34,8 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int GL_MAX = 6;        // finest planning level: 64 cells along the longest axis
 constexpr int GDIM_MAX = 64;        // cells per axis when the cell size is planned from the occupancy pyramid
-constexpr int GDIM_HINT_MAX = 1024; // ... and when the caller gives the cell size (plot-wide searches)
+constexpr int GDIM_HINT_MAX = 1024;
+constexpr int HINT_CELLS_PER_SOURCE = 4;    // table cap of the hinted mode, same as the planned mode (16 measured slower) // ... and when the caller gives the cell size (plot-wide searches)
 constexpr int MERGE_MIN = 5;      // survivors per step above which the step is sorted and merged at once
 
 struct __align__(16) GridTile {
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict_
     } else if (cell_hint > 0.f) {
         // the caller knows the scale (plot-wide searches): start from its cell size, respect the table cap
         float h = cell_hint;
-        const int64_t cap = n * 4 > 64 ? n * 4 : 64;
+        const int64_t cap = n * HINT_CELLS_PER_SOURCE > 64 ? n * HINT_CELLS_PER_SOURCE : 64;
         for (;;) {
             const float fx = ex / h, fy = ey / h, fz = ez / h;
             if (fx < static_cast<float>(GDIM_HINT_MAX) && fy < static_cast<float>(GDIM_HINT_MAX) &&
@@ -404,6 +405,29 @@ __device__ __forceinline__ void merge32(key_t &top, key_t batch, int lane) {
     for (int j = 16; j > 0; j >>= 1) cmpx64(top, j, (lane & j) == 0);
 }
 
+// 64-entry list (two slots per lane, entry e in slot e/32 of lane e%32) <- the 64 smallest of list U batch.
+// The largest 32 of (upper half U batch) cannot be among the 64 smallest: each of them has 32 smaller
+// elements there and, because one of those comes from the upper half, the whole lower half below it too.
+__device__ __forceinline__ void merge64(key_t &lo, key_t &hi, key_t batch, int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) cmpx64(batch, j, ((lane & k2) == 0) == ((lane & j) == 0));
+    }
+    key_t r = __shfl_sync(FULL, batch, 31 - lane);
+    key_t m = r < hi ? r : hi;                                // smallest 32 of (upper half U batch), bitonic
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) cmpx64(m, j, (lane & j) == 0);
+    r = __shfl_sync(FULL, m, 31 - lane);
+    hi = r > lo ? r : lo;                                     // bitonic halves of (lower half U m)
+    lo = r < lo ? r : lo;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        cmpx64(lo, j, (lane & j) == 0);
+        cmpx64(hi, j, (lane & j) == 0);
+    }
+}
+
 constexpr int SMALL_K = 6;        // up to this k a crowded step is reduced by k warp-minimum rounds
 
 // Offers the sources of up to 32 contiguous segments (lane l: spts[start, start+len)) to the top-k.
@@ -447,6 +471,11 @@ __device__ __forceinline__ void scan_segments(int len, uint32_t start, const flo
         const bool hit = in_range && ck < thr;
         unsigned m = __ballot_sync(FULL, hit);
         if (!m) continue;
+        if (S == 2 && __popc(m) > 2 * MERGE_MIN) {
+            merge64(top.key[0], top.key[S - 1], hit ? ck : KEY_NONE, lane);
+            thr = top.kth(k);
+            continue;
+        }
         if (S == 1 && __popc(m) > MERGE_MIN) {
             if (k <= SMALL_K) {
                 bool live = hit;

@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) writeback_kernel(const float *__restrict_
                                                         const int64_t *__restrict__ ptr,
                                                         const float *__restrict__ local_shift, int B, int64_t m,
                                                         float is_wood, double *__restrict__ out64,
-                                                        float *__restrict__ prob, uint8_t *__restrict__ pred) {
+                                                        float *__restrict__ prob, uint8_t *__restrict__ pred,
+                                                        float *__restrict__ xyz32) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= m) return;
     float z = logits[i];
@@ -117,13 +118,23 @@ __global__ void __launch_bounds__(256) writeback_kernel(const float *__restrict_
     const int lab = p >= is_wood ? 1 : 0;
     if (prob) prob[i] = p;
     if (pred) pred[i] = static_cast<uint8_t>(lab);
-    if (out64) {
+    if (out64 || xyz32) {
         const int b = find_tile(ptr, B, i);
-        out64[i * 5 + 0] = static_cast<double>(pos[i * 3 + 0]) + static_cast<double>(local_shift[b * 3 + 0]);
-        out64[i * 5 + 1] = static_cast<double>(pos[i * 3 + 1]) + static_cast<double>(local_shift[b * 3 + 1]);
-        out64[i * 5 + 2] = static_cast<double>(pos[i * 3 + 2]) + static_cast<double>(local_shift[b * 3 + 2]);
-        out64[i * 5 + 3] = static_cast<double>(lab);
-        out64[i * 5 + 4] = static_cast<double>(p);
+        const double x = static_cast<double>(pos[i * 3 + 0]) + static_cast<double>(local_shift[b * 3 + 0]);
+        const double y = static_cast<double>(pos[i * 3 + 1]) + static_cast<double>(local_shift[b * 3 + 1]);
+        const double z = static_cast<double>(pos[i * 3 + 2]) + static_cast<double>(local_shift[b * 3 + 2]);
+        if (out64) {
+            out64[i * 5 + 0] = x;
+            out64[i * 5 + 1] = y;
+            out64[i * 5 + 2] = z;
+            out64[i * 5 + 3] = static_cast<double>(lab);
+            out64[i * 5 + 4] = static_cast<double>(p);
+        }
+        if (xyz32) {   // the same un-shifted coordinates rounded to FP32: the vote's search runs in FP32
+            xyz32[i * 3 + 0] = static_cast<float>(x);
+            xyz32[i * 3 + 1] = static_cast<float>(y);
+            xyz32[i * 3 + 2] = static_cast<float>(z);
+        }
     }
 }
 
@@ -152,9 +163,9 @@ extern "C" int p2w_pack(const float *cloud, int32_t ld, const int64_t *index, co
 
 extern "C" int p2w_writeback(const float *logits, const float *pos, const int64_t *ptr, const float *local_shift,
                              int32_t num_tiles, int64_t m, float is_wood, double *out64, float *prob, uint8_t *pred,
-                             p2w_stream_t stream) {
+                             float *xyz32, p2w_stream_t stream) {
     P2W_REQUIRE(num_tiles >= 1, "p2w_writeback: bad sizes");
     if (m == 0) return P2W_OK;
-    P2W_LAUNCH(writeback_kernel, (unsigned)((m + 255) / 256), 256, 0, as_stream(stream))(logits, pos, ptr, local_shift, num_tiles, m, is_wood, out64, prob, pred);
+    P2W_LAUNCH(writeback_kernel, (unsigned)((m + 255) / 256), 256, 0, as_stream(stream))(logits, pos, ptr, local_shift, num_tiles, m, is_wood, out64, prob, pred, xyz32);
     return check_launch("p2w_writeback");
 }

@@ -580,14 +580,21 @@ def spatial_vote(classified_xyz: Tensor, prob: Tensor, pred: Tensor, original_xy
 
 
 def writeback(logits: Tensor, pos: Tensor, ptr: Tensor, local_shift: Tensor, is_wood: float = 0.5,
-              want_rows: bool = False):
-    """src/predicter.py:199-214: (prob [M] fp32, pred [M] uint8[, rows float64 [M,5] = x,y,z,pred,prob])."""
+              want_rows: bool = False, want_xyz: bool = False):
+    """src/predicter.py:199-214: (prob [M] fp32, pred [M] uint8[, rows float64 [M,5] = x,y,z,pred,prob]
+    [, xyz float32 [M,3] = the un-shifted coordinates for the spatial vote])."""
     logits = _req(logits, torch.float32, "logits", 1)
     m = logits.numel()
     dev = logits.device
     prob = torch.empty(m, device=dev, dtype=torch.float32)
     pred = torch.empty(m, device=dev, dtype=torch.uint8)
     rows = torch.empty((m, 5), device=dev, dtype=torch.float64) if want_rows else None
+    xyz = torch.empty((m, 3), device=dev, dtype=torch.float32) if want_xyz else None
     _lib.check(_lib.lib().p2w_writeback(_dp(logits), _dp(pos), _dp(ptr), _dp(local_shift), ptr.numel() - 1, m,
-                                        float(is_wood), _dp(rows), _dp(prob), _dp(pred), _stream()))
-    return (prob, pred, rows) if want_rows else (prob, pred)
+                                        float(is_wood), _dp(rows), _dp(prob), _dp(pred), _dp(xyz), _stream()))
+    out = (prob, pred)
+    if want_rows:
+        out += (rows,)
+    if want_xyz:
+        out += (xyz,)
+    return out

@@ -70,9 +70,10 @@ def plan_launches(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, batch_ids
 @torch.no_grad()
 def classify_tiles(net: torch.nn.Module, tiles: TileStore, batch_size: int = 8, is_wood: float = 0.5,
                    batch_ids: Optional[Iterable[int]] = None, want_rows: bool = False,
-                   max_points_per_launch: int = 1 << 20):
+                   max_points_per_launch: int = 1 << 20, want_xyz: bool = False):
     """Runs the network over the tiles.  Returns (prob float32 [M'], pred uint8 [M'], rows float64
-    [M',5] or None, spans) on the device, in batch order; M' covers the selected batches.
+    [M',5] or None, spans) on the device, in batch order; M' covers the selected batches.  With
+    want_xyz the third item is instead the un-shifted FP32 coordinates [M',3] the spatial vote searches.
     Batches of `batch_size` tiles are the reference's unit (their composition fixes the voxel-grid
     origin); up to `max_points_per_launch` points of consecutive batches share one launch set."""
     dev = tiles.feat.device
@@ -89,14 +90,15 @@ def classify_tiles(net: torch.nn.Module, tiles: TileStore, batch_size: int = 8, 
         data = M.make_data(pos, refl, batch, sf, local_shift=shift.reshape(-1), ptr=bptr,
                            group_ptr=gptr if len(group) > 1 else None)
         logits = net(data)
-        out = ops.writeback(logits.float().reshape(-1), pos, bptr, shift, is_wood, want_rows=want_rows)
+        out = ops.writeback(logits.float().reshape(-1), pos, bptr, shift, is_wood, want_rows=want_rows,
+                            want_xyz=want_xyz and not want_rows)
         probs.append(out[0])
         preds.append(out[1])
-        if want_rows:
+        if want_rows or want_xyz:
             rows.append(out[2])
         spans.append((lo, hi))
     cat = (lambda xs: torch.cat(xs) if xs else torch.empty(0, device=dev))
-    return cat(probs), cat(preds), (cat(rows) if want_rows else None), spans
+    return cat(probs), cat(preds), (cat(rows) if (want_rows or want_xyz) else None), spans
 
 
 def gather_rows(rows: torch.Tensor, batch_ids: Sequence[int], dst: int = 0):
