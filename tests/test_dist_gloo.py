@@ -54,3 +54,50 @@ def test_shard_and_gather_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+def _worker_allgather(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pointstowood_b200.distributed import all_gather_rows, shard_contiguous
+    from pointstowood_b200.predicter import plan_batches
+    rng = np.random.default_rng(1)
+    ptr = np.concatenate([[0], np.cumsum(rng.integers(10, 200, 53))])
+    batches = plan_batches(53, 8)
+    mine = shard_contiguous(batches, ptr, world, rank)
+    rows = torch.cat([torch.arange(ptr[batches[b][0]], ptr[batches[b][1]], dtype=torch.float32).view(-1, 1).repeat(1, 5)
+                      for b in mine]) if mine else torch.empty((0, 5), dtype=torch.float32)
+    everything = all_gather_rows(rows)                      # every rank: all rows, rank-major = batch order
+    ok = bool(torch.equal(everything[:, 0], torch.arange(ptr[-1], dtype=torch.float32)))
+    out.put((rank, ok, len(mine)))
+    dist.destroy_process_group()
+
+
+def test_contiguous_shards_and_uneven_all_gather_world_size_2():
+    """distributed.classify_plot's exchange: contiguous batch ranges, one all-gather of uneven row blocks."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_allgather, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in got)
+    assert sum(n for _, _, n in got) == 7 and min(n for _, _, n in got) >= 2
+
+
+def test_shard_contiguous_partitions_and_balances():
+    from pointstowood_b200.distributed import shard_contiguous
+    from pointstowood_b200.predicter import plan_batches
+    rng = np.random.default_rng(2)
+    sizes = np.concatenate([rng.integers(128, 2000, 900), rng.integers(2000, 16384, 265)])      # 2 m then 4 m tiles
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    batches = plan_batches(len(sizes), 8)
+    for world in (1, 2, 4, 8):
+        shards = [shard_contiguous(batches, ptr, world, r) for r in range(world)]
+        assert sum(shards, []) == list(range(len(batches)))                                     # a partition, in order
+        load = [sum(int(ptr[batches[b][1]] - ptr[batches[b][0]]) for b in s) for s in shards]
+        assert max(load) <= 1.15 * (ptr[-1] / world) + 8 * 16384
