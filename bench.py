@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--launch-points", type=int, default=1 << 20,
+    ap.add_argument("--launch-points", type=int, default=1 << 21,
                     help="points of consecutive reference batches that share one launch set")
     args = ap.parse_args()
     if args.impl == "reference":

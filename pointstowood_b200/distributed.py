@@ -66,7 +66,7 @@ def all_gather_rows(rows: torch.Tensor) -> torch.Tensor:
 @torch.no_grad()
 def classify_plot(net: torch.nn.Module, cloud: torch.Tensor, min_pts: int = 128, max_pts: int = 16384,
                   grid_size=(2.0, 4.0), batch_size: int = 8, is_wood: float = 0.5, any_wood: float = 1,
-                  max_points_per_launch: int = 1 << 20, rank: Optional[int] = None, world_size: Optional[int] = None):
+                  max_points_per_launch: int = 1 << 21, rank: Optional[int] = None, world_size: Optional[int] = None):
     """cloud [N, >=4] (x, y, z, reflectance) on this rank's device -> (label uint8 [N], pwood float64 [N])
     for the WHOLE plot on every rank.  Single process: rank 0 of 1."""
     import torch.distributed as dist

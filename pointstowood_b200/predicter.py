@@ -70,7 +70,7 @@ def plan_launches(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, batch_ids
 @torch.no_grad()
 def classify_tiles(net: torch.nn.Module, tiles: TileStore, batch_size: int = 8, is_wood: float = 0.5,
                    batch_ids: Optional[Iterable[int]] = None, want_rows: bool = False,
-                   max_points_per_launch: int = 1 << 20, want_xyz: bool = False):
+                   max_points_per_launch: int = 1 << 21, want_xyz: bool = False):
     """Runs the network over the tiles.  Returns (prob float32 [M'], pred uint8 [M'], rows float64
     [M',5] or None, spans) on the device, in batch order; M' covers the selected batches.  With
     want_xyz the third item is instead the un-shifted FP32 coordinates [M',3] the spatial vote searches.
