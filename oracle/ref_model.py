@@ -27,8 +27,14 @@ from . import oracle as O
 BN_EPS = 1e-5
 
 
+_BN_TRAIN = False        # net_forward_train flips it: batch statistics, as nn.BatchNorm1d in train mode
+
+
 def _bn(sd, p, x):
-    """Eval-mode BatchNorm1d over the channel (last) dim of [N, C]."""
+    """BatchNorm1d over the channel (last) dim of [N, C]: running statistics in eval mode, batch
+    statistics (biased variance, running buffers left alone) in train mode."""
+    if _BN_TRAIN:
+        return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.0, BN_EPS)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
                         sd[p + ".weight"], sd[p + ".bias"], False, 0.0, BN_EPS)
 
@@ -85,10 +91,12 @@ def pointnet_conv(sd, p, x, pos4_src, pos4_tgt, nbr):
     return out.scatter_reduce(0, i.view(-1, 1).expand_as(msg), msg, "amax", include_self=False)
 
 
-def sa_module(sd, name, x, pos, batch, refl, sf, res, k, trace=None):
-    """model.py:108-127, eval mode."""
+def sa_module(sd, name, x, pos, batch, refl, sf, res, k, trace=None, idx=None):
+    """model.py:108-127; eval mode samples by voxel, train mode takes the given random half `idx`
+    (model.py:97-101,114: sorted randperm, pinned by the caller)."""
     pos4 = torch.cat([pos[:, :3], refl.unsqueeze(-1)], -1)
-    idx = voxelsample(pos4[:, :3], batch, res)
+    if idx is None:
+        idx = voxelsample(pos4[:, :3], batch, res)
     B = sf.numel()
     ptr_x = O.batch_to_ptr(batch.numpy(), B)
     ptr_y = O.batch_to_ptr(batch[idx].numpy(), B)
@@ -101,7 +109,7 @@ def sa_module(sd, name, x, pos, batch, refl, sf, res, k, trace=None):
     x = pointnet_conv(sd, name + ".conv", x, pos4, pos4[idx], nbr)
     pos4[:, :3] = pos4[:, :3] * s
     if trace is not None:
-        trace[name] = dict(idx=idx.numpy().copy(), nbr=np.asarray(nbr).copy(), conv=x.numpy().copy())
+        trace[name] = dict(idx=idx.numpy().copy(), nbr=np.asarray(nbr).copy(), conv=x.detach().numpy().copy())
     x = _residual(sd, name + ".residual_block", x)
     return x, pos4[idx, :3], batch[idx], refl[idx]
 
@@ -122,13 +130,44 @@ def knn_interpolate(x, pos_x, pos_y, batch_x, batch_y, k, B):
 
 @torch.no_grad()
 def net_forward(sd, pos, reflectance, batch, sf, trace=None):
-    """model.py:226-245 -> logits [N0]."""
+    """model.py:226-245 -> logits [N0] (eval mode)."""
+    return _net_forward(sd, pos, reflectance, batch, sf, trace, (None, None, None))
+
+
+def net_forward_train(sd, pos, reflectance, batch, sf, idx_list, trace=None):
+    """The same forward in TRAIN mode (batch-statistics BatchNorm, the three random halves given by the
+    caller), with autograd on: tensors of `sd` that require grad receive gradients from the result."""
+    global _BN_TRAIN
+    _BN_TRAIN = True
+    try:
+        return _net_forward(sd, pos, reflectance, batch, sf, trace, idx_list)
+    finally:
+        _BN_TRAIN = False
+
+
+def poly1_focal_loss(logits, labels, epsilon=0.1, gamma=2.0, alpha=None, label_smoothing=0.1, eps=1e-6):
+    """src/loss.py:27-80 with the trainer's settings (src/trainer.py:113: reduction mean, gamma 2, alpha None,
+    label smoothing 0.1): clamped logits, smoothed targets, BCE x clamped focal weight + epsilon (1-pt)^(gamma+1)."""
+    z = torch.clamp(logits, min=-10, max=10)
+    y = labels * (1 - label_smoothing) + 0.5 * label_smoothing if label_smoothing is not None else labels
+    p = torch.clamp(torch.sigmoid(z), min=eps, max=1 - eps)
+    ce = torch.clamp(F.binary_cross_entropy_with_logits(z, y, reduction="none"), max=100.0)
+    pt = torch.clamp(y * p + (1 - y) * (1 - p), min=eps, max=1 - eps)
+    loss = torch.clamp(torch.pow(1 - pt, gamma), max=2.0) * ce
+    if alpha is not None:
+        loss = (alpha * y + (1 - alpha) * (1 - y)) * loss
+    loss = loss + torch.clamp(epsilon * torch.pow(1 - pt, gamma + 1), max=100.0)
+    loss = torch.clamp(loss, min=0.0, max=100.0)
+    return torch.where(torch.isnan(loss), torch.zeros_like(loss), loss).mean()
+
+
+def _net_forward(sd, pos, reflectance, batch, sf, trace, idx_list):
     B = sf.numel()
     x0 = _mlp(sd, "stem_mlp", pos[:, :3], 1)
     l0 = (x0, pos, batch, reflectance)
-    l1 = sa_module(sd, "sa1_module", *l0, sf, 0.04, 32, trace)
-    l2 = sa_module(sd, "sa2_module", *l1, sf, 0.08, 32, trace)
-    l3 = sa_module(sd, "sa3_module", *l2, sf, 0.16, 32, trace)
+    l1 = sa_module(sd, "sa1_module", *l0, sf, 0.04, 32, trace, idx_list[0])
+    l2 = sa_module(sd, "sa2_module", *l1, sf, 0.08, 32, trace, idx_list[1])
+    l3 = sa_module(sd, "sa3_module", *l2, sf, 0.16, 32, trace, idx_list[2])
     # GlobalSAModule: model.py:134-140
     x4 = _mlp(sd, "sa4_module.NN", torch.cat([l3[0], l3[1]], 1), 2)
     g = x4.new_zeros(B, x4.size(1)).scatter_reduce(0, l3[2].view(-1, 1).expand_as(x4), x4, "amax",

@@ -219,22 +219,28 @@ __global__ void __launch_bounds__(256) interp_cat_kernel(const TI *__restrict__ 
     float den = 0.f;
     for (int e = 0; e < k; e++) den = __fadd_rn(den, __shfl_sync(FULL, w, e));
     const int groups = (c + cs) >> 3, gi = c >> 3;
+    // BF16 output: the weights are normalised once and the sum is a fused multiply-add chain (the rounding to
+    // bf16 swamps the difference); FP32 output keeps upstream's sum-then-divide, operation for operation.
+    constexpr bool kFast = sizeof(TO) == 2;
+    const float wn = kFast ? __fdividef(w, den) : w;
     for (int g0 = 0; g0 < groups; g0 += 32) {
         const int g = g0 + lane;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int e = 0; e < k; e++) {          // warp-uniform trip count: the shuffles stay converged
             const int je = __shfl_sync(FULL, j, e);
-            const float we = __shfl_sync(FULL, w, e);
+            const float we = __shfl_sync(FULL, wn, e);
             if (je >= 0 && g < gi) {
                 float v[8];
                 ld8(x + static_cast<int64_t>(je) * c + g * 8, v);
 #pragma unroll
-                for (int u = 0; u < 8; u++) acc[u] = __fadd_rn(acc[u], __fmul_rn(v[u], we));
+                for (int u = 0; u < 8; u++) acc[u] = kFast ? fmaf(v[u], we, acc[u]) : __fadd_rn(acc[u], __fmul_rn(v[u], we));
             }
         }
         if (g < gi) {
+            if (!kFast) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) acc[u] = __fdiv_rn(acc[u], den);
+                for (int u = 0; u < 8; u++) acc[u] = __fdiv_rn(acc[u], den);
+            }
             st8(out + q * ld_out + g * 8, acc);
         } else if (g < groups) {
             ld8(skip + q * cs + (g - gi) * 8, acc);

@@ -90,8 +90,14 @@ __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict_
         }
         if (lane == 0) { s_lo[warp][d] = lo[d]; s_hi[warp][d] = hi[d]; }
     }
+    // pyramid depth: a level with more than 4 cells per source can never be chosen (the table cap), so small
+    // tiles get a shallow pyramid (8^LB bits to clear, fill and reduce instead of 64^3)
+    int LB = GL_MAX;
+    while (LB > 2 && (int64_t(1) << (3 * (LB - 1))) >= 4 * n) LB--;
+    const int words0 = (1 << (3 * LB)) >> 5;
     if (threadIdx.x <= GL_MAX) s_occ[threadIdx.x] = 0;
-    for (int w = threadIdx.x; w < 8192; w += blockDim.x) bits[w] = 0;
+    if (n > 32 && cell_hint <= 0.f)
+        for (int w = threadIdx.x; w < words0; w += blockDim.x) bits[w] = 0;
     __syncthreads();
     if (threadIdx.x < 3) {
         const int d = threadIdx.x;
@@ -129,18 +135,19 @@ __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict_
         }
         g.h = h;
     } else {
-        const float scale = 64.f / maxext;
+        const int nb = 1 << LB;
+        const float scale = static_cast<float>(nb) / maxext;
         for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-            const unsigned cx = static_cast<unsigned>(axis_cell(x[i * 3 + 0], ox, scale, 64));
-            const unsigned cy = static_cast<unsigned>(axis_cell(x[i * 3 + 1], oy, scale, 64));
-            const unsigned cz = static_cast<unsigned>(axis_cell(x[i * 3 + 2], oz, scale, 64));
+            const unsigned cx = static_cast<unsigned>(axis_cell(x[i * 3 + 0], ox, scale, nb));
+            const unsigned cy = static_cast<unsigned>(axis_cell(x[i * 3 + 1], oy, scale, nb));
+            const unsigned cz = static_cast<unsigned>(axis_cell(x[i * 3 + 2], oz, scale, nb));
             const unsigned m = spread6(cx) | (spread6(cy) << 1) | (spread6(cz) << 2);
             atomicOr(&bits[m >> 5], 1u << (m & 31u));
         }
         __syncthreads();
         // occupancy pyramid: level L has 8^L bits; 8 sibling bits are one byte
-        int words = 8192;
-        for (int L = GL_MAX; L >= 1; L--) {
+        int words = words0;
+        for (int L = LB; L >= 1; L--) {
             unsigned c = 0;
             for (int w = threadIdx.x; w < words; w += blockDim.x) c += __popc(bits[w]);
             for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
@@ -171,14 +178,14 @@ __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict_
         }
         // finest level whose occupied cells hold >= tau sources on average
         int L = 0;
-        for (int l = GL_MAX; l >= 1; l--) {
+        for (int l = LB; l >= 1; l--) {
             if (static_cast<float>(n) >= tau * static_cast<float>(s_occ[l])) { L = l; break; }
         }
         if (L == 0) {
             g.h = maxext * 1.0001f;
         } else {
             float h = maxext / static_cast<float>(1 << L);
-            if (L < GL_MAX) {
+            if (L < LB) {
                 // between two dyadic levels: shrink h by the local dimension (2 = surface, 3 = volume)
                 const float m = static_cast<float>(n) / static_cast<float>(s_occ[L]);
                 float dim = log2f(static_cast<float>(s_occ[L + 1]) / static_cast<float>(s_occ[L]));
@@ -709,23 +716,35 @@ __global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__r
         const float margin = 1e-5f * g.h * static_cast<float>(nmax) +
                              4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz));
         // safe gaps from the query to the six faces of its own cell
-        const float fx = g.ox + static_cast<float>(cx) * g.h, fy = g.oy + static_cast<float>(cy) * g.h,
-                    fz = g.oz + static_cast<float>(cz) * g.h;
+        const float fy = g.oy + static_cast<float>(cy) * g.h, fz = g.oz + static_cast<float>(cz) * g.h;
         const float k1 = 1.f - 1e-4f;
-        const float lox = fmaxf((qx - fx) * k1 - margin, 0.f), hix = fmaxf((fx + g.h - qx) * k1 - margin, 0.f);
         const float loy = fmaxf((qy - fy) * k1 - margin, 0.f), hiy = fmaxf((fy + g.h - qy) * k1 - margin, 0.f);
         const float loz = fmaxf((qz - fz) * k1 - margin, 0.f), hiz = fmaxf((fz + g.h - qz) * k1 - margin, 0.f);
+        // ring 1 as 9 rows of up to 3 cells (contiguous in the cell table), nearest rows first: the 18 table
+        // entries are fetched up front (independent loads), then a row is scanned unless its distance to the
+        // query already exceeds the current k-th distance
+        uint32_t ra[9], re[9];
+        float rb2[9];
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
 #pragma unroll
-        for (int s = 0; s < 27; s++) {
-            const int ddx = nb_d(NB_DX, s), ddy = nb_d(NB_DY, s), ddz = nb_d(NB_DZ, s);
-            const int xx = cx + ddx, yy = cy + ddy, zz = cz + ddz;
-            if (xx < 0 || xx >= g.nx || yy < 0 || yy >= g.ny || zz < 0 || zz >= g.nz) continue;
-            const float sx = ddx < 0 ? lox : (ddx > 0 ? hix : 0.f);
+        for (int s = 0; s < 9; s++) {
+            const int ddy = static_cast<int>((0x22161u >> (2 * s)) & 3u) - 1;   // 0,-1,1,0,0,-1,1,-1,1
+            const int ddz = static_cast<int>((0x28215u >> (2 * s)) & 3u) - 1;   // 0,0,0,-1,1,-1,-1,1,1
+            const int yy = cy + ddy, zz = cz + ddz;
+            ra[s] = re[s] = 0u;
+            if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+                const int64_t c0 = g.base + x0 + g.nx * (yy + g.ny * zz);
+                ra[s] = __ldg(cell_start + c0);
+                re[s] = __ldg(cell_start + c0 + (x1 - x0) + 1);
+            }
             const float sy = ddy < 0 ? loy : (ddy > 0 ? hiy : 0.f);
             const float sz = ddz < 0 ? loz : (ddz > 0 ? hiz : 0.f);
-            if (sx * sx + sy * sy + sz * sz > __uint_as_float(static_cast<unsigned>(best[K - 1] >> 32))) continue;
-            const int64_t c = g.base + xx + g.nx * (yy + g.ny * zz);
-            small_scan<K>(spts, __ldg(cell_start + c), __ldg(cell_start + c + 1), qx, qy, qz, best);
+            rb2[s] = sy * sy + sz * sz;
+        }
+#pragma unroll
+        for (int s = 0; s < 9; s++) {
+            if (rb2[s] > __uint_as_float(static_cast<unsigned>(best[K - 1] >> 32))) continue;
+            small_scan<K>(spts, ra[s], re[s], qx, qy, qz, best);
         }
         for (int r = 1;; r++) {
             if (r > 1) {                               // rare: shells beyond the first ring, row by row

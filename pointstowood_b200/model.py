@@ -14,8 +14,10 @@ the execution of the hot path (src/model.py:103-127, src/pointnet.py:116-132):
 * the dense per-point blocks (stem, InvertedResidualBlock, FP MLPs, head) stay torch/cuBLAS
   modules evaluated in [N, C] layout (k=1 Conv1d == Linear), optionally under bf16 autocast.
 
-Inference (eval mode) only; the training-mode branch (random 50 % sampling, batch-stat BN inside
-local_nn) belongs to the train.py row of SURVEY.md §8(f) and raises.
+Training mode (train.py, BASELINE.json configs[4]) keeps the reference's semantics -- random 50 %
+sampling (src/model.py:97-101,114), batch-statistics BatchNorm over all E edges inside local_nn -- with
+the graph (radius / kNN tables) from libp2w and the differentiable part in torch autograd on the
+fixed-width neighbour table; the fused forward kernels are eval-mode only.
 """
 from __future__ import annotations
 
@@ -63,6 +65,10 @@ def _bn_affine(bn: nn.BatchNorm1d):
 
 
 def _bn(bn: nn.BatchNorm1d, x: Tensor) -> Tensor:
+    """BatchNorm1d over the rows of [N, C]: running statistics in eval mode, batch statistics (and the
+    running-statistics update) in training mode, as the module itself would do."""
+    if bn.training:
+        return bn(x)
     return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
 
 
@@ -135,12 +141,32 @@ class PointNetConv(nn.Module):
         table[i, slot] = j.to(torch.int32)
         return table
 
+    def _forward_autograd(self, x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor) -> Tensor:
+        """src/pointnet.py:116-132 + aggr='max' in plain torch on the VALID edges of the table (BatchNorm in
+        local_nn sees exactly the E edges the reference sees); differentiable w.r.t. x and the weights."""
+        valid = nbr >= 0
+        i = torch.arange(nbr.size(0), device=nbr.device).view(-1, 1).expand_as(nbr)[valid]
+        j = nbr[valid].long()
+        rel = pos_src[j, :3] - pos_tgt[i, :3]
+        dist = torch.norm(rel, dim=1)
+        dtab = dist.new_full(nbr.shape, float("-inf"))
+        dtab[valid] = dist
+        maxd = dtab.max(dim=1).values                      # scatter_max(|rel|, i), src/pointnet.py:122
+        msg = torch.cat([x[j], rel / (maxd[i].unsqueeze(1) + 1e-8), pos_src[j, 3:4]], dim=1)
+        h = self.local_nn(msg)
+        tab = h.new_full((nbr.size(0), nbr.size(1), h.size(1)), float("-inf"))
+        tab[valid] = h
+        out = tab.max(dim=1).values
+        return torch.where(valid.any(dim=1, keepdim=True), out, torch.zeros_like(out))   # no edge -> 0 (PyG)
+
     def forward(self, x, pos, nbr: Tensor) -> Tensor:
         if isinstance(x, tuple):
             x = x[0]
         pos_src, pos_tgt = pos if isinstance(pos, tuple) else (pos, pos)
         if nbr.dtype == torch.int64 and nbr.dim() == 2 and nbr.size(0) == 2:
             nbr = self.edge_index_to_table(nbr, pos_tgt.size(0))
+        if self.training or torch.is_grad_enabled() and x.requires_grad:
+            return self._forward_autograd(x.float(), pos_src, pos_tgt, nbr)
         lin1, lin2, bn = self.local_nn[0][0], self.local_nn[1][0], self.local_nn[1][2]
         scale, shift = _bn_affine(bn)
         return ops.pointnet_conv_max(x.float(), pos_src, pos_tgt, nbr, lin1.weight, lin1.bias, lin2.weight, lin2.bias,
@@ -174,13 +200,25 @@ class SAModule(nn.Module):
     def voxelsample(self, pos: Tensor, batch: Tensor, resolution: float) -> Tensor:
         return ops.voxel_sample(pos, resolution, batch)
 
+    def random_sample(self, num_points: int, device) -> Tensor:
+        """src/model.py:97-101: a sorted random half of the rows.  `self.sample_idx` (a tensor, consumed once)
+        pins the draw for parity tests; `self.generator` seeds it otherwise."""
+        pinned = getattr(self, "sample_idx", None)
+        if pinned is not None:
+            self.sample_idx = None
+            return pinned.to(device)
+        gen = getattr(self, "generator", None)
+        perm = torch.randperm(num_points, generator=gen, device=gen.device if gen is not None else "cpu")
+        return torch.sort(perm[: int(num_points * 0.5)]).values.to(device)
+
     def forward(self, x, pos, batch, reflectance, sf):
-        if self.training:
-            raise NotImplementedError("training-mode SAModule (random sampling, batch-stat BN) is not built yet")
         B = sf.numel()
         pos = pos[:, :3].contiguous()
         ptr = ops.batch_to_ptr(batch, B)
-        idx = self.voxelsample(pos, batch, self.resolution)
+        if self.training:
+            idx = self.random_sample(pos.size(0), pos.device)
+        else:
+            idx = self.voxelsample(pos, batch, self.resolution)
         batch_t = batch[idx]
         ptr_t = ops.batch_to_ptr(batch_t, B)
         pos_t = pos[idx]
@@ -202,7 +240,11 @@ class GlobalSAModule(nn.Module):
     def forward(self, x, pos, batch, reflectance, sf):
         B = sf.numel()
         x = self.NN(torch.cat([x, pos], dim=1))
-        x = ops.global_max_pool(x.float(), batch, ptr=ops.batch_to_ptr(batch, B))
+        if x.requires_grad:          # global_max_pool with autograd (src/model.py:136)
+            x = torch.zeros((B, x.size(1)), device=x.device, dtype=x.dtype).scatter_reduce(
+                0, batch.view(-1, 1).expand(-1, x.size(1)), x, "amax", include_self=False)
+        else:
+            x = ops.global_max_pool(x.float(), batch, ptr=ops.batch_to_ptr(batch, B))
         pos = pos.new_zeros((B, 3))
         batch = torch.arange(B, device=batch.device)
         return x, pos, batch, reflectance.new_zeros(B), sf
@@ -218,6 +260,15 @@ class FPModule(nn.Module):
         if num_tiles is None:
             num_tiles = int(batch_skip[-1].item()) + 1
         ptr_x, ptr_y = ops.batch_to_ptr(batch, num_tiles), ops.batch_to_ptr(batch_skip, num_tiles)
+        if x.requires_grad:          # knn_interpolate with autograd (src/model.py:149): the graph from libp2w
+            nbr, d2 = ops.knn_table(pos.contiguous(), pos_skip.contiguous(), self.k, ptr_x, ptr_y, return_d2=True)
+            valid = nbr >= 0
+            # d2 as upstream computes it for the weights: plain sum of squares of the coordinate differences
+            diff = pos[nbr.clamp(min=0).long()] - pos_skip.unsqueeze(1)
+            w = torch.where(valid, 1.0 / torch.clamp((diff * diff).sum(-1), min=1e-16), torch.zeros_like(d2))
+            y = (x[nbr.clamp(min=0).long()] * w.unsqueeze(-1)).sum(1) / w.sum(1, keepdim=True)
+            y = y if x_skip is None else torch.cat([y, x_skip], dim=1)
+            return self.NN(y), pos_skip, batch_skip
         c = x.size(1)
         cs = 0 if x_skip is None else x_skip.size(1)
         buf = torch.empty((pos_skip.size(0), c + cs), device=x.device, dtype=torch.float32)

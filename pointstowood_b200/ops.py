@@ -105,11 +105,11 @@ def _ptrs(x, y, batch_x, batch_y, batch_size):
 GRID_MIN_SOURCES_PER_TILE = 192      # below this average the brute-force sweep wins (identical results)
 
 
-def _use_grid(method: Optional[str], nx: int, tiles: int) -> bool:
+def _use_grid(method: Optional[str], nx: int, tiles: int, k: int = 32) -> bool:
     if method not in (None, "grid", "sweep"):
         raise _lib.P2WError("method must be None, 'grid' or 'sweep'")
-    if method is None:
-        return nx >= GRID_MIN_SOURCES_PER_TILE * max(tiles, 1)
+    if method is None:                    # k <= 4 runs thread-per-query on the cell list: cheap at any tile size
+        return k <= 4 or nx >= GRID_MIN_SOURCES_PER_TILE * max(tiles, 1)
     return method == "grid"
 
 
@@ -134,7 +134,7 @@ def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return
     d2 = torch.empty((y.size(0), k), device=x.device, dtype=torch.float32) if return_d2 else None
     work = 12.0 * (x.size(0) + y.size(0)) + 16.0 * y.size(0) * k + 16.0 * ptr_x.numel()
     L = _lib.lib()
-    if _use_grid(method, x.size(0), T):
+    if _use_grid(method, x.size(0), T, k):
         ws = _grid_ws(x.size(0), T, x.device)
         _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn_grid_ex, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T,
                                      x.size(0), y.size(0), k, float(cell_size), _dp(nbr), _dp(d2), _dp(ws), ws.numel(),
