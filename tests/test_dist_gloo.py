@@ -101,3 +101,35 @@ def test_shard_contiguous_partitions_and_balances():
         assert sum(shards, []) == list(range(len(batches)))                                     # a partition, in order
         load = [sum(int(ptr[batches[b][1]] - ptr[batches[b][0]]) for b in s) for s in shards]
         assert max(load) <= 1.15 * (ptr[-1] / world) + 8 * 16384
+
+
+def _worker_grads(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pointstowood_b200.trainer import GradientAllReduce
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(n)) for n in (1000, 37, 5000, 1)]
+    params[1].requires_grad_(False)                                     # frozen parameters stay out of the exchange
+    for i, p in enumerate(params):
+        if p.requires_grad:
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    GradientAllReduce(params, bucket_bytes=8000)()                      # several buckets
+    mean = (1 + 2) / 2
+    ok = all(torch.allclose(p.grad, torch.full_like(p, mean * (i + 1))) for i, p in enumerate(params) if p.requires_grad)
+    out.put((rank, bool(ok and params[1].grad is None)))
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world_size_2():
+    """train.py's only collective: bucketed gradient averaging."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_grads, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in got)

@@ -95,3 +95,16 @@ def test_plan_launches_groups_consecutive_batches_under_a_point_budget():
     assert plan_launches(batches, ptr, [0, 1, 2], 1) == [[0], [1], [2]]      # a batch is never split
     assert plan_launches(batches, ptr, [0, 2], 1 << 30) == [[0], [2]]        # only consecutive batches merge
     assert plan_launches(batches, ptr, [], 10) == []
+
+
+def test_poly1_focal_loss_matches_oracle_restatement():
+    import torch
+    from oracle import ref_model
+    from pointstowood_b200.trainer import Poly1FocalLoss
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(4000, generator=g) * 6
+    y = (torch.rand(4000, generator=g) > 0.7).float()
+    got, gamma = Poly1FocalLoss(reduction="mean", gamma=2.0, alpha=None, label_smoothing=0.1)(z, y)
+    assert gamma == 2.0 and torch.equal(got, ref_model.poly1_focal_loss(z, y))
+    none, _ = Poly1FocalLoss(alpha=0.25)(z, y)
+    assert none.shape == z.shape and (none >= 0).all()
