@@ -44,7 +44,7 @@ def make_batch(n_points, side, seed, n_tiles):
 
 
 def main():
-    sd = ref_model.seeded_state_dict()
+    sd = ref_model.seeded_state_dict(randomise=False)      # fresh BatchNorm affine: the state training starts from
     pos, refl, batch, sf, y = make_batch(5000, 2.4, 21, 2)
     g = torch.Generator().manual_seed(4)
     halves, n = [], pos.size(0)

@@ -189,7 +189,7 @@ def _net_forward(sd, pos, reflectance, batch, sf, trace, idx_list):
     return x.squeeze(-1).float()
 
 
-def seeded_state_dict(seed: int = 141190, bn_seed: int = 5):
+def seeded_state_dict(seed: int = 141190, bn_seed: int = 5, randomise: bool = True):
     """Reference-format state dict with seeded weights (the checkpoint is absent:
     /root/reference/.MISSING_LARGE_BLOBS).  Shapes follow SURVEY.md Appendix D; init
     follows model.py:9-16 (Xavier-uniform Linear, Kaiming-uniform Conv1d, zero bias).
@@ -248,7 +248,8 @@ def seeded_state_dict(seed: int = 141190, bn_seed: int = 5):
     conv("conv1", 16 * C, 16 * C)
     conv("conv2", 1, 16 * C)
     bn("norm", 16 * C)
-    randomise_bn(sd, bn_seed)
+    if randomise:        # False: BatchNorm as freshly initialised (weight 1, bias 0), the state training starts from
+        randomise_bn(sd, bn_seed)
     return sd
 
 
