@@ -45,6 +45,12 @@ N_POINTS = 1_000_000
 CFG = dict(grid_size=(2.0, 4.0), min_pts=128, max_pts=16384, batch_size=8, is_wood=0.5)
 
 
+def workload(n_points: int) -> str:
+    """The same description on both arms (BASELINE.json configs[1])."""
+    return (f"predict {n_points}-point synthetic TLS plot per GPU, grid 2/4 m, min_pts 128, max_pts 16384, batch_size 8, "
+            "seeded weights; cloud -> tiles -> network -> spatial vote -> (label, pwood) per point")
+
+
 def load_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernels, from the
     committed `ncu --set full` capture of this workload (profiles/traffic.json; null if absent)."""
@@ -164,9 +170,8 @@ def run_reference(args):
     line = dict(impl="reference", metric="points classified/sec", value=value, unit="points/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="predict 1M-point synthetic TLS plot, grid 2/4 m, min_pts 128, max_pts 16384, "
-                                     "batch_size 8; cloud -> tiles -> network -> spatial vote (CPU: reference pipeline "
-                                     "restated on oracle ops, bounded sample)"),
+                config=dict(workload=workload(N_POINTS),
+                            arm="reference pipeline restated on oracle CPU ops (kind: port), bounded sample per step"),
                 cpu_baseline=base,
                 e2e=dict(value=value, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -298,9 +303,7 @@ def main():
         line = dict(metric="points classified/sec", value=world * n_points / (ms / 1e3), unit="points/s", n_gpus=world,
                     steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="bf16" if bf16 else "f32", data="synthetic",
-                    config=dict(workload=f"predict {n_points}-point synthetic TLS plot per GPU, grid 2/4 m, min_pts 128, "
-                                         "max_pts 16384, batch_size 8, seeded weights; cloud -> tiles -> network -> spatial vote "
-                                         "-> (label, pwood) per point",
+                    config=dict(workload=workload(n_points),
                                 tile_points=tile_points, tiles=int(store.num_tiles),
                                 launch_points=args.launch_points,
                                 l2="no flush needed: a step streams > 4 GB of activations (e.g. the [N0, 544] and "

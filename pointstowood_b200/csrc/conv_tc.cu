@@ -51,8 +51,15 @@ constexpr int LBO1 = NT * 16 + 16;             // k-chunk stride of the msg tile
 constexpr int TMEM_COLS = 2 * NT;
 constexpr unsigned FULL = 0xffffffffu;
 
-// timing experiments only (P2W_CONV_DEBUG & 16): clock64 timeline of the MMA thread of CTA 0
+// Timing experiments (tools/conv_timeline.py, tools/prof_conv.py): compile with -DP2W_CONV_INSTRUMENT and set
+// the environment variable P2W_CONV_DEBUG to a bit mask -- 1 no weight streaming, 2 no feature gather, 4 empty
+// epilogues, 8 no MMAs, 16 clock64 timeline of the MMA warp of CTA 0.  The default build has none of it.
+#ifdef P2W_CONV_INSTRUMENT
 __device__ long long g_timeline[8192];
+#define P2W_DBG(p, bit) ((p).debug & (bit))
+#else
+#define P2W_DBG(p, bit) 0
+#endif
 
 struct ConvTcParams {
     const void *x;                 // [n_src, C] FP32 or BF16 (x_bf16)
@@ -62,7 +69,7 @@ struct ConvTcParams {
     int K, C, H, Co, K1p, NB1, NB2, num_tiles, x_bf16, out_bf16;
     int msg_bufs;                  // msg tiles in shared memory (the gather runs msg_bufs - 1 tiles ahead)
     int stages, resident;          // ring depth; resident: the ring holds ALL weight slices, loaded once
-    int debug;                     // timing experiments only (P2W_CONV_DEBUG): 1 no weight re-streaming, 2 no feature gather
+    int debug;                     // P2W_CONV_INSTRUMENT builds only
     const unsigned char *wpack;
     const float *b1p, *b2p, *scale, *shift;
     void *out;                     // [n_tgt, Co] FP32 or BF16 (out_bf16)
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         int slot = 0;
         uint32_t ph = 0;
         const int per_tile = p.NB1 * n1 + p.NB2 * n2;
-        const int passes = (p.debug & 1) ? 0 : (p.resident ? (my_tiles > 0 ? 1 : 0) : my_tiles);
+        const int passes = P2W_DBG(p, 1) ? 0 : (p.resident ? (my_tiles > 0 ? 1 : 0) : my_tiles);
         for (int it = 0; it < passes; it++) {
             const unsigned char *src = p.wpack;
             for (int s = 0; s < per_tile; s++) {
@@ -229,10 +236,14 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         const uint64_t b1_desc0 = smem_desc(smem_u32(b1), LBO1, 128);             // + s * 4 LBO1/16 (+ 2 LBO1/16)
         const uint64_t b2_desc0 = smem_desc(smem_u32(b2), 128, p.H * 16);         // + s * 32 (+ 16)
         constexpr uint32_t ID1 = instr_desc(false), ID2 = instr_desc(true);
-        const bool stream = !(p.resident || (p.debug & 1));
-        const bool rec = (p.debug & 16) && blockIdx.x == 0;
+        const bool stream = !(p.resident || P2W_DBG(p, 1));
+        const bool rec = P2W_DBG(p, 16) && blockIdx.x == 0;
         int nrec = 0;
+#ifdef P2W_CONV_INSTRUMENT
 #define P2W_TS(tag) do { if (rec && lane == 0 && nrec < 4090) { g_timeline[2 + nrec++] = (clock64() << 8) | (tag); } } while (0)
+#else
+#define P2W_TS(tag) do { } while (0)
+#endif
         for (int it = 0; it < my_tiles; it++) {
 #pragma unroll 1
             for (int layer = 0; layer < 2; layer++) {
@@ -252,10 +263,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                     const uint32_t d_addr = tmem_base + acc * NT;
                     uint64_t bd = b_desc0;
                     for (int s = 0; s < ns; s++) {
-                        if (stream || (it == 0 && !(p.debug & 1))) mbar_wait(&ring_full[slot], ph);
+                        if (stream || (it == 0 && !P2W_DBG(p, 1))) mbar_wait(&ring_full[slot], ph);
                         const uint64_t ad = a_desc0 + static_cast<uint32_t>(slot) * (SLICE_BYTES >> 4);
                         if (elect_one()) {
-                            if (!(p.debug & 8)) {
+                            if (!P2W_DBG(p, 8)) {
                                 umma(d_addr, ad, bd, idesc, s ? 1u : 0u);
                                 umma(d_addr, ad + 256u, bd + b_half, idesc, 1u);
                             }
@@ -274,7 +285,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             tph ^= 1;
             if (++mbuf == MB) { mbuf = 0; mph ^= 1; }
         }
+#ifdef P2W_CONV_INSTRUMENT
         if (rec && lane == 0) g_timeline[0] = nrec;
+#endif
+        (void)rec; (void)nrec;
 #undef P2W_TS
         __syncwarp();
     } else if (warp >= 4) {
@@ -338,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             j1 = j2; m1 = m2; pt1 = pt2;
             gather_bar();
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
-            if (p.debug & 2) {
+            if (P2W_DBG(p, 2)) {
             } else if (p.x_bf16) {
                 const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16 *>(p.x);
                 for (int r0 = gw * rpw; r0 < NT; r0 += GATHER_WARPS * rpw * 4) {
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // layer 2 of the previous tile is done with hid
                 const int h = blk * 128 + 32 * q + lane;
 #pragma unroll
-                for (int c = 0; c < ((p.debug & 4) ? 0 : NT / 32); c++) {
+                for (int c = 0; c < (P2W_DBG(p, 4) ? 0 : NT / 32); c++) {
                     const int n0 = c * 32;
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + n0, r);
@@ -437,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 const float bias = p.b2p[co], sc = p.scale[co], sh = p.shift[co];
                 const float sgn = sc < 0.f ? -1.f : 1.f;      // rows with a negative BN scale were packed negated
 #pragma unroll
-                for (int tt = 0; tt < ((p.debug & 4) ? 0 : TPT); tt++) {
+                for (int tt = 0; tt < (P2W_DBG(p, 4) ? 0 : TPT); tt++) {
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + tt * 32, r);
                     float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]),
@@ -529,9 +543,11 @@ inline TcPlan tc_plan(int c_in, int hidden, int c_out) {
 
 using namespace p2w;
 
+#ifdef P2W_CONV_INSTRUMENT
 extern "C" int p2wdbg_conv_timeline(long long *dst_host, int n) {
     return (int)cudaMemcpyFromSymbol(dst_host, g_timeline, sizeof(long long) * n);
 }
+#endif
 
 size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out) { return tc_plan(c_in, hidden, c_out).total; }
 
@@ -594,11 +610,14 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     ConvTcParams p;
     p.x_bf16 = x_bf16; p.out_bf16 = out_bf16;
     p.stages = stages; p.resident = resident; p.msg_bufs = msg_bufs;
+    p.debug = 0;
+#ifdef P2W_CONV_INSTRUMENT
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("P2W_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
         p.debug = dbg;
     }
+#endif
     p.x = x; p.pos_src = pos_src; p.pos_tgt = pos_tgt; p.nbr = nbr;
     p.n_tgt = n_tgt; p.K = k; p.C = c_in; p.H = hidden; p.Co = c_out;
     p.K1p = t.K1p; p.NB1 = t.NB1; p.NB2 = t.NB2;

@@ -1,4 +1,5 @@
-"""Timing experiment: clock64 timeline of conv_tc's MMA thread (CTA 0), P2W_CONV_DEBUG must include 16."""
+"""Timing experiment: clock64 timeline of conv_tc's MMA warp (CTA 0).  Needs an instrumented build
+(P2W_CONV_INSTRUMENT=1 python -m pointstowood_b200.build --force) and P2W_CONV_DEBUG including 16."""
 import ctypes
 import os
 import sys
