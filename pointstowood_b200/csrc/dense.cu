@@ -19,47 +19,63 @@ __device__ __forceinline__ float chain(float v, float s1, float t1, float s2, fl
     return v;
 }
 
-// one thread = 8 consecutive channels of one row
+// A thread owns ONE group of 8 channels and walks down the rows: its 16 / 32 per-channel constants stay in
+// registers, and consecutive threads cover consecutive 16-byte pieces of a row (coalesced); two rows per
+// iteration keep two loads in flight per thread.
 template <bool TWO, bool BF16>
 __global__ void __launch_bounds__(256) affine_relu_kernel(const void *__restrict__ xin, void *__restrict__ yout,
                                                           int64_t n, int c, const float *__restrict__ s1,
                                                           const float *__restrict__ t1, const float *__restrict__ s2,
                                                           const float *__restrict__ t2) {
     const int c8 = c >> 3;
-    const int64_t total = n * c8;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int ch = static_cast<int>(i % c8) * 8;
-        float a1[8], b1[8], a2[8], b2[8];
-        *reinterpret_cast<float4 *>(a1) = __ldg(reinterpret_cast<const float4 *>(s1 + ch));
-        *reinterpret_cast<float4 *>(a1 + 4) = __ldg(reinterpret_cast<const float4 *>(s1 + ch + 4));
-        *reinterpret_cast<float4 *>(b1) = __ldg(reinterpret_cast<const float4 *>(t1 + ch));
-        *reinterpret_cast<float4 *>(b1 + 4) = __ldg(reinterpret_cast<const float4 *>(t1 + ch + 4));
-        if (TWO) {
-            *reinterpret_cast<float4 *>(a2) = __ldg(reinterpret_cast<const float4 *>(s2 + ch));
-            *reinterpret_cast<float4 *>(a2 + 4) = __ldg(reinterpret_cast<const float4 *>(s2 + ch + 4));
-            *reinterpret_cast<float4 *>(b2) = __ldg(reinterpret_cast<const float4 *>(t2 + ch));
-            *reinterpret_cast<float4 *>(b2 + 4) = __ldg(reinterpret_cast<const float4 *>(t2 + ch + 4));
-        }
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int g = static_cast<int>(tid % c8);                     // nthreads is a multiple of c8 (see the launch)
+    const int64_t row0 = tid / c8, row_step = nthreads / c8;
+    const int ch = g * 8;
+    float a1[8], b1[8], a2[8], b2[8];
+    *reinterpret_cast<float4 *>(a1) = __ldg(reinterpret_cast<const float4 *>(s1 + ch));
+    *reinterpret_cast<float4 *>(a1 + 4) = __ldg(reinterpret_cast<const float4 *>(s1 + ch + 4));
+    *reinterpret_cast<float4 *>(b1) = __ldg(reinterpret_cast<const float4 *>(t1 + ch));
+    *reinterpret_cast<float4 *>(b1 + 4) = __ldg(reinterpret_cast<const float4 *>(t1 + ch + 4));
+    if (TWO) {
+        *reinterpret_cast<float4 *>(a2) = __ldg(reinterpret_cast<const float4 *>(s2 + ch));
+        *reinterpret_cast<float4 *>(a2 + 4) = __ldg(reinterpret_cast<const float4 *>(s2 + ch + 4));
+        *reinterpret_cast<float4 *>(b2) = __ldg(reinterpret_cast<const float4 *>(t2 + ch));
+        *reinterpret_cast<float4 *>(b2 + 4) = __ldg(reinterpret_cast<const float4 *>(t2 + ch + 4));
+    }
+    for (int64_t r = row0; r < n; r += 2 * row_step) {
+        const int64_t i0 = r * c8 + g, i1 = (r + row_step) * c8 + g;
+        const bool second = r + row_step < n;
         if (BF16) {
-            uint4 raw = reinterpret_cast<const uint4 *>(xin)[i];
-            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&raw);
+            uint4 raw0 = reinterpret_cast<const uint4 *>(xin)[i0];
+            uint4 raw1 = second ? reinterpret_cast<const uint4 *>(xin)[i1] : make_uint4(0, 0, 0, 0);
+            __nv_bfloat162 *h0 = reinterpret_cast<__nv_bfloat162 *>(&raw0), *h1 = reinterpret_cast<__nv_bfloat162 *>(&raw1);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                float2 f = __bfloat1622float2(h[u]);
+                float2 f = __bfloat1622float2(h0[u]), e = __bfloat1622float2(h1[u]);
                 f.x = chain<TWO>(f.x, a1[2 * u], b1[2 * u], a2[2 * u], b2[2 * u]);
                 f.y = chain<TWO>(f.y, a1[2 * u + 1], b1[2 * u + 1], a2[2 * u + 1], b2[2 * u + 1]);
-                h[u] = __floats2bfloat162_rn(f.x, f.y);
+                e.x = chain<TWO>(e.x, a1[2 * u], b1[2 * u], a2[2 * u], b2[2 * u]);
+                e.y = chain<TWO>(e.y, a1[2 * u + 1], b1[2 * u + 1], a2[2 * u + 1], b2[2 * u + 1]);
+                h0[u] = __floats2bfloat162_rn(f.x, f.y);
+                h1[u] = __floats2bfloat162_rn(e.x, e.y);
             }
-            reinterpret_cast<uint4 *>(yout)[i] = raw;
+            reinterpret_cast<uint4 *>(yout)[i0] = raw0;
+            if (second) reinterpret_cast<uint4 *>(yout)[i1] = raw1;
         } else {
-            float v[8];
-            *reinterpret_cast<float4 *>(v) = reinterpret_cast<const float4 *>(xin)[2 * i];
-            *reinterpret_cast<float4 *>(v + 4) = reinterpret_cast<const float4 *>(xin)[2 * i + 1];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = chain<TWO>(v[u], a1[u], b1[u], a2[u], b2[u]);
-            reinterpret_cast<float4 *>(yout)[2 * i] = *reinterpret_cast<float4 *>(v);
-            reinterpret_cast<float4 *>(yout)[2 * i + 1] = *reinterpret_cast<float4 *>(v + 4);
+            for (int half = 0; half < 2; half++) {
+                if (half && !second) break;
+                const int64_t i = half ? i1 : i0;
+                float v[8];
+                *reinterpret_cast<float4 *>(v) = reinterpret_cast<const float4 *>(xin)[2 * i];
+                *reinterpret_cast<float4 *>(v + 4) = reinterpret_cast<const float4 *>(xin)[2 * i + 1];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = chain<TWO>(v[u], a1[u], b1[u], a2[u], b2[u]);
+                reinterpret_cast<float4 *>(yout)[2 * i] = *reinterpret_cast<float4 *>(v);
+                reinterpret_cast<float4 *>(yout)[2 * i + 1] = *reinterpret_cast<float4 *>(v + 4);
+            }
         }
     }
 }
@@ -80,9 +96,18 @@ extern "C" int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, con
                 "p2w_affine_relu: pointers must be 16-byte aligned");
     if (n == 0) return P2W_OK;
     cudaStream_t st = as_stream(stream);
-    const int64_t total = n * (c >> 3);
+    // the thread count is a multiple of the channel groups per row, so that a thread keeps its group
+    const int c8 = c >> 3;
+    const int64_t total = n * c8;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    {
+        int64_t lcm_blocks = c8;                       // blocks * 256 % c8 == 0  <=  blocks % (c8 / gcd(c8, 256)) == 0
+        int64_t a = c8, b = 256;
+        while (b) { const int64_t t = a % b; a = b; b = t; }
+        lcm_blocks = c8 / a;
+        blocks = (blocks + lcm_blocks - 1) / lcm_blocks * lcm_blocks;
+    }
     const bool two = s2 != nullptr, bf = dtype == P2W_BF16;
     if (two && bf) P2W_LAUNCH((affine_relu_kernel<true, true>), (unsigned)blocks, 256, 0, st)(x, y, n, c, s1, t1, s2, t2);
     else if (two) P2W_LAUNCH((affine_relu_kernel<true, false>), (unsigned)blocks, 256, 0, st)(x, y, n, c, s1, t1, s2, t2);

@@ -60,8 +60,45 @@ __device__ __forceinline__ unsigned spread6(unsigned v) {   // 6 bits -> every t
 }
 
 // ------------------------------------------------------------------ plan: one CTA per tile
+// ---- bounding box of ONE huge tile (plot-wide searches) by all SMs; grid_plan_kernel then skips its own pass
+__device__ __forceinline__ void atomic_max_f(float *a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_f(float *a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+__global__ void box_init_kernel(float *box) {
+    if (threadIdx.x < 3) box[threadIdx.x] = __int_as_float(0x7f800000);
+    else if (threadIdx.x < 6) box[threadIdx.x] = __int_as_float(0xff800000);
+}
+__global__ void __launch_bounds__(256) box_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ box) {
+    float lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { lo[d] = __int_as_float(0x7f800000); hi[d] = __int_as_float(0xff800000); }
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const float v = x[i * 3 + d];
+            lo[d] = fminf(lo[d], v);
+            hi[d] = fmaxf(hi[d], v);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        for (int o = 16; o; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(FULL, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(FULL, hi[d], o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomic_min_f(&box[d], lo[d]); atomic_max_f(&box[3 + d], hi[d]); }
+    }
+}
+
 __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict__ x,
                                                         const int64_t *__restrict__ ptr_x, float tau, float cell_hint,
+                                                        const float *__restrict__ pre_box,
                                                         GridTile *__restrict__ grid) {
     __shared__ unsigned bits[8192];          // 64^3 occupancy bits, Morton order
     __shared__ float s_lo[16][3], s_hi[16][3];
@@ -74,13 +111,18 @@ __global__ void __launch_bounds__(512) grid_plan_kernel(const float *__restrict_
     float lo[3], hi[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) { lo[d] = __int_as_float(0x7f800000); hi[d] = __int_as_float(0xff800000); }
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    if (pre_box == nullptr) {
+        for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const float v = x[i * 3 + d];
-            lo[d] = fminf(lo[d], v);
-            hi[d] = fmaxf(hi[d], v);
+            for (int d = 0; d < 3; d++) {
+                const float v = x[i * 3 + d];
+                lo[d] = fminf(lo[d], v);
+                hi[d] = fmaxf(hi[d], v);
+            }
         }
+    } else {
+#pragma unroll
+        for (int d = 0; d < 3; d++) { lo[d] = pre_box[d]; hi[d] = pre_box[3 + d]; }
     }
 #pragma unroll
     for (int d = 0; d < 3; d++) {
@@ -559,6 +601,14 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
                 const int nmax = max(g.nx, max(g.ny, g.nz));
                 const float margin = 1e-5f * g.h * static_cast<float>(nmax) +
                                      4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz));
+                // safe (shrunk) gaps from the query to the faces of its own cell: lower bounds for whole cells / rows
+                const float fx = g.ox + static_cast<float>(cx) * g.h, fy = g.oy + static_cast<float>(cy) * g.h,
+                            fz = g.oz + static_cast<float>(cz) * g.h;
+                const float k1 = 1.f - 1e-4f;
+                const float lox = fmaxf((qx - fx) * k1 - margin, 0.f), hix = fmaxf((fx + g.h - qx) * k1 - margin, 0.f);
+                const float loy = fmaxf((qy - fy) * k1 - margin, 0.f), hiy = fmaxf((fy + g.h - qy) * k1 - margin, 0.f);
+                const float loz = fmaxf((qz - fz) * k1 - margin, 0.f), hiz = fmaxf((fz + g.h - qz) * k1 - margin, 0.f);
+                const float hs = g.h * k1;             // a further whole cell in between adds at least this much
                 // ---- ring 1, cell by cell: own cell + face neighbours, then edge, then corner neighbours;
                 //      a cell whose nearest point is provably beyond the current k-th distance is skipped
                 {
@@ -574,15 +624,10 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
                         a = __ldg(cell_start + c);
                         len = static_cast<int>(__ldg(cell_start + c + 1) - a);
                     }
-                    // squared distance from the query to the neighbour cell, shrunk by the safety margin
-                    const float fx = g.ox + static_cast<float>(cx) * g.h, fy = g.oy + static_cast<float>(cy) * g.h,
-                                fz = g.oz + static_cast<float>(cz) * g.h;
-                    const float gx = ddx < 0 ? qx - fx : (ddx > 0 ? fx + g.h - qx : 0.f);
-                    const float gy = ddy < 0 ? qy - fy : (ddy > 0 ? fy + g.h - qy : 0.f);
-                    const float gz = ddz < 0 ? qz - fz : (ddz > 0 ? fz + g.h - qz : 0.f);
-                    const float sx = ddx ? fmaxf(gx * (1.f - 1e-4f) - margin, 0.f) : 0.f;
-                    const float sy = ddy ? fmaxf(gy * (1.f - 1e-4f) - margin, 0.f) : 0.f;
-                    const float sz = ddz ? fmaxf(gz * (1.f - 1e-4f) - margin, 0.f) : 0.f;
+                    // squared distance from the query to the neighbour cell (safe lower bound)
+                    const float sx = ddx < 0 ? lox : (ddx > 0 ? hix : 0.f);
+                    const float sy = ddy < 0 ? loy : (ddy > 0 ? hiy : 0.f);
+                    const float sz = ddz < 0 ? loz : (ddz > 0 ? hiz : 0.f);
                     const float b2 = sx * sx + sy * sy + sz * sz;
 #pragma unroll 1
                     for (int stage = 0; stage < 3; stage++) {
@@ -616,7 +661,18 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
                                     x0 = x1 = (t & 1) ? cx + r : cx - r;
                                 }
                                 const int yy = cy + dy, zz = cz + dz;
-                                if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+                                // lower bound of the segment: |d| - 1 whole cells plus the gap inside the own cell
+                                const float sy = dy < 0 ? loy + static_cast<float>(-dy - 1) * hs
+                                                        : (dy > 0 ? hiy + static_cast<float>(dy - 1) * hs : 0.f);
+                                const float sz = dz < 0 ? loz + static_cast<float>(-dz - 1) * hs
+                                                        : (dz > 0 ? hiz + static_cast<float>(dz - 1) * hs : 0.f);
+                                const float sx = x0 != x1 ? 0.f
+                                                          : (x0 < cx ? lox + static_cast<float>(r - 1) * hs
+                                                                     : hix + static_cast<float>(r - 1) * hs);
+                                const float lim = RADIUS ? r2 : __uint_as_float(static_cast<unsigned>(thr >> 32));
+                                const float b2 = sx * sx + sy * sy + sz * sz;
+                                const bool reach = RADIUS ? b2 < lim : b2 <= lim;
+                                if (reach && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
                                     x0 = max(x0, 0);
                                     x1 = min(x1, g.nx - 1);
                                     if (x0 <= x1) {
@@ -795,6 +851,7 @@ __global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__r
 struct GridWs {
     GridTile *grid;
     uint32_t *slot, *cell_start, *fill, *bsum;
+    float *box;
     float4 *spts;
     int64_t table;     // entries of cell_start / fill (bound on the total number of cells, + 1)
     size_t total;
@@ -813,6 +870,7 @@ inline GridWs grid_ws(void *base, int64_t nx, int T) {
     };
     w.table = 4 * nx + 64 * static_cast<int64_t>(T) + 1;       // sum over tiles of max(4 n_b, 64), + the end slot
     w.grid = static_cast<GridTile *>(take(sizeof(GridTile) * static_cast<size_t>(T)));
+    w.box = static_cast<float *>(take(64));
     w.slot = static_cast<uint32_t *>(take(4 * static_cast<size_t>(nx)));
     w.spts = static_cast<float4 *>(take(16 * static_cast<size_t>(nx)));
     w.cell_start = static_cast<uint32_t *>(take(4 * static_cast<size_t>(w.table)));
@@ -834,7 +892,13 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
                 "%s: workspace too small or misaligned (%zu bytes needed)", what, w.total);
     const float tau = fmaxf(1.f, 0.45f * static_cast<float>(k));
     P2W_REQUIRE(cell_hint >= 0.f && cell_hint < 1e30f, "%s: bad cell size", what);
-    P2W_LAUNCH(grid_plan_kernel, T, 512, 0, st)(x, ptr_x, tau, cell_hint, w.grid);
+    const float *pre_box = nullptr;
+    if (T == 1 && cell_hint > 0.f && nx > 65536) {          // one plot-wide tile: the box is everybody's job
+        P2W_LAUNCH(box_init_kernel, 1, 32, 0, st)(w.box);
+        P2W_LAUNCH(box_kernel, kNumSMs * 8, 256, 0, st)(x, nx, w.box);
+        pre_box = w.box;
+    }
+    P2W_LAUNCH(grid_plan_kernel, T, 512, 0, st)(x, ptr_x, tau, cell_hint, pre_box, w.grid);
     P2W_LAUNCH(grid_base_kernel, 1, 1024, 0, st)(w.grid, T);
     // cell_start and fill are adjacent: one memset clears both
     cudaMemsetAsync(w.cell_start, 0, reinterpret_cast<unsigned char *>(w.fill + w.table) -
