@@ -164,14 +164,16 @@ int p2w_pointnet_conv_max(const float *x, const float *pos_src, const float *pos
 /* Extended form: feature rows in / out may be BF16 in the tensor-core mode (x_dtype, out_dtype =
  * P2W_F32 | P2W_BF16), and flags & P2W_CONV_WS_PACKED says `ws` still holds the weights re-laid-out
  * by an earlier call with the same (w1, b1, w2, b2, bn) and mode, so the packing kernels are skipped
- * (a model packs once). */
+ * (a model packs once).  tgt_index (may be NULL, int64 [n_tgt], tensor-core mode): target t sits at
+ * pos_tgt[tgt_index[t]] -- pass pos_src as pos_tgt and the sampled indices instead of gathering pos[idx]. */
 #define P2W_CONV_WS_PACKED 1
 int p2w_pointnet_conv_max_ex(const void *x, int32_t x_dtype, const float *pos_src, const float *pos_tgt,
                              const int32_t *nbr, int64_t n_src, int64_t n_tgt, int32_t k,
                              int32_t c_in, int32_t hidden, int32_t c_out,
                              const float *w1, const float *b1, const float *w2, const float *b2,
                              const float *bn_scale, const float *bn_shift, void *out, int32_t out_dtype,
-                             int32_t mode, void *ws, size_t ws_bytes, int32_t flags, p2w_stream_t stream);
+                             int32_t mode, void *ws, size_t ws_bytes, int32_t flags, const int64_t *tgt_index,
+                             p2w_stream_t stream);
 size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, int32_t mode);
 
 /* ---- knn_interpolate (src/model.py:149, torch_geometric.nn.knn_interpolate) ---------
@@ -200,6 +202,11 @@ int p2w_knn_interpolate_cat(const void *x, int32_t x_dtype, const float *pos_x, 
  * on [n, c] activations (c % 8 == 0; x may alias y). */
 int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, const float *s1, const float *t1,
                     const float *s2, const float *t2, int32_t dtype, p2w_stream_t stream);
+
+/* out[r] = dot(x[r, :], w) + bias over [n, c] FP32 / BF16 rows (c % 8 == 0, c <= 1024): the 1-channel head
+ * conv2 (src/model.py:243) as one streaming pass instead of a GEMM with one output column. */
+int p2w_rowdot(const void *x, int32_t dtype, int64_t n, int32_t c, const float *w, float bias, float *out,
+               p2w_stream_t stream);
 
 /* ---- segment / scatter reductions ---------------------------------------------------
  * p2w_segment_max: torch_geometric global_max_pool (src/model.py:136) for a sorted batch

@@ -41,13 +41,14 @@ SIGNATURES = {
     "p2w_pointnet_conv_max": (c_int32, [_P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                         _P, _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
     "p2w_pointnet_conv_max_ex": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
-                                           _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, c_int32, _P]),
+                                           _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, c_int32, _P, _P]),
     "p2w_pointnet_conv_ws_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "p2w_knn_interpolate": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "p2w_knn_interpolate_ex": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, c_int32, _P]),
     "p2w_knn_interpolate_cat": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int32, c_int32, c_int32,
                                           _P, c_int32, _P]),
     "p2w_affine_relu": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, _P]),
+    "p2w_rowdot": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_float, _P, _P]),
     "p2w_segment_max": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "p2w_scatter_minmax": (c_int32, [_P, _P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),
     "p2w_sa_prepare": (c_int32, [_P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P, _P]),

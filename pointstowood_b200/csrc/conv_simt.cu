@@ -311,7 +311,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
                        int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out,
                        const float *w1, const float *b1, const float *w2, const float *b2, const float *bn_scale,
                        const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
-                       bool packed);
+                       bool packed, const int64_t *tgt_index);
 size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out);
 
 extern "C" size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, int32_t mode) {
@@ -323,7 +323,7 @@ static int conv_dispatch(const void *xv, int32_t x_dtype, const float *pos_src, 
                          const int32_t *nbr, int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden,
                          int32_t c_out, const float *w1, const float *b1, const float *w2, const float *b2,
                          const float *bn_scale, const float *bn_shift, void *outv, int32_t out_dtype, int32_t mode,
-                         void *ws, size_t ws_bytes, p2w_stream_t stream, bool packed) {
+                         void *ws, size_t ws_bytes, p2w_stream_t stream, bool packed, const int64_t *tgt_index = nullptr) {
     P2W_REQUIRE((x_dtype == P2W_F32 || x_dtype == P2W_BF16) && (out_dtype == P2W_F32 || out_dtype == P2W_BF16),
                 "p2w_pointnet_conv_max: unknown dtype");
     P2W_REQUIRE(mode == P2W_CONV_BF16_TC || (x_dtype == P2W_F32 && out_dtype == P2W_F32),
@@ -341,7 +341,8 @@ static int conv_dispatch(const void *xv, int32_t x_dtype, const float *pos_src, 
     if (mode == P2W_CONV_BF16_TC)
         return p2w_conv_tc_launch(xv, x_dtype == P2W_BF16, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out,
                                   w1, b1, w2, b2, bn_scale, bn_shift, outv, out_dtype == P2W_BF16, ws, ws_bytes, st,
-                                  packed);
+                                  packed, tgt_index);
+    P2W_REQUIRE(tgt_index == nullptr, "p2w_pointnet_conv_max: tgt_index needs the tensor-core mode");
     const int K1 = c_in + 4;
     float *w1t = static_cast<float *>(ws);
     float *w2t = w1t + static_cast<size_t>(K1) * hidden;
@@ -377,10 +378,11 @@ extern "C" int p2w_pointnet_conv_max_ex(const void *x, int32_t x_dtype, const fl
                                         int32_t hidden, int32_t c_out, const float *w1, const float *b1,
                                         const float *w2, const float *b2, const float *bn_scale,
                                         const float *bn_shift, void *out, int32_t out_dtype, int32_t mode, void *ws,
-                                        size_t ws_bytes, int32_t flags, p2w_stream_t stream) {
+                                        size_t ws_bytes, int32_t flags, const int64_t *tgt_index,
+                                        p2w_stream_t stream) {
     return conv_dispatch(x, x_dtype, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out, w1, b1, w2, b2,
                          bn_scale, bn_shift, out, out_dtype, mode, ws, ws_bytes, stream,
-                         (flags & P2W_CONV_WS_PACKED) != 0);
+                         (flags & P2W_CONV_WS_PACKED) != 0, tgt_index);
 }
 
 extern "C" int p2w_knn_interpolate_ex(const void *x, int32_t x_dtype, const float *pos_x, const float *pos_y,

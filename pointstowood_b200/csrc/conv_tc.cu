@@ -65,6 +65,7 @@ struct ConvTcParams {
     const void *x;                 // [n_src, C] FP32 or BF16 (x_bf16)
     const float *pos_src, *pos_tgt;
     const int32_t *nbr;
+    const int64_t *tgt_index;       // optional: target t sits at pos_tgt[tgt_index[t]]
     int64_t n_tgt;
     int K, C, H, Co, K1p, NB1, NB2, num_tiles, x_bf16, out_bf16;
     int msg_bufs;                  // msg tiles in shared memory (the gather runs msg_bufs - 1 tiles ahead)
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 const int64_t t = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x) * TPT + gw;
                 if (t < p.n_tgt) {
                     if (lane < p.K) j = p.nbr[t * p.K + lane];
-                    pt = __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + t);
+                    pt = __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + (p.tgt_index ? p.tgt_index[t] : t));
                 }
             }
             m = __ballot_sync(FULL, j >= 0);
@@ -555,7 +556,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
                        int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out, const float *w1,
                        const float *b1, const float *w2, const float *b2, const float *bn_scale,
                        const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
-                       bool packed) {
+                       bool packed, const int64_t *tgt_index) {
     (void)n_src;
     P2W_REQUIRE(c_in % 8 == 0 && c_in >= 8 && c_in <= 256,
                 "p2w_pointnet_conv_max(bf16): c_in=%d must be a multiple of 8 in [8, 256]", c_in);
@@ -618,6 +619,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
         p.debug = dbg;
     }
 #endif
+    p.tgt_index = tgt_index;
     p.x = x; p.pos_src = pos_src; p.pos_tgt = pos_tgt; p.nbr = nbr;
     p.n_tgt = n_tgt; p.K = k; p.C = c_in; p.H = hidden; p.Co = c_out;
     p.K1p = t.K1p; p.NB1 = t.NB1; p.NB2 = t.NB2;

@@ -80,10 +80,69 @@ __global__ void __launch_bounds__(256) affine_relu_kernel(const void *__restrict
     }
 }
 
+// out[r] = dot(x[r, :], w) + bias: the 1-channel head (conv2, src/model.py:243).  Warp per row, 16-byte loads,
+// weights in registers (c <= 1024): one pass over x at HBM speed instead of a GEMM with N = 1.
+template <bool BF16>
+__global__ void __launch_bounds__(256) rowdot_kernel(const void *__restrict__ xin, int64_t n, int c,
+                                                     const float *__restrict__ w, float bias, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int c8 = c >> 3;
+    float wr[4][8];                                   // this lane's channel groups: lane, lane + 32, ...
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int g = lane + 32 * u;
+#pragma unroll
+        for (int e = 0; e < 8; e++) wr[u][e] = g < c8 ? __ldg(w + g * 8 + e) : 0.f;
+    }
+    for (int64_t r = warp; r < n; r += nwarps) {
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int g = lane + 32 * u;
+            if (g < c8) {
+                float v[8];
+                if (BF16) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(xin) + r * c8 + g);
+                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float2 f = __bfloat1622float2(h[e]);
+                        v[2 * e] = f.x;
+                        v[2 * e + 1] = f.y;
+                    }
+                } else {
+                    *reinterpret_cast<float4 *>(v) = __ldg(reinterpret_cast<const float4 *>(xin) + 2 * (r * c8 + g));
+                    *reinterpret_cast<float4 *>(v + 4) = __ldg(reinterpret_cast<const float4 *>(xin) + 2 * (r * c8 + g) + 1);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc = fmaf(v[e], wr[u][e], acc);
+            }
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[r] = acc + bias;
+    }
+}
+
 }  // namespace
 }  // namespace p2w
 
 using namespace p2w;
+
+extern "C" int p2w_rowdot(const void *x, int32_t dtype, int64_t n, int32_t c, const float *w, float bias, float *out,
+                          p2w_stream_t stream) {
+    P2W_REQUIRE(c >= 8 && c % 8 == 0 && c <= 1024, "p2w_rowdot: c=%d must be a multiple of 8, at most 1024", c);
+    P2W_REQUIRE(dtype == P2W_F32 || dtype == P2W_BF16, "p2w_rowdot: unknown dtype %d", dtype);
+    P2W_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "p2w_rowdot: rows must be 16-byte aligned");
+    if (n == 0) return P2W_OK;
+    int64_t blocks = (n * 32 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == P2W_BF16) P2W_LAUNCH(rowdot_kernel<true>, (unsigned)blocks, 256, 0, st)(x, n, c, w, bias, out);
+    else P2W_LAUNCH(rowdot_kernel<false>, (unsigned)blocks, 256, 0, st)(x, n, c, w, bias, out);
+    return check_launch("p2w_rowdot");
+}
 
 extern "C" int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, const float *s1, const float *t1,
                                const float *s2, const float *t2, int32_t dtype, p2w_stream_t stream) {

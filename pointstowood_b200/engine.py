@@ -138,6 +138,8 @@ class InferenceEngine:
             self.fp.append(dict(k=mod.k, l1=l1, l2=l2))
             pend = _affine(nn_[1][2])
         self.head1 = _Lin(net.conv1.weight, net.conv1.bias, dt, True, pend[0], pend[1], *_affine(net.norm))
+        self.head2_w = net.conv2.weight.detach().reshape(-1).float().contiguous()       # one output channel: a row dot
+        self.head2_b = float(net.conv2.bias.detach().reshape(-1)[0]) if net.conv2.weight.size(0) == 1 else None
         self.head2 = _Lin(net.conv2.weight, net.conv2.bias, dt, False)
 
     # ------------------------------------------------------------------ forward
@@ -166,8 +168,12 @@ class InferenceEngine:
             else:
                 nbr = ops.knn_table(pos, pos[idx], lvl["k"], ptr, ptr_t)
             pos4, back = ops.sa_prepare(pos, refl, ptr, sf)
-            h = ops.pointnet_conv_max(x, pos4, pos4[idx], nbr, *lvl["w"], mode=self.conv_mode, ws=lvl["ws"],
-                                      packed=lvl["packed"], out_dtype=dt)
+            if self.conv_mode == ops.CONV_BF16_TC:          # targets addressed through idx: no pos4[idx] gather
+                h = ops.pointnet_conv_max(x, pos4, pos4, nbr, *lvl["w"], mode=self.conv_mode, ws=lvl["ws"],
+                                          packed=lvl["packed"], out_dtype=dt, tgt_index=idx)
+            else:
+                h = ops.pointnet_conv_max(x, pos4, pos4[idx], nbr, *lvl["w"], mode=self.conv_mode, ws=lvl["ws"],
+                                          packed=lvl["packed"], out_dtype=dt)
             lvl["packed"] = lvl["packed"] or idx.numel() > 0          # an empty call returns before packing
             x = lvl["residual"](h)
             pos, batch, refl, ptr = back[idx], batch_t, refl[idx], ptr_t
@@ -187,5 +193,7 @@ class InferenceEngine:
             buf = ops.knn_interpolate_cat(x, pos_c, pos_skip, x_skip, fp["k"], ptr_c, ptr_skip, out_dtype=dt)
             x = fp["l2"](fp["l1"](buf))
             pos_c, ptr_c = pos_skip, ptr_skip
-        x = self.head2(self.head1(x))
-        return x.reshape(-1).float()
+        x = self.head1(x)
+        if self.head2_b is not None and x.size(1) % 8 == 0 and x.size(1) <= 1024:
+            return ops.rowdot(x, self.head2_w, self.head2_b)
+        return self.head2(x).reshape(-1).float()

@@ -27,7 +27,7 @@ __all__ = [
     "batch_to_ptr", "knn", "radius", "fps", "grid_cluster", "voxel_grid", "consecutive_cluster",
     "knn_interpolate", "knn_interpolate_cat", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
     "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback", "spatial_vote",
-    "sort_pairs", "affine_relu_", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
+    "sort_pairs", "affine_relu_", "rowdot", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
 ]
 
 CONV_FP32 = 0
@@ -483,10 +483,12 @@ _DT = {torch.float32: 0, torch.bfloat16: 1}       # P2W_F32 / P2W_BF16
 
 def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, w1: Tensor, b1: Tensor, w2: Tensor,
                       b2: Tensor, bn_scale: Tensor, bn_shift: Tensor, mode: int = CONV_FP32,
-                      ws: Optional[Tensor] = None, packed: bool = False, out_dtype=torch.float32) -> Tensor:
+                      ws: Optional[Tensor] = None, packed: bool = False, out_dtype=torch.float32,
+                      tgt_index: Optional[Tensor] = None) -> Tensor:
     """Fused PointNetConv.message + local_nn + max aggregation (src/pointnet.py:108-132).
     `ws` (from pointnet_conv_ws) with packed=True re-uses the weights laid out by an earlier call.
-    In the tensor-core mode x may be bf16 and `out_dtype` may be torch.bfloat16."""
+    In the tensor-core mode x may be bf16, `out_dtype` may be torch.bfloat16, and `tgt_index` (int64
+    [n_tgt]) addresses the targets inside `pos_tgt` (pass the source positions: no pos[idx] gather)."""
     if x.dtype not in _DT or out_dtype not in _DT:
         raise _lib.P2WError("pointnet_conv_max: feature rows must be float32 or bfloat16")
     x = _req(x, x.dtype, "x", 2)
@@ -497,20 +499,36 @@ def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, 
     H, K1 = w1.shape
     Co = w2.size(0)
     C = x.size(1)
-    if K1 != C + 4 or w2.size(1) != H or nbr.size(0) != pos_tgt.size(0):
+    n_tgt = nbr.size(0)
+    if tgt_index is not None:
+        tgt_index = _req(tgt_index, torch.int64, "tgt_index", 1)
+        if tgt_index.numel() != n_tgt or mode != CONV_BF16_TC:
+            raise _lib.P2WError("pointnet_conv_max: tgt_index needs one entry per target and the tensor-core mode")
+    if K1 != C + 4 or w2.size(1) != H or (tgt_index is None and n_tgt != pos_tgt.size(0)):
         raise _lib.P2WError("pointnet_conv_max: inconsistent shapes")
     L = _lib.lib()
     if ws is None:
         if packed:
             raise _lib.P2WError("pointnet_conv_max: packed=True needs the workspace of the packing call")
         ws = pointnet_conv_ws(C, H, Co, mode, x.device)
-    out = torch.empty((pos_tgt.size(0), Co), device=x.device, dtype=out_dtype)
+    out = torch.empty((n_tgt, Co), device=x.device, dtype=out_dtype)
     args = [_req(t, torch.float32, "weights") for t in (w1, b1, w2, b2, bn_scale, bn_shift)]
-    flops = float(pos_tgt.size(0)) * 32.0 * (2.0 * (C + 4) * H + 2.0 * H * Co)
+    flops = float(n_tgt) * 32.0 * (2.0 * (C + 4) * H + 2.0 * H * Co)                       # SURVEY.md §8(d)
     _lib.check(KERNEL_TIMER.call("p2w_pointnet_conv_max", flops, L.p2w_pointnet_conv_max_ex, _dp(x), _DT[x.dtype],
-                                 _dp(pos_src), _dp(pos_tgt), _dp(nbr), x.size(0), pos_tgt.size(0), nbr.size(1), C, H, Co,
+                                 _dp(pos_src), _dp(pos_tgt), _dp(nbr), x.size(0), n_tgt, nbr.size(1), C, H, Co,
                                  *[_dp(a) for a in args], _dp(out), _DT[out_dtype], mode, _dp(ws), ws.numel(),
-                                 1 if packed else 0, _stream()))
+                                 1 if packed else 0, _dp(tgt_index), _stream()))
+    return out
+
+
+def rowdot(x: Tensor, w: Tensor, bias: float) -> Tensor:
+    """[N] float32 = x @ w + bias for [N, C] float32 / bfloat16 rows: the 1-channel head (conv2, src/model.py:243)."""
+    if x.dtype not in _DT:
+        raise _lib.P2WError("rowdot: rows must be float32 or bfloat16")
+    x = _req(x, x.dtype, "x", 2)
+    w = _req(w, torch.float32, "w", 1)
+    out = torch.empty(x.size(0), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().p2w_rowdot(_dp(x), _DT[x.dtype], x.size(0), x.size(1), _dp(w), float(bias), _dp(out), _stream()))
     return out
 
 

@@ -72,6 +72,12 @@ def test_fused_conv_bf16_many_tiles_and_missing_edges(p2w):
     err = (out - ref).abs()
     assert err.max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
     assert err.mean().item() <= 4e-3 * max(1.0, ref.abs().mean().item())
+    # targets addressed inside the source positions (tgt_index) instead of a gathered pos[idx]: same bits
+    via_index = ops.pointnet_conv_max(args[0], args[1], args[1], *args[3:], mode=ops.CONV_BF16_TC,
+                                      tgt_index=idx.cuda())
+    assert torch.equal(via_index, out)
+    with pytest.raises(RuntimeError):
+        ops.pointnet_conv_max(args[0], args[1], args[1], *args[3:], mode=ops.CONV_FP32, tgt_index=idx.cuda())
 
 
 def test_net_forward_bf16_conv_within_1e2(p2w, golden_dir):

@@ -133,6 +133,23 @@ def test_affine_relu_matches_torch(p2w):
         assert (got2.float() - want2).abs().max().item() <= tol * (1 + want2.abs().max().item())
 
 
+def test_rowdot_matches_torch(p2w):
+    """The 1-channel head (conv2, src/model.py:243) as a streaming row dot."""
+    _, ops = p2w
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for c in (8, 128, 200, 1024):
+        w = torch.randn(c, device="cuda", generator=g)
+        for dtype, n in ((torch.float32, 4099), (torch.bfloat16, 70001), (torch.float32, 0)):
+            x = torch.randn(n, c, device="cuda", generator=g).to(dtype)
+            got = ops.rowdot(x, w, 0.25)
+            want = (x.double() @ w.double() + 0.25).float()
+            assert got.shape == (n,) and got.dtype == torch.float32
+            if n:
+                assert (got - want).abs().max().item() <= 1e-5 * c ** 0.5 * (1 + want.abs().max().item())
+    with pytest.raises(RuntimeError):
+        ops.rowdot(torch.zeros(4, 12, device="cuda"), torch.zeros(12, device="cuda"), 0.0)
+
+
 def test_conv_tc_bf16_rows_in_and_out(p2w, golden_dir):
     """The tensor-core PointNetConv with bf16 feature rows in / out agrees with its fp32-row form."""
     _, ops = p2w
