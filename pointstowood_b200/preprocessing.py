@@ -64,15 +64,24 @@ class Voxelise:
         self.cloud: Optional[Tensor] = None
         self.n_z: Optional[Tensor] = None
         self.refl: Optional[Tensor] = None
+        self._stats = None
 
     # ---- src/preprocessing.py:37-53
+    def _cloud_stats(self):
+        """Column min / max of (x, y, z, reflectance): ONE host round trip serves the ground grid and the
+        `reflectance != 0` test of :94 (any non-zero <=> min or max non-zero)."""
+        if self._stats is None:
+            mn, mx = ops._colminmax(self.cloud[:, :4])
+            self._stats = (mn, torch.stack([mn, mx]).cpu().numpy())
+        return self._stats
+
     def gpu_ground(self) -> Tensor:
         cloud = self.cloud
         n = cloud.size(0)
         L = _lib.lib()
-        mn, mx = ops._colminmax(cloud[:, :2])
-        lo = mn.cpu().numpy()
-        hi = (mx + 5.0).cpu().numpy()          # x_max + grid_resolution, rounded in fp32 like the tensor op
+        mn, ext = self._cloud_stats()
+        lo = ext[0, :2]
+        hi = ext[1, :2] + np.float32(5.0)      # x_max + grid_resolution, rounded in fp32 like the tensor op
         nb = [max(1, int(math.ceil((float(hi[d]) - float(lo[d])) / 5.0))) for d in range(2)]
         cell_min = torch.empty((nb[0] + 1) * (nb[1] + 1), device=cloud.device, dtype=torch.float32)
         n_z = torch.empty(n, device=cloud.device, dtype=torch.float32)
@@ -99,9 +108,11 @@ class Voxelise:
     # ---- src/preprocessing.py:55-64: per grid size, the member lists of voxels with >= minpoints
     def grid(self, feat: Tensor):
         out = []
+        n = feat.size(0)
+        mn, mx = ops._colminmax(feat)
+        ext = torch.stack([mn, mx]).cpu().numpy()                       # one round trip for every grid size
+        L = _lib.lib()
         for size in self.gridsize:
-            mn, mx = ops._colminmax(feat)
-            ext = torch.stack([mn, mx]).cpu().numpy()
             cells = 1
             for d in range(feat.size(1)):
                 cells *= int(np.float32(ext[1, d] - ext[0, d]) / np.float32(size)) + 1
@@ -109,9 +120,19 @@ class Voxelise:
             sz = torch.full((feat.size(1),), float(size), device=feat.device, dtype=torch.float32)
             ids = ops.grid_cluster(feat, sz, mn, mx)
             keys, order = ops.sort_pairs(ids, bits)
-            _, _, cnt, starts = ops._unique_last(keys, order, False, want_perm=False, want_starts=True)
-            nvox = int(cnt.item())
-            seg = starts[: nvox + 1].cpu().numpy()
+            # voxel count and segment starts side by side: ONE device-to-host copy of [count | starts[:bound + 1]]
+            buf = torch.empty(n + 2, device=feat.device, dtype=torch.int64)
+            ws = torch.empty(max(int(L.p2w_unique_ws_bytes(n)), 8), device=feat.device, dtype=torch.uint8)
+            _lib.check(L.p2w_unique_last(keys.data_ptr(), order.data_ptr(), n, None, None, buf[1:].data_ptr(),
+                                         buf.data_ptr(), ws.data_ptr(), _stream()))
+            bound = min(int(cells), n)                                   # occupied voxels <= cells of the box
+            if bound <= (1 << 22):
+                host = buf[: bound + 2].cpu().numpy()
+                nvox = int(host[0])
+                seg = host[1: nvox + 2]
+            else:
+                nvox = int(buf[0].item())
+                seg = buf[1: nvox + 2].cpu().numpy()
             out.append((float(size), order, seg))
         return out
 
@@ -146,33 +167,46 @@ class Voxelise:
         self.cloud = cloud = cloud.contiguous()
         if cloud.dim() != 2 or cloud.size(1) < 4:
             raise _lib.P2WError("Voxelise: the cloud needs x, y, z, reflectance columns")
+        self._stats = None
         n_z = cloud[:, -1].contiguous() if has_nz else self.gpu_ground()
         self.n_z = n_z
-        reflectance_not_zero = bool((cloud[:, 3] != 0).any().item())
+        ext = self._cloud_stats()[1]
+        reflectance_not_zero = bool(ext[0, 3] != 0 or ext[1, 3] != 0)
         refl = self.quantile_normalize_reflectance() if reflectance_not_zero else None
         n = cloud.size(0)
-        feat = torch.empty((n, 5), device=cloud.device, dtype=torch.float32)
+        dev = cloud.device
+        feat = torch.empty((n, 5), device=dev, dtype=torch.float32)
         _lib.check(_lib.lib().p2w_assemble5(cloud.data_ptr(), cloud.stride(0), None if refl is None else refl.data_ptr(),
                                             n_z.data_ptr(), n, feat.data_ptr(), _stream()))
         pieces: List[Tensor] = []
-        sizes: List[int] = []
-        grids: List[float] = []
-        refl_min = float(feat[:, 3].min().item()) if reflectance_not_zero else 0.0
+        sizes: List[np.ndarray] = []
+        grids: List[np.ndarray] = []
         for size, order, seg in self.grid(feat):
             counts = np.diff(seg)
             keep = np.nonzero(counts >= self.minpoints)[0]
+            if not len(keep):
+                continue
             big = keep[counts[keep] > self.maxpoints]
             if len(big) and not reflectance_not_zero:
                 raise NotImplementedError("oversized tiles without reflectance (torch.randint path, :120)")
-            thinned = dict(zip(big.tolist(), self._thin(feat, order, seg, big, refl_min))) if len(big) else {}
-            for v in keep.tolist():
-                m = thinned[v] if v in thinned else order[seg[v]: seg[v + 1]]
-                pieces.append(m)
-                sizes.append(int(m.numel()))
-                grids.append(size)
-        members = torch.cat(pieces).to(torch.int64) if pieces else torch.empty(0, dtype=torch.int64, device=cloud.device)
-        ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-        return TileStore(feat=feat, members=members, ptr=ptr, grid_of_tile=np.asarray(grids, dtype=np.float32))
+            # all kept voxels of this grid in one gather: member m of tile t sits at order[seg[v_t] + m]
+            tile_sizes = np.minimum(counts[keep], self.maxpoints).astype(np.int64)
+            off = np.concatenate([[0], np.cumsum(tile_sizes)]).astype(np.int64)
+            plan = torch.from_numpy(np.stack([seg[keep].astype(np.int64) - off[:-1], tile_sizes])).to(dev, non_blocking=True)
+            src = torch.arange(int(off[-1]), device=dev) + torch.repeat_interleave(plan[0], plan[1], output_size=int(off[-1]))
+            members = order[src].to(torch.int64)
+            if len(big):                                                # thinned tiles overwrite their placeholder rows
+                refl_min = float(feat[:, 3].min().item())
+                where = {int(v): i for i, v in enumerate(keep.tolist())}
+                for v, picked in zip(big.tolist(), self._thin(feat, order, seg, big, refl_min)):
+                    members[off[where[v]]: off[where[v] + 1]] = picked.to(torch.int64)
+            pieces.append(members)
+            sizes.append(tile_sizes)
+            grids.append(np.full(len(keep), size, dtype=np.float32))
+        members = torch.cat(pieces) if pieces else torch.empty(0, dtype=torch.int64, device=dev)
+        ptr = np.concatenate([[0], np.cumsum(np.concatenate(sizes))]).astype(np.int64) if sizes else np.zeros(1, np.int64)
+        grids = np.concatenate(grids) if grids else np.zeros(0, np.float32)
+        return TileStore(feat=feat, members=members, ptr=ptr, grid_of_tile=grids)
 
 
 def preprocess(args) -> None:

@@ -20,6 +20,11 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
                  "l"(a), "l"(b), "r"(idesc), "r"(acc)
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -32,14 +37,19 @@ __device__ __forceinline__ bool try_wait(uint64_t *bar, uint32_t parity) {
 
 // mode: 0 none K-major (LBO 2048, SBO 128), 1 SW128 K-major, 2 SW64 K-major, 3 SW32 K-major,
 //       4 none with B MN-major (as libp2w's hid tile), 5 none K-major, padded LBO (2064, as the msg tile)
-__global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int nacc, int N, long long *out) {
+__global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int nacc, int N, int M, int same_a, long long *out,
+                                                   const unsigned char *gsrc, int tma_on) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
+    __shared__ uint64_t cbar[4];
+    __shared__ volatile int stop_flag;
     __shared__ uint32_t tmem_slot;
     unsigned char *A = smem, *B = smem + 65536;
     for (int i = threadIdx.x; i < 131072 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&cbar[i])));
+        stop_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -51,28 +61,52 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int nacc
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // warp-uniform issue loop, one elected lane per group of 4 MMAs (the pattern libp2w's conv_tc uses)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((mode == 4 ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
+                               ((uint32_t)(M >> 4) << 24);
         uint64_t ad, bd;
         uint32_t kstep_a, kstep_b;          // descriptor increment per K=16 step (in 16-byte units)
         const uint32_t a = smem_u32(A), b = smem_u32(B);
         if (mode == 1) { ad = make_desc(a, 16, 1024, 2); bd = make_desc(b, 16, 1024, 2); kstep_a = kstep_b = 2; }
-        else if (mode == 2) { ad = make_desc(a, 16, 512, 4); bd = make_desc(b, 16, 512, 4); kstep_a = kstep_b = 2; }
-        else if (mode == 3) { ad = make_desc(a, 16, 256, 6); bd = make_desc(b, 16, 256, 6); kstep_a = kstep_b = 2; }
         else if (mode == 4) { ad = make_desc(a, 2048, 128, 0); bd = make_desc(b, 128, 192 * 16, 0); kstep_a = 256; kstep_b = 16; }
         else if (mode == 5) { ad = make_desc(a, 2048, 128, 0); bd = make_desc(b, 2064, 128, 0); kstep_a = 256; kstep_b = 258; }
-        else { ad = make_desc(a, 2048, 128, 0); bd = make_desc(b, 2048, 128, 0); kstep_a = kstep_b = 256; }
+        else if (mode == 0) { ad = make_desc(a, 2048, 128, 0); bd = make_desc(b, 2048, 128, 0); kstep_a = kstep_b = 256; }
+        else { ad = make_desc(a, 2048, 128, 0); bd = make_desc(b, 4096, 128, 0); kstep_a = 256; kstep_b = 512; }
+        const uint32_t d0 = tmem, d1 = tmem + (nacc > 1 ? N : 0);
+        const uint64_t a1 = ad + (same_a ? 0 : kstep_a), a2 = ad + 2 * kstep_a, a3 = ad + (same_a ? 2 : 3) * kstep_a;
+        const uint64_t b1 = bd + kstep_b, b2 = bd + 2 * kstep_b, b3 = bd + 3 * kstep_b;
+        __syncwarp();
         const long long t0 = clock64();
-        for (int i = 0; i < n_mma; i++) {
-            const uint32_t k = i & 3;      // walk 4 K-steps of a 64-wide tile
-            umma(tmem + (i % nacc) * N, ad + k * kstep_a, bd + k * kstep_b, idesc, i >= nacc ? 1u : 0u);
+        for (int i = 0; i < n_mma; i += 4) {
+            if (elect_one()) {
+                umma(d0, ad, bd, idesc, i ? 1u : 0u);
+                umma(d1, a1, b1, idesc, (i || nacc == 1) ? 1u : 0u);
+                umma(d0, a2, b2, idesc, 1u);
+                umma(d1, a3, b3, idesc, 1u);
+            }
+            __syncwarp();
         }
-        commit(&bar);
+        if (elect_one()) commit(&bar);
         const long long t1 = clock64();
         while (!try_wait(&bar, 0)) {}
         const long long t2 = clock64();
-        if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        stop_flag = 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    } else if (threadIdx.x == 32 && tma_on) {
+        // concurrent writer: 8 KB bulk copies global -> shared, four in flight (the weight ring of conv_tc)
+        long long copies = 0;
+        uint32_t ph[4] = {0, 0, 0, 0};
+        unsigned char *dst = smem + 140 * 1024;
+        for (int i = 0; !stop_flag; i++) {
+            const int sl = i & 3;
+            if (i >= 4) { while (!try_wait(&cbar[sl], ph[sl])) {} ph[sl] ^= 1; }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&cbar[sl])), "r"(8192) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst + sl * 8192)),
+                         "l"(gsrc + (size_t)((i * 37 + blockIdx.x) & 63) * 8192), "r"(8192), "r"(smem_u32(&cbar[sl])) : "memory");
+            copies++;
+        }
+        if (blockIdx.x == 0) out[2] = copies;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -80,21 +114,24 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int nacc
 }
 
 int main() {
-    long long *d, h[2];
-    cudaMalloc(&d, 16);
-    cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 4096);
-    const char *names[] = {"none K-major", "SW128 K-major", "SW64 K-major", "SW32 K-major", "none, B MN-major", "none K-major padded LBO"};
+    long long *d, h[3];
+    unsigned char *g;
+    cudaMalloc(&d, 24);
+    cudaMalloc(&g, 64 * 8192);
+    cudaMemset(g, 0, 64 * 8192);
+    cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int N : {128, 256}) {
-        for (int nacc : {1, 2}) {
-            for (int mode = 0; mode < 6; mode++) {
-                for (int rep = 0; rep < 2; rep++) {
-                    rate_kernel<<<148, 128, 131072 + 2048>>>(mode, 2048, nacc, N, d);
-                    cudaError_t e = cudaDeviceSynchronize();
-                    if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
-                }
-                cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-                printf("N=%d acc=%d %-26s issue %.1f cyc/mma   complete %.1f cyc/mma\n", N, nacc, names[mode], h[0] / 2048.0, h[1] / 2048.0);
+        for (int tma_on = 0; tma_on < 2; tma_on++) {
+            for (int rep = 0; rep < 2; rep++) {
+                cudaMemset(d, 0, 24);
+                rate_kernel<<<148, 128, 200 * 1024>>>(6, 8192, N <= 128 ? 2 : 1, N, 128, 0, d, g, tma_on);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); return 1; }
             }
+            cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
+            printf("M=128 N=%d  %s  %.1f cyc/mma (floor %d), TMA into smem %.1f B/cyc (%.0f B per MMA)\n", N,
+                   tma_on ? "with concurrent 8 KB bulk copies" : "MMAs alone                     ", h[1] / 8192.0, N / 2,
+                   h[2] * 8192.0 / h[1], h[2] * 8192.0 / 8192.0);
         }
     }
     return 0;
