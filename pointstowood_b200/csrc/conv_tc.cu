@@ -38,9 +38,11 @@ namespace {
 
 constexpr int NT = 128;                        // edges per tile (MMA N)
 constexpr int TPT = NT / 32;                   // targets per tile
-constexpr int SLICE_K = 32;                    // k extent of one ring slice (two K=16 MMAs)
-constexpr int SLICE_BYTES = 128 * SLICE_K * 2; // 8 KB: [4 k-chunks][128 rows][8 bf16]
-constexpr int MAX_STAGES = 16;                  // weight-ring depth is chosen per layer shape (tc_stages)
+constexpr int PAD_K = 32;                      // K extents (C + 5, H) are padded / required to multiples of this
+constexpr int SLICE_K = 64;                    // k extent of one ring slice: four K=16 MMAs per wait / elect / commit
+constexpr int SLICE_BYTES = 128 * SLICE_K * 2; // 16 KB: [8 k-chunks][128 rows][8 bf16]; the last slice of a block
+constexpr int TAIL_BYTES = SLICE_BYTES / 2;    // may be a half one (K % 64 == 32: two MMAs, 8 KB copied)
+constexpr int MAX_STAGES = 14;                  // weight-ring depth is chosen per layer shape
 constexpr int EPI_THREADS = 128;                // warps 0-3 (one TMEM lane quarter each)
 constexpr int GATHER_WARPS = 4;                 // warps 4-7
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
@@ -93,11 +95,15 @@ __host__ __device__ constexpr uint32_t instr_desc(bool b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) |
            (static_cast<uint32_t>(NT >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// Descriptors travel as (low word, high word): only the 14-bit start-address field in the low word moves inside
+// the issue loop, so stepping a descriptor is ONE 32-bit uniform add instead of a 64-bit add on a register pair.
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                     uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -204,7 +210,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 
     const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
-    const int n1 = p.K1p / SLICE_K, n2 = p.H / SLICE_K;   // ring slices per accumulator block
+    const int n1 = (p.K1p + SLICE_K - 1) / SLICE_K, n2 = (p.H + SLICE_K - 1) / SLICE_K;   // ring slices per accumulator block
+    const bool tail1 = (p.K1p % SLICE_K) != 0, tail2 = (p.H % SLICE_K) != 0;               // last slice is a half one
 
     if (warp == 9) {
         // ------------------------------------------------ weight producer
@@ -212,18 +219,24 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         // in uniform registers, so the loop body is a wait, an expect_tx and a bulk copy.
         int slot = 0;
         uint32_t ph = 0;
-        const int per_tile = p.NB1 * n1 + p.NB2 * n2;
         const int passes = P2W_DBG(p, 1) ? 0 : (p.resident ? (my_tiles > 0 ? 1 : 0) : my_tiles);
         for (int it = 0; it < passes; it++) {
             const unsigned char *src = p.wpack;
-            for (int s = 0; s < per_tile; s++) {
-                mbar_wait(&ring_empty[slot], ph ^ 1);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&ring_full[slot], SLICE_BYTES);
-                    bulk_g2s(ring + slot * SLICE_BYTES, src, SLICE_BYTES, &ring_full[slot]);
+#pragma unroll 1
+            for (int layer = 0; layer < 2; layer++) {
+                const int ns = layer == 0 ? n1 : n2, total = (layer == 0 ? p.NB1 : p.NB2) * ns;
+                const uint32_t last_bytes = (layer == 0 ? tail1 : tail2) ? TAIL_BYTES : SLICE_BYTES;
+                for (int i = 0, s = 0; i < total; i++) {
+                    const uint32_t bytes = s == ns - 1 ? last_bytes : static_cast<uint32_t>(SLICE_BYTES);
+                    mbar_wait(&ring_empty[slot], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&ring_full[slot], bytes);
+                        bulk_g2s(ring + slot * SLICE_BYTES, src, bytes, &ring_full[slot]);
+                    }
+                    src += bytes;
+                    if (++s == ns) s = 0;
+                    if (++slot == STAGES) { slot = 0; ph ^= 1; }
                 }
-                src += SLICE_BYTES;
-                if (++slot == STAGES) { slot = 0; ph ^= 1; }
             }
         }
         __syncwarp();
@@ -233,9 +246,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         // dependent instruction, so the per-slice body must stay a few instructions long).
         int slot = 0, acc = 0, mbuf = 0;
         uint32_t ph = 0, tph = 0, mph = 0, use0 = 0, use1 = 0;
-        const uint64_t a_desc0 = smem_desc(smem_u32(ring), 2048, 128);            // + slot * 512 (+ 256 for kk = 1)
-        const uint64_t b1_desc0 = smem_desc(smem_u32(b1), LBO1, 128);             // + s * 4 LBO1/16 (+ 2 LBO1/16)
-        const uint64_t b2_desc0 = smem_desc(smem_u32(b2), 128, p.H * 16);         // + s * 32 (+ 16)
+        const uint64_t a_desc0 = smem_desc(smem_u32(ring), 2048, 128);            // + slot * 1024 (+ 256 per K = 16 step)
+        const uint64_t b1_desc0 = smem_desc(smem_u32(b1), LBO1, 128);             // + 2 LBO1/16 per K = 16 step
+        const uint64_t b2_desc0 = smem_desc(smem_u32(b2), 128, p.H * 16);         // + 16 per K = 16 step
         constexpr uint32_t ID1 = instr_desc(false), ID2 = instr_desc(true);
         const bool stream = !(p.resident || P2W_DBG(p, 1));
         const bool rec = P2W_DBG(p, 16) && blockIdx.x == 0;
@@ -254,7 +267,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 P2W_TS(3 + layer);
                 const int nb = layer == 0 ? p.NB1 : p.NB2, ns = layer == 0 ? n1 : n2;
                 const uint64_t b_desc0 = layer == 0 ? b1_desc0 + static_cast<uint32_t>(mbuf) * (msg_bytes >> 4) : b2_desc0;
-                const uint32_t b_step = layer == 0 ? 4u * (LBO1 >> 4) : 32u, b_half = b_step >> 1;
+                const uint32_t b_hi = static_cast<uint32_t>(b_desc0 >> 32), a_hi = static_cast<uint32_t>(a_desc0 >> 32);
+                const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0);
+                const uint32_t bq = layer == 0 ? 2u * (LBO1 >> 4) : 16u;      // B descriptor step per K = 16
+                const bool tail = layer == 0 ? tail1 : tail2;
                 const uint32_t idesc = layer == 0 ? ID1 : ID2;
                 for (int blk = 0; blk < nb; blk++) {
                     P2W_TS(5);
@@ -262,18 +278,23 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                     tc_fence_after();
                     P2W_TS(6);
                     const uint32_t d_addr = tmem_base + acc * NT;
-                    uint64_t bd = b_desc0;
+                    uint32_t bd = static_cast<uint32_t>(b_desc0);
                     for (int s = 0; s < ns; s++) {
                         if (stream || (it == 0 && !P2W_DBG(p, 1))) mbar_wait(&ring_full[slot], ph);
-                        const uint64_t ad = a_desc0 + static_cast<uint32_t>(slot) * (SLICE_BYTES >> 4);
+                        const uint32_t ad = a_lo0 + static_cast<uint32_t>(slot) * (SLICE_BYTES >> 4);
+                        const bool half = tail && s == ns - 1;
                         if (elect_one()) {
                             if (!P2W_DBG(p, 8)) {
-                                umma(d_addr, ad, bd, idesc, s ? 1u : 0u);
-                                umma(d_addr, ad + 256u, bd + b_half, idesc, 1u);
+                                umma(d_addr, ad, a_hi, bd, b_hi, idesc, s ? 1u : 0u);
+                                umma(d_addr, ad + 256u, a_hi, bd + bq, b_hi, idesc, 1u);
+                                if (!half) {
+                                    umma(d_addr, ad + 512u, a_hi, bd + 2u * bq, b_hi, idesc, 1u);
+                                    umma(d_addr, ad + 768u, a_hi, bd + 3u * bq, b_hi, idesc, 1u);
+                                }
                             }
                             if (stream) umma_commit(&ring_empty[slot]);
                         }
-                        bd += b_step;
+                        bd += 4u * bq;
                         if (++slot == STAGES) { slot = 0; ph ^= 1; }
                     }
                     P2W_TS(7);
@@ -526,7 +547,7 @@ struct TcPlan {
 };
 inline TcPlan tc_plan(int c_in, int hidden, int c_out) {
     TcPlan t;
-    t.K1p = round_up(c_in + 5, SLICE_K);       // + the constant-one column that carries b1
+    t.K1p = round_up(c_in + 5, PAD_K);         // + the constant-one column that carries b1
     t.NB1 = (hidden + 127) / 128;
     t.NB2 = (c_out + 127) / 128;
     t.w1_bytes = static_cast<size_t>(t.NB1) * t.K1p * 128 * 2;
@@ -560,7 +581,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     (void)n_src;
     P2W_REQUIRE(c_in % 8 == 0 && c_in >= 8 && c_in <= 256,
                 "p2w_pointnet_conv_max(bf16): c_in=%d must be a multiple of 8 in [8, 256]", c_in);
-    P2W_REQUIRE(hidden % SLICE_K == 0, "p2w_pointnet_conv_max(bf16): hidden=%d must be a multiple of 32", hidden);
+    P2W_REQUIRE(hidden % PAD_K == 0, "p2w_pointnet_conv_max(bf16): hidden=%d must be a multiple of 32", hidden);
     P2W_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(pos_src) & 15u) == 0 &&
                     (reinterpret_cast<uintptr_t>(pos_tgt) & 15u) == 0 && (reinterpret_cast<uintptr_t>(ws) & 127u) == 0,
                 "p2w_pointnet_conv_max(bf16): x / pos / workspace must be 16-byte aligned");
@@ -569,7 +590,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     // Weight-ring depth.  The ring must keep (L2 latency x consumption rate) bytes in flight, so it takes
     // whatever shared memory the tiles leave: all of it when one CTA per SM is the only option, up to
     // the two-CTAs-per-SM budget otherwise.  A layer whose slices all fit (SA1) keeps them resident.
-    const int per_tile = t.NB1 * (t.K1p / SLICE_K) + t.NB2 * (hidden / SLICE_K);
+    const int per_tile = t.NB1 * ((t.K1p + SLICE_K - 1) / SLICE_K) + t.NB2 * ((hidden + SLICE_K - 1) / SLICE_K);
     const unsigned budget2 = 113u * 1024u, budget1 = 227u * 1024u;
     // msg buffers: the gather (three dependent global loads per tile) runs ahead of layer 1 when the tiles
     // leave room for a second / third msg tile next to a weight ring of useful depth.
@@ -577,11 +598,11 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     for (int mb = MAX_MSG_BUFS; mb >= 1; mb--) {
         const unsigned fixed = smem_layout(t.K1p, hidden, 0, mb).total;
         int st;
-        if (fixed + 4u * SLICE_BYTES <= budget2) st = static_cast<int>((budget2 - fixed) / SLICE_BYTES);
+        if (fixed + 2u * SLICE_BYTES <= budget2) st = static_cast<int>((budget2 - fixed) / SLICE_BYTES);
         else st = fixed + 2u * SLICE_BYTES <= budget1 ? static_cast<int>((budget1 - fixed) / SLICE_BYTES) : 0;
         if (st > MAX_STAGES) st = MAX_STAGES;
         const int res = per_tile <= st ? 1 : 0;
-        if (res || st >= 8 || mb == 1) {
+        if (res || st >= 4 || mb == 1) {
             msg_bufs = mb;
             stages = res ? per_tile : st;
             resident = res;
