@@ -72,6 +72,7 @@ struct ConvTcParams {
     int K, C, H, Co, K1p, NB1, NB2, num_tiles, x_bf16, out_bf16;
     int msg_bufs;                  // msg tiles in shared memory (the gather runs msg_bufs - 1 tiles ahead)
     int stages, resident;          // ring depth; resident: the ring holds ALL weight slices, loaded once
+    int dup;                       // rows of W1 packed twice (H <= 64): epilogue 1 splits the columns four ways
     int debug;                     // P2W_CONV_INSTRUMENT builds only
     const unsigned char *wpack;
     const float *b1p, *b2p, *scale, *shift;
@@ -322,38 +323,44 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         const int cpr_c = CPR < 32 ? CPR : 32;
         const int rpw = 32 / cpr_c;
         const int ck = lane % cpr_c, ri = lane / cpr_c;
-        // Software pipeline over tiles (this warp owns target gw of every tile): the neighbour row of tile
-        // it+2 and the source positions of tile it+1 are in flight while the features of tile it are fetched,
-        // so a tile costs one global-load latency instead of a chain of three.
+        // Software pipeline over tiles (this warp owns target gw of every tile): the neighbour row and the
+        // target index of tile it+2 and the positions of tile it+1 are in flight while the features of tile it
+        // are fetched; NOTHING is consumed in the step that loads it (a ballot on a freshly loaded row would
+        // expose a DRAM latency per tile), so a tile costs one global-load latency instead of a chain.
         static_assert(TPT == GATHER_WARPS, "one gather warp per target of a tile");
-        auto load_row = [&](int it, int &j, unsigned &m, float4 &pt) {
+        auto load_raw = [&](int it, int &j, int64_t &ti) {
             j = -1;
-            pt = make_float4(0.f, 0.f, 0.f, 0.f);
+            ti = -1;
             if (it < my_tiles) {
                 const int64_t t = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x) * TPT + gw;
                 if (t < p.n_tgt) {
                     if (lane < p.K) j = p.nbr[t * p.K + lane];
-                    pt = __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + (p.tgt_index ? p.tgt_index[t] : t));
+                    ti = p.tgt_index ? p.tgt_index[t] : t;
                 }
             }
+        };
+        auto resolve = [&](int &j, int64_t ti, unsigned &m, float4 &ps, float4 &pt) {
             m = __ballot_sync(FULL, j >= 0);
             const int jf = m ? __shfl_sync(FULL, j, __ffs(m) - 1) : 0;
             if (j < 0) j = jf;                     // padded slot: duplicate a valid edge (max unchanged)
+            ps = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j);
+            pt = ti >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + ti) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         int j0, j1, j2;
-        unsigned m0, m1, m2;
-        float4 pt0, pt1, pt2, ps0, ps1;
-        load_row(0, j0, m0, pt0);
-        load_row(1, j1, m1, pt1);
-        ps0 = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j0);
+        int64_t ti0, ti1, ti2;
+        unsigned m0, m1;
+        float4 pt0, pt1, ps0, ps1;
+        load_raw(0, j0, ti0);
+        load_raw(1, j1, ti1);
+        resolve(j0, ti0, m0, ps0, pt0);
         for (int it = 0; it < my_tiles; it++) {
             const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
             const int64_t t0 = static_cast<int64_t>(tile) * TPT;
             (void)t0;
             unsigned char *msg = b1 + mbuf * msg_bytes;
             int *sj = s_j + (it & 1) * NT;
-            ps1 = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j1);     // tile it+1
-            load_row(it + 2, j2, m2, pt2);                                      // tile it+2
+            load_raw(it + 2, j2, ti2);                                          // tile it+2: stays in flight
+            resolve(j1, ti1, m1, ps1, pt1);                                     // tile it+1: its row was loaded a step ago
             const int n = gw * 32 + lane;
             sj[n] = j0;
             if (lane == 0) s_valid[(it & (VALID_SLOTS - 1)) * TPT + gw] = m0 ? 1 : 0;
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 *reinterpret_cast<uint4 *>(msg + CPR * LBO1 + n * 16) = g;
             }
             j0 = j1; m0 = m1; pt0 = pt1; ps0 = ps1;
-            j1 = j2; m1 = m2; pt1 = pt2;
+            j1 = j2; ti1 = ti2;
             gather_bar();
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
             if (P2W_DBG(p, 2)) {
@@ -437,9 +444,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
                 if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // layer 2 of the previous tile is done with hid
-                const int h = blk * 128 + 32 * q + lane;
-#pragma unroll
-                for (int c = 0; c < (P2W_DBG(p, 4) ? 0 : NT / 32); c++) {
+                // H <= 64: the rows of W1 were packed twice, lanes 64-127 repeat lanes 0-63, and the four warps
+                // convert a quarter of the tile each; otherwise a warp whose channels are all padding skips the block
+                const int h = p.dup ? ((32 * q + lane) & 63) : blk * 128 + 32 * q + lane;
+                const int c_lo = p.dup ? (q >> 1) * 2 : 0;
+                const int c_hi = P2W_DBG(p, 4) ? 0 : (p.dup ? c_lo + 2 : (blk * 128 + 32 * q < p.H ? NT / 32 : 0));
+                for (int c = c_lo; c < c_hi; c++) {
                     const int n0 = c * 32;
                     uint32_t r[32];
                     tmem_ld32(lane_taddr + acc * NT + n0, r);
@@ -513,9 +523,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
 
 // w [R, Kreal] fp32 row-major -> bf16 [NB][Kp/8][128][8] (zero padded): every ring slice contiguous
 // bias_col (may be NULL): an extra column Kreal holding bias[row] (b1 rides in the contraction);
-// neg_if (may be NULL): rows with neg_if[row] < 0 are stored negated (W2 rows of negative BN scale).
+// neg_if (may be NULL): rows with neg_if[row] < 0 are stored negated (W2 rows of negative BN scale);
+// dup64: packed row r holds source row r % 64 (W1 with H <= 64: TMEM lanes 64-127 repeat lanes 0-63).
 __global__ void prepack_kernel(const float *__restrict__ w, int R, int Kreal, int NB, int Kp,
-                               const float *__restrict__ bias_col, const float *__restrict__ neg_if,
+                               const float *__restrict__ bias_col, const float *__restrict__ neg_if, int dup64,
                                __nv_bfloat16 *__restrict__ out) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = static_cast<int64_t>(NB) * Kp * 128;
@@ -524,7 +535,7 @@ __global__ void prepack_kernel(const float *__restrict__ w, int R, int Kreal, in
     const int r = static_cast<int>((idx >> 3) & 127);
     const int kc = static_cast<int>((idx >> 10) % (Kp >> 3));
     const int blk = static_cast<int>((idx >> 10) / (Kp >> 3));
-    const int row = blk * 128 + r, k = kc * 8 + e;
+    const int row = dup64 ? ((blk * 128 + r) & 63) : blk * 128 + r, k = kc * 8 + e;
     float v = 0.f;
     if (row < R) {
         if (k < Kreal) v = w[static_cast<int64_t>(row) * Kreal + k];
@@ -620,10 +631,11 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     float *b2p = reinterpret_cast<float *>(base + t.off_b2);
     float *scp = reinterpret_cast<float *>(base + t.off_scale);
     float *shp = reinterpret_cast<float *>(base + t.off_shift);
+    const int dup = hidden <= 64 ? 1 : 0;
     if (!packed) {
         const int64_t n1 = static_cast<int64_t>(t.NB1) * t.K1p * 128, n2 = static_cast<int64_t>(t.NB2) * hidden * 128;
-        P2W_LAUNCH(prepack_kernel, (unsigned)((n1 + 255) / 256), 256, 0, st)(w1, hidden, c_in + 4, t.NB1, t.K1p, b1, nullptr, w1p);
-        P2W_LAUNCH(prepack_kernel, (unsigned)((n2 + 255) / 256), 256, 0, st)(w2, c_out, hidden, t.NB2, hidden, nullptr, bn_scale, w2p);
+        P2W_LAUNCH(prepack_kernel, (unsigned)((n1 + 255) / 256), 256, 0, st)(w1, hidden, c_in + 4, t.NB1, t.K1p, b1, nullptr, dup, w1p);
+        P2W_LAUNCH(prepack_kernel, (unsigned)((n2 + 255) / 256), 256, 0, st)(w2, c_out, hidden, t.NB2, hidden, nullptr, bn_scale, 0, w2p);
         P2W_LAUNCH(padvec_kernel, (t.NB1 * 128 + 255) / 256, 256, 0, st)(b1, hidden, t.NB1 * 128, b1p);
         P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(b2, c_out, t.NB2 * 128, b2p);
         P2W_LAUNCH(padvec_kernel, (t.NB2 * 128 + 255) / 256, 256, 0, st)(bn_scale, c_out, t.NB2 * 128, scp);
@@ -632,6 +644,7 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
     ConvTcParams p;
     p.x_bf16 = x_bf16; p.out_bf16 = out_bf16;
     p.stages = stages; p.resident = resident; p.msg_bufs = msg_bufs;
+    p.dup = dup;
     p.debug = 0;
 #ifdef P2W_CONV_INSTRUMENT
     {

@@ -169,7 +169,9 @@ class InferenceEngine:
                 nbr = ops.knn_table(pos, pos[idx], lvl["k"], ptr, ptr_t)
             pos4, back = ops.sa_prepare(pos, refl, ptr, sf)
             if self.conv_mode == ops.CONV_BF16_TC:          # targets addressed through idx: no pos4[idx] gather
-                h = ops.pointnet_conv_max(x, pos4, pos4, nbr, *lvl["w"], mode=self.conv_mode, ws=lvl["ws"],
+                # the kernel rounds the rows to bf16 as it gathers them (each ~14 times): round them once instead
+                xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+                h = ops.pointnet_conv_max(xb, pos4, pos4, nbr, *lvl["w"], mode=self.conv_mode, ws=lvl["ws"],
                                           packed=lvl["packed"], out_dtype=dt, tgt_index=idx)
             else:
                 h = ops.pointnet_conv_max(x, pos4, pos4[idx], nbr, *lvl["w"], mode=self.conv_mode, ws=lvl["ws"],
