@@ -74,16 +74,26 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int n_mma, int nacc
         else if (mode == 0) { ad = make_desc(a, 2048, 128, 0); bd = make_desc(b, 2048, 128, 0); kstep_a = kstep_b = 256; }
         else { ad = make_desc(a, 2048, 128, 0); bd = make_desc(b, 4096, 128, 0); kstep_a = 256; kstep_b = 512; }
         const uint32_t d0 = tmem, d1 = tmem + (nacc > 1 ? N : 0);
-        const uint64_t a1 = ad + (same_a ? 0 : kstep_a), a2 = ad + 2 * kstep_a, a3 = ad + (same_a ? 2 : 3) * kstep_a;
-        const uint64_t b1 = bd + kstep_b, b2 = bd + 2 * kstep_b, b3 = bd + 3 * kstep_b;
+        const uint64_t a2 = ad + 2 * kstep_a, a3 = ad + 3 * kstep_a;
+        const uint64_t b2 = bd + 2 * kstep_b, b3 = bd + 3 * kstep_b;
         __syncwarp();
         const long long t0 = clock64();
+        // same_a doubles as the overhead mode here: bit 0 = tcgen05.commit after every group of four MMAs (the ring
+        // slot release of conv_tc), bit 1 = a (satisfied) mbarrier try_wait before every group (the ring_full wait)
+        const int ovh = same_a;
+        uint32_t rdy_phase = 0;
+        if (ovh & 2) {          // cbar[1] completes one phase now; waiting on parity 0 is satisfied from then on
+            if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&cbar[1])) : "memory");
+            __syncwarp();
+        }
         for (int i = 0; i < n_mma; i += 4) {
+            if (ovh & 2) { while (!try_wait(&cbar[1], rdy_phase)) {} }
             if (elect_one()) {
                 umma(d0, ad, bd, idesc, i ? 1u : 0u);
-                umma(d1, a1, b1, idesc, (i || nacc == 1) ? 1u : 0u);
+                umma(d1, ad + kstep_a, bd + kstep_b, idesc, (i || nacc == 1) ? 1u : 0u);
                 umma(d0, a2, b2, idesc, 1u);
                 umma(d1, a3, b3, idesc, 1u);
+                if (ovh & 1) commit(&cbar[0]);
             }
             __syncwarp();
         }
@@ -120,18 +130,17 @@ int main() {
     cudaMalloc(&g, 64 * 8192);
     cudaMemset(g, 0, 64 * 8192);
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    for (int N : {128, 256}) {
-        for (int tma_on = 0; tma_on < 2; tma_on++) {
+    for (int N : {128}) {
+        for (int ovh = 0; ovh < 4; ovh++) {
             for (int rep = 0; rep < 2; rep++) {
                 cudaMemset(d, 0, 24);
-                rate_kernel<<<148, 128, 200 * 1024>>>(6, 8192, N <= 128 ? 2 : 1, N, 128, 0, d, g, tma_on);
+                rate_kernel<<<148, 128, 200 * 1024>>>(6, 8192, 2, N, 128, ovh, d, g, 0);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); return 1; }
             }
             cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
-            printf("M=128 N=%d  %s  %.1f cyc/mma (floor %d), TMA into smem %.1f B/cyc (%.0f B per MMA)\n", N,
-                   tma_on ? "with concurrent 8 KB bulk copies" : "MMAs alone                     ", h[1] / 8192.0, N / 2,
-                   h[2] * 8192.0 / h[1], h[2] * 8192.0 / 8192.0);
+            printf("M=128 N=%d  groups of 4 MMAs%s%s: %.1f cyc/mma (floor %d)\n", N, (ovh & 2) ? " + satisfied try_wait before" : "",
+                   (ovh & 1) ? " + tcgen05.commit after" : "", h[1] / 8192.0, N / 2);
         }
     }
     return 0;
