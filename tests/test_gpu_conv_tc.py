@@ -80,6 +80,35 @@ def test_fused_conv_bf16_many_tiles_and_missing_edges(p2w):
         ops.pointnet_conv_max(args[0], args[1], args[1], *args[3:], mode=ops.CONV_FP32, tgt_index=idx.cuda())
 
 
+@pytest.mark.parametrize("C,H,Co,K", [(8, 32, 64, 7), (32, 64, 128, 32), (64, 96, 200, 16), (256, 384, 512, 32)])
+def test_fused_conv_bf16_layer_shapes(p2w, C, H, Co, K):
+    """Padding paths of the tensor-core kernel: H <= 64 (rows of W1 packed twice), K % 64 == 32 (half tail
+    slice), C' not a multiple of 128, fewer than 32 neighbour slots, bf16 rows in -- against the FP32 kernel."""
+    _, ops = p2w
+    g = torch.Generator().manual_seed(C + H)
+    ns, nt = 3000, 1201
+    x = torch.randn(ns, C, generator=g)
+    ps = torch.cat([torch.rand(ns, 3, generator=g), torch.randn(ns, 1, generator=g)], 1)
+    idx = torch.randint(0, ns, (nt,), generator=g)
+    nbr = torch.randint(0, ns, (nt, K), generator=g, dtype=torch.int32)
+    cnt = torch.randint(0, K + 1, (nt,), generator=g)
+    nbr[torch.arange(K)[None, :] >= cnt[:, None]] = -1
+    w1 = torch.randn(H, C + 4, generator=g) * 0.1
+    w2 = torch.randn(Co, H, generator=g) * 0.1
+    b1, b2 = torch.randn(H, generator=g) * 0.1, torch.randn(Co, generator=g) * 0.1
+    sc = torch.where(torch.rand(Co, generator=g) < 0.3, -1.0, 1.0) * (torch.rand(Co, generator=g) + 0.5)
+    sh = torch.randn(Co, generator=g) * 0.1
+    args = [t.cuda() for t in (x, ps, ps[idx], nbr, w1, b1, w2, b2, sc, sh)]
+    ref = ops.pointnet_conv_max(*args, mode=ops.CONV_FP32)
+    out = ops.pointnet_conv_max(args[0].bfloat16(), *args[1:], mode=ops.CONV_BF16_TC)
+    torch.cuda.synchronize()
+    assert out.shape == (nt, Co)
+    assert (out[cnt.cuda() == 0] == 0).all()
+    err = (out - ref).abs()
+    assert err.max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
+    assert err.mean().item() <= 4e-3 * max(1.0, ref.abs().mean().item())
+
+
 def test_net_forward_bf16_conv_within_1e2(p2w, golden_dir):
     model_mod, ops = p2w
     g = np.load(os.path.join(golden_dir, "net_b.npz"))
