@@ -216,6 +216,11 @@ int p2w_rowdot(const void *x, int32_t dtype, int64_t n, int32_t c, const float *
  * arg [dim_size,c] int64 (n for empty slots; lowest row on ties).  is_max: 1 max, 0 min. */
 int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_segments, int32_t c,
                     float *out, p2w_stream_t stream);
+/* The same over FP32 / BF16 rows (dtype = P2W_F32 | P2W_BF16, c even) with an optional per-channel affine
+ * applied to every element first: out[b,ch] = max_r (x[r,ch] * scale[ch] + shift[ch]) -- GlobalSAModule's
+ * last BatchNorm + global_max_pool (src/model.py:134-136) in one pass.  scale / shift may be NULL. */
+int p2w_segment_max_ex(const void *x, int32_t dtype, const int64_t *ptr, int32_t num_segments, int32_t c,
+                       const float *scale, const float *shift, float *out, p2w_stream_t stream);
 int p2w_scatter_minmax(const float *src, const int64_t *index, int64_t n, int32_t c,
                        int64_t dim_size, int32_t is_max, float *out, int64_t *arg,
                        p2w_stream_t stream);

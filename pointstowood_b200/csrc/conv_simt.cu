@@ -261,6 +261,51 @@ __global__ void __launch_bounds__(128) segment_max_kernel(const float *__restric
     out[static_cast<int64_t>(b) * c + ch] = (r1 > r0) ? m : 0.f;
 }
 
+// rows in FP32 or BF16, optional per-channel affine applied to every element before the max (the eval-mode
+// BatchNorm that follows the last MLP of GlobalSAModule, src/model.py:134-136): one pass over the rows instead
+// of a cast, a multiply and an add over [n, c] in front of the pooling.  Two channels per thread, four rows in flight.
+template <bool BF16>
+__global__ void __launch_bounds__(128) segment_max_affine_kernel(const void *__restrict__ xin, const int64_t *__restrict__ ptr,
+                                                                 int c, const float *__restrict__ scale,
+                                                                 const float *__restrict__ shift, float *__restrict__ out) {
+    const int b = blockIdx.x;
+    const int ch = 2 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (ch >= c) return;
+    const int64_t r0 = ptr[b], r1 = ptr[b + 1];
+    const float s0 = scale ? scale[ch] : 1.f, s1 = scale ? scale[ch + 1] : 1.f;
+    const float t0 = shift ? shift[ch] : 0.f, t1 = shift ? shift[ch + 1] : 0.f;
+    float m0 = __int_as_float(0xff800000), m1 = m0;
+    auto load = [&](int64_t r, float &a, float &bb) {
+        if (BF16) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(
+                static_cast<const __nv_bfloat16 *>(xin) + r * c + ch));
+            a = f.x; bb = f.y;
+        } else {
+            const float2 f = *reinterpret_cast<const float2 *>(static_cast<const float *>(xin) + r * c + ch);
+            a = f.x; bb = f.y;
+        }
+    };
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+        float a[4], bb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) load(r + u, a[u], bb[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            m0 = fmaxf(m0, __fadd_rn(__fmul_rn(a[u], s0), t0));      // mul then add, as the tensor expression h * s + t
+            m1 = fmaxf(m1, __fadd_rn(__fmul_rn(bb[u], s1), t1));
+        }
+    }
+    for (; r < r1; r++) {
+        float a, bb;
+        load(r, a, bb);
+        m0 = fmaxf(m0, __fadd_rn(__fmul_rn(a, s0), t0));
+        m1 = fmaxf(m1, __fadd_rn(__fmul_rn(bb, s1), t1));
+    }
+    const bool any = r1 > r0;
+    *reinterpret_cast<float2 *>(out + static_cast<int64_t>(b) * c + ch) = make_float2(any ? m0 : 0.f, any ? m1 : 0.f);
+}
+
 // ------------------------------------------------------------------ scatter max / min with arg
 __device__ __forceinline__ void atomic_max_f(float *a, float v) {
     if (v >= 0.f) atomicMax(reinterpret_cast<int *>(a), __float_as_int(v));
@@ -457,6 +502,20 @@ extern "C" int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_s
     dim3 grid(num_segments, (c + 127) / 128);
     P2W_LAUNCH(segment_max_kernel, grid, 128, 0, as_stream(stream))(x, ptr, c, out);
     return check_launch("p2w_segment_max");
+}
+
+extern "C" int p2w_segment_max_ex(const void *x, int32_t dtype, const int64_t *ptr, int32_t num_segments, int32_t c,
+                                  const float *scale, const float *shift, float *out, p2w_stream_t stream) {
+    P2W_REQUIRE(num_segments >= 1 && c >= 2 && c % 2 == 0, "p2w_segment_max_ex: c=%d must be even, segments >= 1", c);
+    P2W_REQUIRE(dtype == P2W_F32 || dtype == P2W_BF16, "p2w_segment_max_ex: unknown dtype %d", dtype);
+    P2W_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
+                "p2w_segment_max_ex: rows must be 8-byte aligned");
+    dim3 grid(num_segments, (c / 2 + 127) / 128);
+    if (dtype == P2W_BF16)
+        P2W_LAUNCH(segment_max_affine_kernel<true>, grid, 128, 0, as_stream(stream))(x, ptr, c, scale, shift, out);
+    else
+        P2W_LAUNCH(segment_max_affine_kernel<false>, grid, 128, 0, as_stream(stream))(x, ptr, c, scale, shift, out);
+    return check_launch("p2w_segment_max_ex");
 }
 
 extern "C" int p2w_scatter_minmax(const float *src, const int64_t *index, int64_t n, int32_t c, int64_t dim_size,

@@ -185,9 +185,8 @@ class InferenceEngine:
         buf = torch.zeros((n3, x.size(1) + 3 + self.g_pad), device=x.device, dtype=dt)
         buf[:, : x.size(1)] = x
         buf[:, x.size(1): x.size(1) + 3] = pos
-        h = self.g2(self.g1(buf)).float()
-        h = h * self.g_s + self.g_t
-        x = ops.global_max_pool(h, batch, ptr=ptr)                     # [T,512] fp32
+        h = self.g2(self.g1(buf))
+        x = ops.global_max_pool(h, batch, ptr=ptr, scale=self.g_s, shift=self.g_t)   # BN + pooling in one pass: [T,512] fp32
         pos_c = pos.new_zeros((T, 3))
         ptr_c = torch.arange(T + 1, device=pos.device, dtype=torch.int64)
         # ---- FPModules (src/model.py:148-153), coarse -> fine

@@ -414,15 +414,27 @@ def scatter_min(src: Tensor, index: Tensor, dim: int = -1, out=None, dim_size: O
     return _scatter(src, index, dim, out, dim_size, False)
 
 
-def global_max_pool(x: Tensor, batch: Tensor, size: Optional[int] = None, ptr: Optional[Tensor] = None) -> Tensor:
-    """torch_geometric.nn.global_max_pool for a sorted batch vector."""
-    x = _req(x, torch.float32, "x", 2)
+def global_max_pool(x: Tensor, batch: Tensor, size: Optional[int] = None, ptr: Optional[Tensor] = None,
+                    scale: Optional[Tensor] = None, shift: Optional[Tensor] = None) -> Tensor:
+    """torch_geometric.nn.global_max_pool for a sorted batch vector.  float32 [B, C] out.
+    Extensions: bfloat16 rows, and an optional per-channel affine applied to every element before the max
+    (x * scale + shift: the eval-mode BatchNorm in front of the pooling, src/model.py:134-136) in the same pass."""
     if ptr is None:
         if size is None:
             size = int(batch.max()) + 1
         ptr = batch_to_ptr(batch, size)
     out = torch.empty((ptr.numel() - 1, x.size(1)), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().p2w_segment_max(_dp(x), _dp(ptr), ptr.numel() - 1, x.size(1), _dp(out), _stream()))
+    if x.dtype == torch.float32 and scale is None and shift is None:
+        x = _req(x, torch.float32, "x", 2)
+        _lib.check(_lib.lib().p2w_segment_max(_dp(x), _dp(ptr), ptr.numel() - 1, x.size(1), _dp(out), _stream()))
+        return out
+    if x.dtype not in _DT:
+        raise _lib.P2WError("global_max_pool: rows must be float32 or bfloat16")
+    x = _req(x, x.dtype, "x", 2)
+    scale = None if scale is None else _req(scale, torch.float32, "scale", 1)
+    shift = None if shift is None else _req(shift, torch.float32, "shift", 1)
+    _lib.check(_lib.lib().p2w_segment_max_ex(_dp(x), _DT[x.dtype], _dp(ptr), ptr.numel() - 1, x.size(1), _dp(scale),
+                                             _dp(shift), _dp(out), _stream()))
     return out
 
 

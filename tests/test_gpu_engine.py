@@ -133,6 +133,23 @@ def test_affine_relu_matches_torch(p2w):
         assert (got2.float() - want2).abs().max().item() <= tol * (1 + want2.abs().max().item())
 
 
+def test_global_max_pool_with_affine_and_bf16_rows(p2w):
+    """GlobalSAModule's BatchNorm + global_max_pool in one pass equals the tensor expression, bit for bit."""
+    _, ops = p2w
+    g = torch.Generator(device="cuda").manual_seed(4)
+    ptr = torch.tensor([0, 5, 5, 1300, 1301, 4000], device="cuda")             # an empty and a one-row segment
+    batch = torch.repeat_interleave(torch.arange(5, device="cuda"), ptr[1:] - ptr[:-1])
+    s, t = torch.randn(512, device="cuda", generator=g), torch.randn(512, device="cuda", generator=g)
+    for dtype in (torch.float32, torch.bfloat16):
+        x = torch.randn(4000, 512, device="cuda", generator=g).to(dtype)
+        want = ops.global_max_pool(x.float() * s + t, batch, ptr=ptr)
+        got = ops.global_max_pool(x, batch, ptr=ptr, scale=s, shift=t)
+        assert torch.equal(got, want)
+        assert torch.equal(ops.global_max_pool(x, batch, ptr=ptr, scale=None, shift=None),
+                           ops.global_max_pool(x.float(), batch, ptr=ptr))
+    assert (got[1] == 0).all()
+
+
 def test_rowdot_matches_torch(p2w):
     """The 1-channel head (conv2, src/model.py:243) as a streaming row dot."""
     _, ops = p2w
