@@ -208,6 +208,10 @@ int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, const float *s
 int p2w_rowdot(const void *x, int32_t dtype, int64_t n, int32_t c, const float *w, float bias, float *out,
                p2w_stream_t stream);
 
+/* out[i] = relu(a[i] + b[i]) over n FP32 / BF16 elements (n a multiple of 4 / 8; out may alias a): the shortcut
+ * add + ReLU that closes InvertedResidualBlock (src/model.py:84) in one pass. */
+int p2w_add_relu(const void *a, const void *b, void *out, int64_t n, int32_t dtype, p2w_stream_t stream);
+
 /* ---- segment / scatter reductions ---------------------------------------------------
  * p2w_segment_max: torch_geometric global_max_pool (src/model.py:136) for a sorted batch
  * given as ptr: out[b,:] = max over rows ptr[b]..ptr[b+1] (0 for empty segments).

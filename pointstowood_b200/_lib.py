@@ -49,6 +49,7 @@ SIGNATURES = {
                                           _P, c_int32, _P]),
     "p2w_affine_relu": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, _P]),
     "p2w_rowdot": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_float, _P, _P]),
+    "p2w_add_relu": (c_int32, [_P, _P, _P, c_int64, c_int32, _P]),
     "p2w_segment_max": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "p2w_segment_max_ex": (c_int32, [_P, c_int32, _P, c_int32, c_int32, _P, _P, _P, _P]),
     "p2w_scatter_minmax": (c_int32, [_P, _P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P]),

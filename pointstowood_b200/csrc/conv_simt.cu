@@ -263,17 +263,20 @@ __global__ void __launch_bounds__(128) segment_max_kernel(const float *__restric
 
 // rows in FP32 or BF16, optional per-channel affine applied to every element before the max (the eval-mode
 // BatchNorm that follows the last MLP of GlobalSAModule, src/model.py:134-136): one pass over the rows instead
-// of a cast, a multiply and an add over [n, c] in front of the pooling.  Two channels per thread, four rows in flight.
+// of a cast, a multiply and an add over [n, c] in front of the pooling.  A block owns 64 channels of one
+// segment: lanes = channel pairs, the four warps take every fourth row (four rows in flight each) and meet
+// in shared memory.
 template <bool BF16>
 __global__ void __launch_bounds__(128) segment_max_affine_kernel(const void *__restrict__ xin, const int64_t *__restrict__ ptr,
                                                                  int c, const float *__restrict__ scale,
                                                                  const float *__restrict__ shift, float *__restrict__ out) {
-    const int b = blockIdx.x;
-    const int ch = 2 * (blockIdx.y * blockDim.x + threadIdx.x);
-    if (ch >= c) return;
+    __shared__ float2 part[4][32];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ch = 2 * (blockIdx.y * 32 + lane);
+    const bool live = ch < c;
     const int64_t r0 = ptr[b], r1 = ptr[b + 1];
-    const float s0 = scale ? scale[ch] : 1.f, s1 = scale ? scale[ch + 1] : 1.f;
-    const float t0 = shift ? shift[ch] : 0.f, t1 = shift ? shift[ch + 1] : 0.f;
+    const float s0 = live && scale ? scale[ch] : 1.f, s1 = live && scale ? scale[ch + 1] : 1.f;
+    const float t0 = live && shift ? shift[ch] : 0.f, t1 = live && shift ? shift[ch + 1] : 0.f;
     float m0 = __int_as_float(0xff800000), m1 = m0;
     auto load = [&](int64_t r, float &a, float &bb) {
         if (BF16) {
@@ -285,25 +288,36 @@ __global__ void __launch_bounds__(128) segment_max_affine_kernel(const void *__r
             a = f.x; bb = f.y;
         }
     };
-    int64_t r = r0;
-    for (; r + 4 <= r1; r += 4) {
-        float a[4], bb[4];
+    if (live) {
+        int64_t r = r0 + w;
+        for (; r + 12 < r1; r += 16) {
+            float a[4], bb[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) load(r + u, a[u], bb[u]);
+            for (int u = 0; u < 4; u++) load(r + 4 * u, a[u], bb[u]);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            m0 = fmaxf(m0, __fadd_rn(__fmul_rn(a[u], s0), t0));      // mul then add, as the tensor expression h * s + t
-            m1 = fmaxf(m1, __fadd_rn(__fmul_rn(bb[u], s1), t1));
+            for (int u = 0; u < 4; u++) {
+                m0 = fmaxf(m0, __fadd_rn(__fmul_rn(a[u], s0), t0));      // mul then add, as the tensor expression h * s + t
+                m1 = fmaxf(m1, __fadd_rn(__fmul_rn(bb[u], s1), t1));
+            }
+        }
+        for (; r < r1; r += 4) {
+            float a, bb;
+            load(r, a, bb);
+            m0 = fmaxf(m0, __fadd_rn(__fmul_rn(a, s0), t0));
+            m1 = fmaxf(m1, __fadd_rn(__fmul_rn(bb, s1), t1));
         }
     }
-    for (; r < r1; r++) {
-        float a, bb;
-        load(r, a, bb);
-        m0 = fmaxf(m0, __fadd_rn(__fmul_rn(a, s0), t0));
-        m1 = fmaxf(m1, __fadd_rn(__fmul_rn(bb, s1), t1));
+    part[w][lane] = make_float2(m0, m1);
+    __syncthreads();
+    if (w == 0 && live) {
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+            m0 = fmaxf(m0, part[k][lane].x);
+            m1 = fmaxf(m1, part[k][lane].y);
+        }
+        const bool any = r1 > r0;
+        *reinterpret_cast<float2 *>(out + static_cast<int64_t>(b) * c + ch) = make_float2(any ? m0 : 0.f, any ? m1 : 0.f);
     }
-    const bool any = r1 > r0;
-    *reinterpret_cast<float2 *>(out + static_cast<int64_t>(b) * c + ch) = make_float2(any ? m0 : 0.f, any ? m1 : 0.f);
 }
 
 // ------------------------------------------------------------------ scatter max / min with arg
@@ -510,7 +524,7 @@ extern "C" int p2w_segment_max_ex(const void *x, int32_t dtype, const int64_t *p
     P2W_REQUIRE(dtype == P2W_F32 || dtype == P2W_BF16, "p2w_segment_max_ex: unknown dtype %d", dtype);
     P2W_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
                 "p2w_segment_max_ex: rows must be 8-byte aligned");
-    dim3 grid(num_segments, (c / 2 + 127) / 128);
+    dim3 grid(num_segments, (c / 2 + 31) / 32);
     if (dtype == P2W_BF16)
         P2W_LAUNCH(segment_max_affine_kernel<true>, grid, 128, 0, as_stream(stream))(x, ptr, c, scale, shift, out);
     else

@@ -125,6 +125,32 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const void *__restrict__ xi
     }
 }
 
+// out = relu(a + b) over n elements of FP32 / BF16 rows, 16 bytes per thread: the shortcut add + ReLU that closes
+// InvertedResidualBlock (src/model.py:84) in one pass instead of an add and a clamp.
+template <bool BF16>
+__global__ void __launch_bounds__(256) add_relu_kernel(const void *__restrict__ a, const void *__restrict__ b,
+                                                       void *__restrict__ out, int64_t nvec) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 va = __ldg(reinterpret_cast<const uint4 *>(a) + i), vb = __ldg(reinterpret_cast<const uint4 *>(b) + i);
+        uint4 vo;
+        if (BF16) {
+            const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&va);
+            const __nv_bfloat162 *pb = reinterpret_cast<const __nv_bfloat162 *>(&vb);
+            __nv_bfloat162 *po = reinterpret_cast<__nv_bfloat162 *>(&vo);
+            const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
+#pragma unroll
+            for (int e = 0; e < 4; e++) po[e] = __hmax2(__hadd2(pa[e], pb[e]), zero);   // one bf16 rounding, as torch's add_
+        } else {
+            const float *pa = reinterpret_cast<const float *>(&va), *pb = reinterpret_cast<const float *>(&vb);
+            float *po = reinterpret_cast<float *>(&vo);
+#pragma unroll
+            for (int e = 0; e < 4; e++) po[e] = fmaxf(pa[e] + pb[e], 0.f);
+        }
+        reinterpret_cast<uint4 *>(out)[i] = vo;
+    }
+}
+
 }  // namespace
 }  // namespace p2w
 
@@ -142,6 +168,22 @@ extern "C" int p2w_rowdot(const void *x, int32_t dtype, int64_t n, int32_t c, co
     if (dtype == P2W_BF16) P2W_LAUNCH(rowdot_kernel<true>, (unsigned)blocks, 256, 0, st)(x, n, c, w, bias, out);
     else P2W_LAUNCH(rowdot_kernel<false>, (unsigned)blocks, 256, 0, st)(x, n, c, w, bias, out);
     return check_launch("p2w_rowdot");
+}
+
+extern "C" int p2w_add_relu(const void *a, const void *b, void *out, int64_t n, int32_t dtype, p2w_stream_t stream) {
+    P2W_REQUIRE(dtype == P2W_F32 || dtype == P2W_BF16, "p2w_add_relu: unknown dtype %d", dtype);
+    const int per = dtype == P2W_BF16 ? 8 : 4;
+    P2W_REQUIRE(n >= 0 && n % per == 0, "p2w_add_relu: n=%lld must be a multiple of %d", (long long)n, per);
+    P2W_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                "p2w_add_relu: operands must be 16-byte aligned");
+    if (n == 0) return P2W_OK;
+    const int64_t nvec = n / per;
+    int64_t blocks = (nvec + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == P2W_BF16) P2W_LAUNCH(add_relu_kernel<true>, (unsigned)blocks, 256, 0, st)(a, b, out, nvec);
+    else P2W_LAUNCH(add_relu_kernel<false>, (unsigned)blocks, 256, 0, st)(a, b, out, nvec);
+    return check_launch("p2w_add_relu");
 }
 
 extern "C" int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, const float *s1, const float *t1,

@@ -27,7 +27,7 @@ __all__ = [
     "batch_to_ptr", "knn", "radius", "fps", "grid_cluster", "voxel_grid", "consecutive_cluster",
     "knn_interpolate", "knn_interpolate_cat", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
     "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback", "spatial_vote",
-    "sort_pairs", "affine_relu_", "rowdot", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
+    "sort_pairs", "affine_relu_", "add_relu_", "rowdot", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
 ]
 
 CONV_FP32 = 0
@@ -531,6 +531,18 @@ def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, 
                                  *[_dp(a) for a in args], _dp(out), _DT[out_dtype], mode, _dp(ws), ws.numel(),
                                  1 if packed else 0, _dp(tgt_index), _stream()))
     return out
+
+
+def add_relu_(a: Tensor, b: Tensor) -> Tensor:
+    """a <- relu(a + b) in place (float32 / bfloat16, same shape): InvertedResidualBlock's shortcut (src/model.py:84)."""
+    if a.dtype not in _DT or b.dtype != a.dtype or a.shape != b.shape:
+        raise _lib.P2WError("add_relu_: operands must be float32 or bfloat16 tensors of one shape and dtype")
+    if not a.is_contiguous():
+        raise _lib.P2WError("add_relu_: the in-place operand must be contiguous")
+    a = _req(a, a.dtype, "a")
+    b = _req(b, b.dtype, "b")
+    _lib.check(_lib.lib().p2w_add_relu(_dp(a), _dp(b), _dp(a), a.numel(), _DT[a.dtype], _stream()))
+    return a
 
 
 def rowdot(x: Tensor, w: Tensor, bias: float) -> Tensor:

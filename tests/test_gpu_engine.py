@@ -150,11 +150,24 @@ def test_global_max_pool_with_affine_and_bf16_rows(p2w):
     assert (got[1] == 0).all()
 
 
+def test_add_relu_matches_torch(p2w):
+    _, ops = p2w
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for dtype in (torch.float32, torch.bfloat16):
+        a = torch.randn(3001, 136, device="cuda", generator=g).to(dtype)
+        b = torch.randn(3001, 136, device="cuda", generator=g).to(dtype)
+        want = torch.relu(a.clone().add_(b))
+        got = ops.add_relu_(a, b)
+        assert got.data_ptr() == a.data_ptr() and torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        ops.add_relu_(torch.zeros(8, 8, device="cuda").t()[:, :4], torch.zeros(8, 4, device="cuda"))
+
+
 def test_rowdot_matches_torch(p2w):
     """The 1-channel head (conv2, src/model.py:243) as a streaming row dot."""
     _, ops = p2w
     g = torch.Generator(device="cuda").manual_seed(9)
-    for c in (8, 128, 200, 1024):
+    for c in (8, 32, 64, 128, 200, 512, 1024):
         w = torch.randn(c, device="cuda", generator=g)
         for dtype, n in ((torch.float32, 4099), (torch.bfloat16, 70001), (torch.float32, 0)):
             x = torch.randn(n, c, device="cuda", generator=g).to(dtype)
