@@ -73,3 +73,41 @@ def test_shard_batches_covers_everything_once():
     batches = plan_batches(53, 8)
     seen = sorted(i for r in range(4) for i in shard_batches(batches, ptr, 4, r))
     assert seen == list(range(len(batches)))
+
+
+def test_predict_cli_file_to_file(tmp_path):
+    """predict.py's flow on files (pointstowood/predict.py:58-180): PLY in, `<name>_ours.ply` out with n_z / label /
+    pwood appended, equal to the in-memory pipeline on the same cloud."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import pandas as pd
+    from pointstowood_b200 import io as pio
+    from pointstowood_b200 import model as M
+    from pointstowood_b200 import ops, predict
+    from pointstowood_b200.predicter import classify_tiles
+    from pointstowood_b200.preprocessing import Voxelise
+    from pointstowood_b200.synthetic import tls_plot
+    cloud, _ = tls_plot(60_000, 43, side=5.0)
+    src = tmp_path / "plot.ply"
+    pio.write_ply(str(src), pd.DataFrame(cloud, columns=["x", "y", "z", "scalar_Reflectance"]))
+    sd = ref_model.seeded_state_dict()
+    ckpt = tmp_path / "seeded.pth"
+    torch.save({"model_state_dict": {"module." + k: v for k, v in sd.items()}}, str(ckpt))   # DataParallel prefix, as shipped
+    outs = predict.main(["--point-cloud", str(src), "--model", str(ckpt), "--precision", "fp32", "--is-wood", "0.5"])
+    assert outs == [str(tmp_path / "plot_ours.ply")]
+    got = pio.read_ply(outs[0])
+    assert list(got.columns) == ["x", "y", "z", "reflectance", "n_z", "label", "pwood"] and len(got) == len(cloud)
+    assert np.array_equal(got[["x", "y", "z"]].to_numpy(dtype=np.float32), cloud[:, :3])
+    # the same cloud through the in-memory path
+    net = M.Net(num_classes=1)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval().set_precision("fp32")
+    dev = torch.from_numpy(cloud).cuda()
+    vox = Voxelise(dev, minpoints=128, maxpoints=16384, gridsize=(2.0, 4.0))
+    store = vox.write_voxels()
+    prob, pred, xyz, _ = classify_tiles(net, store, 8, 0.5, want_xyz=True)
+    label, pwood = ops.spatial_vote(xyz, prob, pred, dev[:, :3].contiguous(), 64, 1.0)
+    assert np.array_equal(got["n_z"].to_numpy(dtype=np.float32), vox.n_z.cpu().numpy())
+    assert (got["label"].to_numpy() == label.cpu().numpy()).mean() >= 0.999
+    assert np.abs(got["pwood"].to_numpy() - pwood.cpu().numpy()).max() <= 1e-3 or \
+        (np.abs(got["pwood"].to_numpy() - pwood.cpu().numpy()) <= 1e-3).mean() >= 0.995
