@@ -55,12 +55,21 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // Timing experiments (tools/conv_timeline.py, tools/prof_conv.py): compile with -DP2W_CONV_INSTRUMENT and set
 // the environment variable P2W_CONV_DEBUG to a bit mask -- 1 no weight streaming, 2 no feature gather, 4 empty
-// epilogues, 8 no MMAs, 16 clock64 timeline of the MMA warp of CTA 0.  The default build has none of it.
+// epilogues, 8 no MMAs, 16 clock64 timeline of every role of CTA 0.  The default build has none of it.
 #ifdef P2W_CONV_INSTRUMENT
-__device__ long long g_timeline[8192];
+__device__ long long g_timeline[16 * 512];       // one region per warp of CTA 0: the stores never stall on an atomic
+// event = clock64 << 16 | tile << 8 | role << 4 | tag, tiles 20..27 of CTA 0 (tools/conv_timeline.py decodes)
+#define P2W_TSR(p, it, role, tag)                                                                              \
+    do {                                                                                                       \
+        if (((p).debug & 16) && blockIdx.x == 0 && (it) >= 20 && (it) < 28 && (threadIdx.x & 31) == 0 &&        \
+            ts_n < 512)                                                                                        \
+            g_timeline[(threadIdx.x >> 5) * 512 + ts_n++] =                                                    \
+                (clock64() << 16) | ((long long)(it) << 8) | ((role) << 4) | (tag);                            \
+    } while (0)
 #define P2W_DBG(p, bit) ((p).debug & (bit))
 #else
 #define P2W_DBG(p, bit) 0
+#define P2W_TSR(p, it, role, tag) do { } while (0)
 #endif
 
 struct ConvTcParams {
@@ -179,6 +188,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L.tmem);
 
     const int warp = __shfl_sync(FULL, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+#ifdef P2W_CONV_INSTRUMENT
+    int ts_n = 0;
+#endif
     const int lane = threadIdx.x & 31;
     const int kchunks = p.K1p >> 3;
 
@@ -252,20 +264,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
         const uint64_t b2_desc0 = smem_desc(smem_u32(b2), 128, p.H * 16);         // + 16 per K = 16 step
         constexpr uint32_t ID1 = instr_desc(false), ID2 = instr_desc(true);
         const bool stream = !(p.resident || P2W_DBG(p, 1));
-        const bool rec = P2W_DBG(p, 16) && blockIdx.x == 0;
-        int nrec = 0;
-#ifdef P2W_CONV_INSTRUMENT
-#define P2W_TS(tag) do { if (rec && lane == 0 && nrec < 4090) { g_timeline[2 + nrec++] = (clock64() << 8) | (tag); } } while (0)
-#else
-#define P2W_TS(tag) do { } while (0)
-#endif
         for (int it = 0; it < my_tiles; it++) {
 #pragma unroll 1
             for (int layer = 0; layer < 2; layer++) {
-                P2W_TS(1 + layer);
+                P2W_TSR(p, it, 1 + layer, 0);
                 mbar_wait(layer == 0 ? &b1_full[mbuf] : b2_full, layer == 0 ? mph : tph);
                 tc_fence_after();
-                P2W_TS(3 + layer);
+                P2W_TSR(p, it, 1 + layer, 1);
                 const int nb = layer == 0 ? p.NB1 : p.NB2, ns = layer == 0 ? n1 : n2;
                 const uint64_t b_desc0 = layer == 0 ? b1_desc0 + static_cast<uint32_t>(mbuf) * (msg_bytes >> 4) : b2_desc0;
                 const uint32_t b_hi = static_cast<uint32_t>(b_desc0 >> 32), a_hi = static_cast<uint32_t>(a_desc0 >> 32);
@@ -274,10 +279,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 const bool tail = layer == 0 ? tail1 : tail2;
                 const uint32_t idesc = layer == 0 ? ID1 : ID2;
                 for (int blk = 0; blk < nb; blk++) {
-                    P2W_TS(5);
                     mbar_wait(&acc_empty[acc], ((acc ? use1 : use0) & 1) ^ 1);
                     tc_fence_after();
-                    P2W_TS(6);
+                    P2W_TSR(p, it, 1 + layer, 2);
                     const uint32_t d_addr = tmem_base + acc * NT;
                     uint32_t bd = static_cast<uint32_t>(b_desc0);
                     for (int s = 0; s < ns; s++) {
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                         bd += 4u * bq;
                         if (++slot == STAGES) { slot = 0; ph ^= 1; }
                     }
-                    P2W_TS(7);
+                    P2W_TSR(p, it, 1 + layer, 3);
                     if (elect_one()) umma_commit(&acc_full[acc]);
                     if (acc) use1++; else use0++;
                     acc ^= 1;
@@ -308,11 +312,6 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             tph ^= 1;
             if (++mbuf == MB) { mbuf = 0; mph ^= 1; }
         }
-#ifdef P2W_CONV_INSTRUMENT
-        if (rec && lane == 0) g_timeline[0] = nrec;
-#endif
-        (void)rec; (void)nrec;
-#undef P2W_TS
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------ gather warps: one tile ahead of the MMAs
@@ -364,7 +363,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             const int n = gw * 32 + lane;
             sj[n] = j0;
             if (lane == 0) s_valid[(it & (VALID_SLOTS - 1)) * TPT + gw] = m0 ? 1 : 0;
+            P2W_TSR(p, it, 3, 0);
             mbar_wait(&b1_empty[mbuf], mph ^ 1);   // layer 1 of the tile that last used this buffer is done
+            P2W_TSR(p, it, 3, 1);
             {
                 const float dx = ps0.x - pt0.x, dy = ps0.y - pt0.y, dz = ps0.z - pt0.z;
                 float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             j0 = j1; m0 = m1; pt0 = pt1; ps0 = ps1;
             j1 = j2; ti1 = ti2;
             gather_bar();
+            P2W_TSR(p, it, 3, 3);
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
             if (P2W_DBG(p, 2)) {
             } else if (p.x_bf16) {
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             }
             fence_proxy_async();
             mbar_arrive(&b1_full[mbuf]);
+            P2W_TSR(p, it, 3, 2);
             if (++mbuf == MB) { mbuf = 0; mph ^= 1; }
         }
     } else {
@@ -441,9 +444,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             const int64_t t0 = static_cast<int64_t>(tile) * TPT;
             // ---- epilogue 1: hid[e, h] = relu(D1^T[h, e] + b1[h]) as the MN-major B operand of layer 2
             for (int blk = 0; blk < p.NB1; blk++) {
+                P2W_TSR(p, it, 5, 0);
                 mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
+                P2W_TSR(p, it, 5, 1);
                 if (blk == 0) mbar_wait(b2_empty, tph ^ 1);   // layer 2 of the previous tile is done with hid
+                P2W_TSR(p, it, 5, 2);
                 // H <= 64: the rows of W1 were packed twice, lanes 64-127 repeat lanes 0-63, and the four warps
                 // convert a quarter of the tile each; otherwise a warp whose channels are all padding skips the block
                 const int h = p.dup ? ((32 * q + lane) & 63) : blk * 128 + 32 * q + lane;
@@ -473,12 +479,15 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             }
             fence_proxy_async();
             mbar_arrive(b2_full);
+            P2W_TSR(p, it, 5, 3);
 
             // ---- epilogue 2: out[t, c] = max_e BN(relu(D2^T[c, e] + b2[c]))
             const int *valid = s_valid + (it & (VALID_SLOTS - 1)) * TPT;
             for (int blk = 0; blk < p.NB2; blk++) {
+                P2W_TSR(p, it, 6, 0);
                 mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
+                P2W_TSR(p, it, 6, 1);
                 const int co = blk * 128 + 32 * q + lane;
                 const float bias = p.b2p[co], sc = p.scale[co], sh = p.shift[co];
                 const float sgn = sc < 0.f ? -1.f : 1.f;      // rows with a negative BN scale were packed negated
@@ -506,6 +515,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[acc]);
+                P2W_TSR(p, it, 6, 2);
                 if (acc) use1++; else use0++;
                 acc ^= 1;
             }
@@ -578,7 +588,15 @@ using namespace p2w;
 
 #ifdef P2W_CONV_INSTRUMENT
 extern "C" int p2wdbg_conv_timeline(long long *dst_host, int n) {
-    return (int)cudaMemcpyFromSymbol(dst_host, g_timeline, sizeof(long long) * n);
+    static long long host[16 * 512];
+    cudaMemcpyFromSymbol(host, g_timeline, sizeof(host));
+    int cnt = 0;
+    for (int i = 0; i < 16 * 512 && cnt < n; i++)
+        if (host[i]) dst_host[cnt++] = host[i];
+    void *sym = nullptr;
+    cudaGetSymbolAddress(&sym, g_timeline);
+    cudaMemset(sym, 0, sizeof(host));
+    return cnt;
 }
 #endif
 

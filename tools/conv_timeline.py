@@ -1,4 +1,4 @@
-"""Timing experiment: clock64 timeline of every role of conv_tc's CTA 0 over its tiles 20..23.  Needs an
+"""Timing experiment: clock64 timeline of every role of conv_tc's CTA 0 over its tiles 20..27.  Needs an
 instrumented build (P2W_CONV_INSTRUMENT=1 python -m pointstowood_b200.build --force) and P2W_CONV_DEBUG=16.
 Usage: python tools/conv_timeline.py [sa1|sa2|sa3]"""
 import ctypes
@@ -33,9 +33,9 @@ for _ in range(3):
     n = fn(buf.ctypes.data_as(ctypes.c_void_p), 8192)
 ev = np.sort(buf[:n])
 clk, it, role, tag = ev >> 16, (ev >> 8) & 255, (ev >> 4) & 15, ev & 15
-roles = {1: "mma L1", 2: "mma L2", 3: "gather0", 4: "gather1", 5: "epi1", 6: "epi2"}
+roles = {1: "mma L1", 2: "mma L2", 3: "gather", 5: "epi1", 6: "epi2"}
 tags = {1: {0: "wait msg_full", 1: "go", 2: "acc free", 3: "issued+commit"}, 2: {0: "wait hid_full", 1: "go", 2: "acc free", 3: "issued+commit"},
-        3: {0: "wait msg_empty", 1: "go", 2: "arrived msg_full"}, 4: {0: "wait msg_empty", 1: "go", 2: "arrived msg_full"},
+        3: {0: "wait msg_empty", 1: "go", 2: "arrived msg_full", 3: "rows ready"},
         5: {0: "wait acc1_full", 1: "go", 2: "hid free", 3: "arrived hid_full"}, 6: {0: "wait acc2_full", 1: "go", 2: "arrived acc2_empty"}}
 t0 = clk[0]
 for i in range(n):
