@@ -345,12 +345,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             ps = __ldg(reinterpret_cast<const float4 *>(p.pos_src) + j);
             pt = ti >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.pos_tgt) + ti) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        int j0, j1, j2;
-        int64_t ti0, ti1, ti2;
+        int j0, j1, j2, j3;
+        int64_t ti0, ti1, ti2, ti3;
         unsigned m0, m1;
         float4 pt0, pt1, ps0, ps1;
         load_raw(0, j0, ti0);
         load_raw(1, j1, ti1);
+        load_raw(2, j2, ti2);
         resolve(j0, ti0, m0, ps0, pt0);
         for (int it = 0; it < my_tiles; it++) {
             const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
             (void)t0;
             unsigned char *msg = b1 + mbuf * msg_bytes;
             int *sj = s_j + (it & 1) * NT;
-            load_raw(it + 2, j2, ti2);                                          // tile it+2: stays in flight
+            load_raw(it + 3, j3, ti3);                                          // tile it+3: two rows stay in flight
             resolve(j1, ti1, m1, ps1, pt1);                                     // tile it+1: its row was loaded a step ago
             const int n = gw * 32 + lane;
             sj[n] = j0;
@@ -372,14 +373,16 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 for (int o = 16; o; o >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(FULL, nrm, o));
                 const float den = nrm + 1e-8f;
                 uint4 g;
-                g.x = pack_bf16(dx / den, dy / den);
-                g.y = pack_bf16(dz / den, ps0.w);
+                const float inv = 1.f / den;        // one division; the quotients are rounded to bf16 right below
+                g.x = pack_bf16(dx * inv, dy * inv);
+                g.y = pack_bf16(dz * inv, ps0.w);
                 g.z = 0x00003F80u;                 // column C+4 = 1.0: carries b1 through the contraction
                 g.w = 0;
                 *reinterpret_cast<uint4 *>(msg + CPR * LBO1 + n * 16) = g;
             }
             j0 = j1; m0 = m1; pt0 = pt1; ps0 = ps1;
             j1 = j2; ti1 = ti2;
+            j2 = j3; ti2 = ti3;
             gather_bar();
             P2W_TSR(p, it, 3, 3);
             // feature rows: lanes run along a row (coalesced), 8 channels -> one 16-byte smem store
