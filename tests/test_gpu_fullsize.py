@@ -1,0 +1,172 @@
+"""GPU tests at BASELINE.json's FULL sizes (tiles of 16 384 points, batches of 8 tiles, a 1 M-point plot), where
+the CPU oracle is too slow to check everything: size-independent properties instead -- two independent
+implementations agreeing bit for bit, sortedness, idempotence, permutation invariance, exact affine relations,
+run-to-run determinism -- plus the oracle on a random SAMPLE of the queries."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TILE = 16384
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pointstowood_b200 import ops as _ops
+    return _ops
+
+
+def _full_tiles(kind, tiles=8, seed=3):
+    """`tiles` tiles of exactly 16 384 points (SURVEY.md 8(d) micro-bench tiles): uniform in a 2 m cube, or cut
+    from the synthetic TLS plot (surface-like, strongly non-uniform)."""
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        x = rng.random((tiles * TILE, 3), dtype=np.float32) * 2
+    else:
+        from pointstowood_b200.synthetic import tls_plot
+        p, _ = tls_plot(tiles * TILE * 3, seed, side=12.0)
+        order = np.argsort((p[:, 0] // 2.0) * 16 + (p[:, 1] // 2.0), kind="stable")     # 2 m columns, contiguous
+        x = np.ascontiguousarray(p[order][: tiles * TILE, :3])
+    ptr = (np.arange(tiles + 1) * TILE).astype(np.int64)
+    return x, ptr
+
+
+@pytest.mark.parametrize("kind", ["uniform", "tls"])
+@pytest.mark.parametrize("k", [16, 32])
+def test_knn_on_full_tiles(ops, kind, k):
+    x, ptr = _full_tiles(kind)
+    xd, pd = torch.from_numpy(x).cuda(), torch.from_numpy(ptr).cuda()
+    grid, gd = ops.knn_table(xd, xd, k, pd, pd, return_d2=True, method="grid")
+    sweep, sd = ops.knn_table(xd, xd, k, pd, pd, return_d2=True, method="sweep")
+    assert torch.equal(grid, sweep) and torch.equal(gd, sd), "cell-list and brute-force searches disagree"
+    # every row ascending in (d2, index); the query itself first (d2 = 0) unless a duplicate precedes it
+    key = (gd.view(torch.int32).to(torch.int64) << 32) | grid.to(torch.int64)
+    assert bool((key[:, 1:] > key[:, :-1]).all()), "rows are not strictly ascending in (d2, index)"
+    assert bool((gd[:, 0] == 0).all())
+    # neighbours stay inside the query's tile
+    tile_of = torch.arange(x.shape[0], device="cuda") // TILE
+    assert bool((grid.to(torch.int64) // TILE == tile_of[:, None]).all())
+    # the oracle on a sample of the queries (same sources, same tiles)
+    rng = np.random.default_rng(k)
+    pick = np.sort(rng.choice(x.shape[0], 1024, replace=False))
+    ptr_q = np.searchsorted(pick, ptr).astype(np.int64)
+    ref, ref_d = O.knn(x, x[pick], k, ptr, ptr_q, return_d2=True)
+    assert np.array_equal(grid[pick].cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(gd[pick].cpu().numpy(), ref_d)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "tls"])
+def test_radius_on_full_tiles(ops, kind):
+    x, ptr = _full_tiles(kind)
+    xd, pd = torch.from_numpy(x).cuda(), torch.from_numpy(ptr).cuda()
+    r = 0.08
+    grid, gc = ops.radius_table(xd, xd, r, pd, pd, 32, method="grid")
+    sweep, sc = ops.radius_table(xd, xd, r, pd, pd, 32, method="sweep")
+    assert torch.equal(grid, sweep) and torch.equal(gc, sc)
+    valid = grid >= 0
+    assert bool((valid.sum(1) == gc).all()) and bool((gc >= 1).all())          # a point is its own neighbour
+    # ascending indices, all within r (FP32 d2 < r^2 as upstream), padding only at the end
+    g64 = grid.to(torch.int64)
+    assert bool(((g64[:, 1:] > g64[:, :-1]) | ~valid[:, 1:]).all())
+    assert bool((valid[:, :-1] | ~valid[:, 1:]).all())
+    src = xd[g64.clamp_min(0)]
+    d2 = ((src - xd[:, None, :]) ** 2).sum(-1)
+    assert bool((d2[valid] < np.float32(r) * np.float32(r) * 1.0001).all())
+    pick = np.sort(np.random.default_rng(5).choice(x.shape[0], 1024, replace=False))
+    ref = O.radius(x, x[pick], r, ptr, np.searchsorted(pick, ptr).astype(np.int64), 32)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    assert np.array_equal(grid[pick].cpu().numpy().astype(np.int64), ref)
+
+
+def test_voxel_sample_covers_every_voxel_once(ops):
+    x, ptr = _full_tiles("tls")
+    xd = torch.from_numpy(x).cuda()
+    batch = (torch.arange(x.shape[0], device="cuda") // TILE).to(torch.int64)
+    for size in (0.04, 0.08, 0.16):
+        idx = ops.voxel_sample(xd, size, batch)
+        ids = ops.voxel_grid(xd, size, batch)
+        rep_ids = ids[idx]
+        assert bool((rep_ids[1:] > rep_ids[:-1]).all()), "representatives are not in ascending voxel order"
+        assert torch.unique(ids).numel() == idx.numel(), "a voxel has no / two representatives"
+        # the representative is the LAST point of its voxel (the pinned CPU behaviour)
+        last = torch.zeros(int(ids.max()) + 1, device="cuda", dtype=torch.int64).scatter_reduce_(
+            0, ids, torch.arange(x.shape[0], device="cuda"), reduce="amax", include_self=False)
+        assert torch.equal(last[rep_ids], idx)
+        # idempotence: on the same grid every representative is alone in its voxel
+        assert torch.unique(rep_ids).numel() == idx.numel()
+
+
+def test_fused_conv_is_invariant_to_neighbour_order_and_affine_in_bn(ops):
+    """SA2-sized call (100 k targets x 32 edges): max aggregation does not see the order of a target's edges,
+    and out(scale, shift) = scale * out(1, 0) + shift exactly for a positive scale (FP32 rows out)."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    C, H, Co, ns, nt = 128, 192, 256, 200_000, 100_000
+    x = torch.randn(ns, C, device="cuda", generator=g).bfloat16()
+    ps = torch.rand(ns, 4, device="cuda", generator=g)
+    idx = torch.linspace(0, ns - 1, nt, device="cuda").long()
+    nbr = (idx[:, None] + torch.randint(-200, 200, (nt, 32), device="cuda", generator=g)).clamp_(0, ns - 1).to(torch.int32)
+    nbr[torch.rand(nt, 32, device="cuda", generator=g) < 0.1] = -1                       # ragged rows
+    w1 = torch.randn(H, C + 4, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(Co, H, device="cuda", generator=g) * 0.1
+    b1, b2 = torch.randn(H, device="cuda", generator=g) * 0.1, torch.randn(Co, device="cuda", generator=g) * 0.1
+    one, zero = torch.ones(Co, device="cuda"), torch.zeros(Co, device="cuda")
+    run = lambda table, sc, sh: ops.pointnet_conv_max(x, ps, ps, table, w1, b1, w2, b2, sc, sh, mode=ops.CONV_BF16_TC,
+                                                      tgt_index=idx)
+    base = run(nbr, one, zero)
+    perm = torch.argsort(torch.rand(nt, 32, device="cuda", generator=g), dim=1)
+    assert torch.equal(run(torch.gather(nbr, 1, perm), one, zero), base), "edge order changed the result"
+    two = run(nbr, 2 * one, one)
+    has_edges = (nbr >= 0).any(1)
+    assert torch.equal(two[has_edges], base[has_edges] * 2 + 1)
+    assert bool((two[~has_edges] == 0).all())
+    assert torch.equal(run(nbr, one, zero), base), "two runs differ"
+
+
+def test_one_million_point_plot_properties():
+    """configs[1] at full size: tile-store invariants, run-to-run determinism of the whole path, launch-size
+    invariance of the integer results, ranges of the voted outputs."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pointstowood_b200 import model as M
+    from pointstowood_b200 import ops
+    from pointstowood_b200.predicter import classify_tiles
+    from pointstowood_b200.preprocessing import Voxelise
+    from pointstowood_b200.synthetic import tls_plot
+    cloud, _ = tls_plot(1_000_000, 1)
+    dev = torch.from_numpy(cloud).cuda()
+    torch.manual_seed(141190)
+    net = M.randomise_bn_(M.Net(num_classes=1), 5).cuda().eval().set_precision("bf16")
+
+    def tiles():
+        return Voxelise(dev, minpoints=128, maxpoints=16384, gridsize=(2.0, 4.0)).write_voxels()
+
+    a, b = tiles(), tiles()
+    assert np.array_equal(a.ptr, b.ptr) and torch.equal(a.members, b.members) and torch.equal(a.feat, b.feat)
+    sizes = a.sizes
+    assert sizes.min() >= 128 and sizes.max() <= 16384 and a.num_tiles > 1000
+    assert int(a.members.min()) >= 0 and int(a.members.max()) < len(cloud)
+    two_m = a.grid_of_tile == 2.0
+    n2 = int(a.ptr[int(two_m.sum())])                       # 2 m tiles come first
+    for part in (a.members[:n2], a.members[n2:]):           # a point sits in at most one tile per grid size
+        assert torch.unique(part).numel() == part.numel()
+    assert bool(torch.equal(a.feat[:, :3], dev[:, :3]))
+
+    def run(launch):
+        prob, pred, xyz, _ = classify_tiles(net, a, 8, 0.5, max_points_per_launch=launch, want_xyz=True)
+        label, pwood = ops.spatial_vote(xyz, prob, pred, dev[:, :3].contiguous(), 64, 1.0)
+        return prob, pred, label, pwood
+
+    p1, q1, l1, w1 = run(1 << 21)
+    p2, q2, l2, w2 = run(1 << 21)
+    assert torch.equal(p1, p2) and torch.equal(q1, q2) and torch.equal(l1, l2) and torch.equal(w1, w2), "non-deterministic"
+    p3, q3, l3, w3 = run(1 << 19)                           # four launch sets instead of one
+    # (bf16 GEMMs may pick another blocking for another row count: probabilities move in the last bf16 bits)
+    assert (q1 == q3).float().mean().item() >= 0.995 and (p1 - p3).abs().max().item() <= 5e-2
+    assert (l1 == l3).float().mean().item() >= 0.995
+    assert bool(((w1 >= 0) & (w1 <= 1)).all()) and bool((l1 <= 1).all()) and bool(torch.isfinite(p1).all())
+    assert p1.numel() == int(a.ptr[-1]) and l1.numel() == len(cloud)
