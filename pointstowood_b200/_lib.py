@@ -86,6 +86,16 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+def to_device(values, device, dtype=None):
+    """Small host metadata (CSR pointers, plans) to the device WITHOUT blocking the host: staged through the
+    caching pinned allocator and copied asynchronously.  torch.tensor(list, device=...) copies from pageable
+    memory, which makes the host wait for everything queued on the stream before it can launch again."""
+    import numpy as np
+    import torch
+    a = np.ascontiguousarray(values if dtype is None else np.asarray(values, dtype=dtype))
+    return torch.from_numpy(a).pin_memory().to(device, non_blocking=True)
+
+
 def check(rc: int) -> None:
     if rc != 0:
         raise P2WError(lib().p2w_last_error().decode() or f"libp2w error {rc}")

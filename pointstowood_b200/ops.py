@@ -18,6 +18,7 @@ from __future__ import annotations
 import math
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -611,8 +612,8 @@ def spatial_vote(classified_xyz: Tensor, prob: Tensor, pred: Tensor, original_xy
     if xyz.size(1) != 3 or org.size(1) != 3 or prob.numel() != xyz.size(0) or pred.numel() != xyz.size(0):
         raise _lib.P2WError("spatial_vote: inconsistent shapes")
     dev = xyz.device
-    px = torch.tensor([0, xyz.size(0)], device=dev, dtype=torch.int64)
-    py = torch.tensor([0, org.size(0)], device=dev, dtype=torch.int64)
+    px = _lib.to_device([0, xyz.size(0)], dev, np.int64)
+    py = _lib.to_device([0, org.size(0)], dev, np.int64)
     nbr = knn_table(xyz, org, k, px, py, method="grid", cell_size=cell_size)
     label = torch.empty(org.size(0), device=dev, dtype=torch.uint8)
     pwood = torch.empty(org.size(0), device=dev, dtype=torch.float64)

@@ -21,6 +21,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from . import _lib
 from . import model as M
 from . import ops
 from .preprocessing import TileStore
@@ -79,13 +80,13 @@ def classify_tiles(net: torch.nn.Module, tiles: TileStore, batch_size: int = 8, 
     dev = tiles.feat.device
     batches = plan_batches(tiles.num_tiles, batch_size)
     batch_ids = list(range(len(batches)) if batch_ids is None else batch_ids)
-    ptr_dev = torch.as_tensor(tiles.ptr, device=dev)
+    ptr_dev = _lib.to_device(tiles.ptr, dev, np.int64)
     probs, preds, rows, spans = [], [], [], []
     for group in plan_launches(batches, tiles.ptr, batch_ids, max_points_per_launch):
         t0, t1 = batches[group[0]][0], batches[group[-1]][1]
         lo, hi = int(tiles.ptr[t0]), int(tiles.ptr[t1])
         bptr = ptr_dev[t0: t1 + 1] - lo
-        gptr = torch.tensor([batches[b][0] - t0 for b in group] + [t1 - t0], device=dev, dtype=torch.int64)
+        gptr = _lib.to_device([batches[b][0] - t0 for b in group] + [t1 - t0], dev, np.int64)
         pos, refl, batch, shift, sf = ops.pack_tiles(tiles.feat, tiles.members[lo:hi], bptr)
         data = M.make_data(pos, refl, batch, sf, local_shift=shift.reshape(-1), ptr=bptr,
                            group_ptr=gptr if len(group) > 1 else None)

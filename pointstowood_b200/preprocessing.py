@@ -192,7 +192,7 @@ class Voxelise:
             # all kept voxels of this grid in one gather: member m of tile t sits at order[seg[v_t] + m]
             tile_sizes = np.minimum(counts[keep], self.maxpoints).astype(np.int64)
             off = np.concatenate([[0], np.cumsum(tile_sizes)]).astype(np.int64)
-            plan = torch.from_numpy(np.stack([seg[keep].astype(np.int64) - off[:-1], tile_sizes])).to(dev, non_blocking=True)
+            plan = _lib.to_device(np.stack([seg[keep].astype(np.int64) - off[:-1], tile_sizes]), dev)
             src = torch.arange(int(off[-1]), device=dev) + torch.repeat_interleave(plan[0], plan[1], output_size=int(off[-1]))
             members = order[src].to(torch.int64)
             if len(big):                                                # thinned tiles overwrite their placeholder rows
