@@ -92,3 +92,27 @@ def test_predict_column_handling():
     assert list(out.columns) == ["x", "y", "z", "reflectance", "red"] and headers == ["red", "reflectance"] and has
     out, headers, _ = preprocess_point_cloud_data(pd.DataFrame({"x": [0.0], "y": [1.0], "z": [2.0]}))
     assert list(out.columns) == ["x", "y", "z", "reflectance"] and out["reflectance"][0] == 0.0 and headers == []
+
+
+def test_predict_flags_match_the_reference(golden_dir):
+    """Every flag of the reference's predict.py exists with the same spellings, default, type, nargs and action
+    (tests/golden/predict_flags.json is read from the reference's source by oracle/make_golden_cli.py)."""
+    import json
+    from pointstowood_b200.predict import build_parser
+    want = json.load(open(os.path.join(golden_dir, "predict_flags.json")))
+    have = {}
+    for a in build_parser()._actions:
+        if a.option_strings:
+            have[max(a.option_strings, key=len)] = a
+    for flag, spec in want.items():
+        assert flag in have, f"missing {flag}"
+        a = have[flag]
+        assert sorted(a.option_strings) == spec["names"]
+        if "default" in spec:
+            assert a.default == spec["default"], flag
+        if "type" in spec:
+            assert a.type.__name__ == spec["type"], flag
+        if "nargs" in spec:
+            assert a.nargs == spec["nargs"], flag
+        if spec.get("action") == "store_true":
+            assert a.const is True and a.nargs == 0, flag
