@@ -17,44 +17,61 @@ from .io import load_file, save_file
 __all__ = ["preprocess_point_cloud_data", "build_parser", "predict_file", "main"]
 
 
+_RESULT_COLUMNS = ("label", "pwood", "pleaf")          # outputs of an earlier run: never inputs
+_REFLECTANCE_ALIASES = ("refl", "intensity")
+
+
 def preprocess_point_cloud_data(df):
-    """predict.py:36-53: lower-case names, drop earlier results, reflectance as the 4th column (zeros if absent).
-    Returns (frame, extra headers, has_reflectance)."""
-    df.columns = df.columns.str.lower()
-    dropped = ["label", "pwood", "pleaf"]
-    df = df.drop(columns=dropped, errors="ignore")
-    df = df.rename(columns=lambda c: c.replace("scalar_", "") if "scalar_" in c else c)
-    df = df.rename(columns={"refl": "reflectance", "intensity": "reflectance"})
-    headers = [h for h in df.columns[3:] if h not in dropped]
-    if "reflectance" not in df.columns:
+    """Column handling of predict.py:36-53: names lower-cased, a `scalar_` prefix (CloudCompare) removed, earlier
+    results dropped, the reflectance column (alias `refl` / `intensity`; zeros when the file has none) moved
+    to position 3.  Returns (frame, names of the extra columns in file order, True)."""
+    names = []
+    for col in df.columns:
+        low = str(col).lower()
+        if low in _RESULT_COLUMNS:
+            names.append(None)
+            continue
+        low = low.replace("scalar_", "")
+        names.append("reflectance" if low in _REFLECTANCE_ALIASES else low)
+    keep = [i for i, n in enumerate(names) if n is not None]
+    df = df.iloc[:, keep].copy()
+    df.columns = [names[i] for i in keep]
+    extras = [c for c in df.columns[3:] if c not in _RESULT_COLUMNS]
+    if "reflectance" in df.columns:
+        print("Reflectance detected")
+    else:
         df["reflectance"] = np.zeros(len(df))
         print("No reflectance detected, column added with zeros.")
-    else:
-        print("Reflectance detected")
-    cols = list(df.columns)
-    cols.insert(3, cols.pop(cols.index("reflectance")))
-    return df[cols], headers, True
+    order = list(df.columns[:3]) + ["reflectance"] + [c for c in df.columns[3:] if c != "reflectance"]
+    return df[order], extras, True
+
+
+# (flag spellings, argparse keywords): the reference's command line (predict.py:62-75) plus --precision / --wdir
+_FLAGS = [
+    (("--point-cloud", "-p"), dict(default=[], nargs="+", type=str, help="point cloud files (.ply, .pcd, .las)")),
+    (("--odir",), dict(type=str, default=".", help="output directory")),
+    (("--batch_size",), dict(default=8, type=int, help="tiles per reference batch (it fixes the voxel-grid origin)")),
+    (("--num_procs",), dict(default=-1, type=int, help="host threads, -1 = all")),
+    (("--resolution",), dict(type=float, default=0.01, help="accepted for compatibility")),
+    (("--grid_size",), dict(type=float, nargs="+", default=[2.0, 4.0], help="tile sizes in metres")),
+    (("--min_pts",), dict(type=int, default=128, help="smallest tile kept")),
+    (("--max_pts",), dict(type=int, default=16384, help="largest tile (bigger ones are thinned)")),
+    (("--model",), dict(type=str, default="model.pth", help="checkpoint: a path, or a name under <wdir>/model/")),
+    (("--is-wood",), dict(default=0.5, type=float, help="probability from which a point counts as wood")),
+    (("--any-wood",), dict(default=1, type=float, help="probability from which ANY neighbour makes a point wood")),
+    (("--output_fmt",), dict(default="ply", help="ply, pcd, csv or las")),
+    (("--verbose",), dict(action="store_true", help="progress messages")),
+    (("--precision",), dict(default="bf16", choices=["bf16", "fp32"],
+                            help="bf16: tensor-core PointNetConv (|dp| <= 1e-2); fp32: parity mode (|dp| <= 1e-3)")),
+    (("--wdir",), dict(type=str, default=".", help="directory holding model/ (the reference derives it from the cwd)")),
+]
 
 
 def build_parser() -> argparse.ArgumentParser:
-    p = argparse.ArgumentParser(description=__doc__)
-    p.add_argument("--point-cloud", "-p", default=[], nargs="+", type=str, help="list of point cloud files")
-    p.add_argument("--odir", type=str, default=".", help="output directory")
-    p.add_argument("--batch_size", default=8, type=int, help="tiles per reference batch (fixes the voxel-grid origin)")
-    p.add_argument("--num_procs", default=-1, type=int, help="host threads (torch.set_num_threads)")
-    p.add_argument("--resolution", type=float, default=0.01, help="kept for compatibility")
-    p.add_argument("--grid_size", type=float, nargs="+", default=[2.0, 4.0], help="grid sizes for voxelization")
-    p.add_argument("--min_pts", type=int, default=128, help="minimum number of points in a voxel")
-    p.add_argument("--max_pts", type=int, default=16384, help="maximum number of points in a voxel")
-    p.add_argument("--model", type=str, default="model.pth", help="checkpoint: a path, or a name under <wdir>/model/")
-    p.add_argument("--is-wood", default=0.5, type=float, help="probability above which a point is wood")
-    p.add_argument("--any-wood", default=1, type=float, help="probability above which ANY neighbour makes a point wood")
-    p.add_argument("--output_fmt", default="ply", help="file type of the output")
-    p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
-                   help="bf16: tensor-core PointNetConv (|dp| <= 1e-2); fp32: parity mode (|dp| <= 1e-3)")
-    p.add_argument("--wdir", type=str, default=".", help="directory that holds model/ (the reference derives it from the cwd)")
-    p.add_argument("--verbose", action="store_true", help="print stuff")
-    return p
+    parser = argparse.ArgumentParser(description=__doc__)
+    for names, kw in _FLAGS:
+        parser.add_argument(*names, **kw)
+    return parser
 
 
 def predict_file(args, point_cloud_file: str, net=None) -> str:
