@@ -719,7 +719,6 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
 // more than the handful of distances a query needs; here a thread walks the 27 cells of its first ring
 // in the same nearest-first order, skips cells that cannot beat its current k-th distance, and keeps
 // its k best keys in registers.  Same keys, same stopping bound, same results.
-__host__ __device__ constexpr int nb_d(unsigned long long lut, int s) { return static_cast<int>((lut >> (2 * s)) & 3ull) - 1; }
 
 template <int K>
 __device__ __forceinline__ void small_insert(key_t (&best)[K], key_t ck) {

@@ -305,7 +305,6 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ sr
     __shared__ float red_v[32];
     __shared__ int red_i[32];
     __shared__ float last[3];
-    __shared__ int last_i;
     const int b = blockIdx.x;
     const int64_t s0 = ptr[b];
     const int n = static_cast<int>(ptr[b + 1] - s0);
@@ -329,7 +328,6 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ sr
         last[0] = src[s0 * 3 + 0];
         last[1] = src[s0 * 3 + 1];
         last[2] = src[s0 * 3 + 2];
-        last_i = 0;
     }
     __syncthreads();
     for (int j = 1; j < m; j++) {
@@ -374,7 +372,6 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ sr
             }
             if (lane == 0) {
                 if (bi == 0x7fffffff) bi = 0;
-                last_i = bi;
                 out[o0 + j] = s0 + bi;
                 last[0] = src[(s0 + bi) * 3 + 0];
                 last[1] = src[(s0 + bi) * 3 + 1];
