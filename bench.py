@@ -66,7 +66,9 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], src="measured")
+        if "hbm_gbs" in p and "bf16_tflops" in p:           # a driver file without the sustained figure: burst for both
+            return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"],
+                        bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
