@@ -19,11 +19,14 @@ median pwood, class votes).  File I/O (src/io.py) is outside the region on both 
 `cpu_baseline` / `--impl reference`: the reference's host + model code cannot be imported on the
             GPU box (torch_geometric, torch_cluster, torch_scatter absent), so the CPU arm is the
             oracle's restatement (oracle/ref_pipeline.py + ref_model.py, kind "port") on all host
-            threads: full tiling, a bounded sample of the batches extrapolated by tile points to the
-            whole plot, and the full spatial vote (scipy cKDTree on all cores) on a plot-sized stand-in
-            for the classified rows.
-N > 1 (torchrun): every rank classifies its own 1 M-point plot (seed 1 + rank): weak scaling, no
-collective on the data path; time = max over ranks.
+            threads, with one KD-tree per tile for knn / radius (torch_cluster's CPU back end).  A step is
+            the WHOLE pipeline on a bounded sample -- every point of the 5 x 5 m corner of the plot -- and
+            the value is those points over that time: nothing extrapolated.
+N > 1 (torchrun): ONE plot sharded over the ranks (pointstowood_b200/distributed.py): rank r holds a chunk of
+the rows, tiles are owned in contiguous ranges of whole batches, the vote runs on x-slabs with a halo; the
+result equals the single-GPU one.  `--scaling weak` (default): the plot has N x --points points (per-GPU work
+fixed); `--scaling strong`: --points points in total (BASELINE.json configs[3]: --points 100000000 --gpus 8).
+Time = max over ranks.
 """
 from __future__ import annotations
 
@@ -49,6 +52,12 @@ def workload(n_points: int) -> str:
     """The same description on both arms (BASELINE.json configs[1])."""
     return (f"predict {n_points}-point synthetic TLS plot per GPU, grid 2/4 m, min_pts 128, max_pts 16384, batch_size 8, "
             "seeded weights; cloud -> tiles -> network -> spatial vote -> (label, pwood) per point")
+
+
+def workload_sharded(total_points: int, world: int) -> str:
+    return (f"predict ONE {total_points}-point synthetic TLS plot ({total_points // 1_000_000 or 1} blocks of 1 M points, 2500 points/m^2) "
+            f"sharded over {world} GPU(s), grid 2/4 m, min_pts 128, max_pts 16384, batch_size 8, seeded weights; "
+            "cloud -> tiles -> network -> spatial vote -> (label, pwood) per point")
 
 
 def load_traffic():
@@ -111,70 +120,66 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_arm(n_points: int, seed: int, budget_s: float = 20.0):
-    """Times the oracle restatement of the same pipeline on the host cores: full tiling, then as
-    many batches as fit the budget, extrapolated by tile points to the whole plot."""
+CPU_SAMPLE_SIDE = 5.0        # metres: the [0, 5) x [0, 5) m corner of the plot, every point in it (1/16 of the 1 M plot)
+
+
+def cpu_sample(n_points: int, seed: int, side: float = CPU_SAMPLE_SIDE):
+    from pointstowood_b200.synthetic import tls_plot
+    cloud, _ = tls_plot(n_points, seed)
+    return np.ascontiguousarray(cloud[(cloud[:, 0] < side) & (cloud[:, 1] < side)])
+
+
+def cpu_arm(cloud: np.ndarray):
+    """One pass of the oracle restatement of the SAME pipeline over `cloud` on the host cores, nothing skipped and
+    nothing extrapolated: tiling, every batch through the network (neighbour searches on one KD-tree per tile,
+    single-threaded per call like torch_cluster's CPU back end; dense layers on torch with all threads,
+    predict.py:79-84), write-back, spatial vote (KD-tree over the classified rows just produced).
+    Returns (seconds, points)."""
     import torch
     from oracle import oracle as O
     from oracle import ref_model, ref_pipeline
-    from pointstowood_b200.synthetic import tls_plot
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)                       # predict.py:79-84
-    O.lib().orc_set_threads(cores)
-    cloud, _ = tls_plot(n_points, seed)
+    O.SEARCH = "kdtree"
     sd = ref_model.seeded_state_dict()
     t0 = time.perf_counter()
     feat5, tiles, _ = ref_pipeline.preprocess(cloud, CFG["grid_size"], CFG["min_pts"], CFG["max_pts"])
-    t_pre = time.perf_counter() - t0
-    total_pts = sum(len(t) for t in tiles)
-    # sample batches evenly across the tile list (2 m tiles are small, 4 m tiles large)
-    nb = (len(tiles) + CFG["batch_size"] - 1) // CFG["batch_size"]
-    order = np.linspace(0, nb - 1, num=min(nb, 64)).round().astype(int)
-    done_pts, t_cls, used = 0, 0.0, 0
-    for b in dict.fromkeys(order.tolist()):
-        group = tiles[b * CFG["batch_size"]:(b + 1) * CFG["batch_size"]]
-        t1 = time.perf_counter()
-        ref_pipeline.classify(sd, feat5, group, CFG["batch_size"], CFG["is_wood"])
-        t_cls += time.perf_counter() - t1
-        done_pts += sum(len(t) for t in group)
-        used += 1
-        if t_cls > budget_s:
-            break
-    # spatial vote on a plot-sized stand-in for the classified rows: every tile point at its own
-    # coordinates with a synthetic probability (the KD-tree cost does not depend on the values)
-    members = np.concatenate(tiles)
-    rng = np.random.default_rng(0)
-    prob = rng.random(len(members))
-    rows = np.concatenate([feat5[members, :3].astype(np.float64), (prob >= 0.5)[:, None].astype(np.float64),
-                           prob[:, None]], axis=1)
-    t2 = time.perf_counter()
+    rows = ref_pipeline.classify(sd, feat5, tiles, CFG["batch_size"], CFG["is_wood"])
     ref_pipeline.collect_predictions(rows, cloud[:, :3], 1, workers=cores)
-    t_vote = time.perf_counter() - t2
-    est = t_pre + t_cls * total_pts / max(done_pts, 1) + t_vote
-    return dict(value=n_points / est, unit="points/s", cores=cores, kind="port",
-                sample=f"full tiling ({t_pre:.2f} s) + {used} of {nb} batches ({done_pts} of {total_pts} tile points, "
-                       f"{t_cls:.1f} s), extrapolated by tile points + full spatial vote ({t_vote:.1f} s)"), est
+    dt = time.perf_counter() - t0
+    O.SEARCH = "brute"
+    return dt, len(cloud), len(tiles), len(rows)
+
+
+def cpu_baseline_dict(value, cores, n_sample, n_tiles, n_rows, secs):
+    return dict(value=value, unit="points/s", cores=cores, kind="port",
+                sample=f"every point of the [0,{CPU_SAMPLE_SIDE:g}) x [0,{CPU_SAMPLE_SIDE:g}) m corner of the plot ({n_sample} points, "
+                       f"{n_tiles} tiles, {n_rows} classified rows) through the whole pipeline in {secs:.1f} s; "
+                       "value = those points / that time, nothing extrapolated; oracle port of the reference host + model "
+                       "code (the reference itself needs torch_geometric / torch_cluster / torch_scatter, absent here), "
+                       "KD-tree per tile for knn / radius, torch CPU for the dense layers")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    base = None
+    cloud = cpu_sample(N_POINTS, 1)
+    secs = []
     for i in range(args.warmup + args.steps):
-        base, est = cpu_arm(N_POINTS, 1, budget_s=12.0)
+        dt, n, n_tiles, n_rows = cpu_arm(cloud)
         if i >= args.warmup:
-            vals.append(est)
-    ms = float(np.mean(vals)) * 1e3
-    value = N_POINTS / (ms / 1e3)
-    base["value"] = value
+            secs.append(dt)
+    ms = float(np.mean(secs)) * 1e3
+    value = len(cloud) / (ms / 1e3)
+    cores = os.cpu_count() or 1
     line = dict(impl="reference", metric="points classified/sec", value=value, unit="points/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=workload(N_POINTS),
-                            arm="reference pipeline restated on oracle CPU ops (kind: port), bounded sample per step"),
-                cpu_baseline=base,
+                config=dict(workload=workload(N_POINTS) if args.gpus == 1 else workload_sharded(N_POINTS * args.gpus, args.gpus),
+                            arm="oracle port of the reference pipeline on the host cores; each step = the whole pipeline "
+                                f"on a bounded sample of the workload ({len(cloud)} points, see cpu_baseline.sample)"),
+                cpu_baseline=cpu_baseline_dict(value, cores, len(cloud), n_tiles, n_rows, ms / 1e3),
                 e2e=dict(value=value, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -187,10 +192,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="p2w", choices=["p2w", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--points", type=int, default=N_POINTS,
+                    help="points per GPU (--scaling weak) or of the whole plot (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1 always shards ONE plot over the ranks: of N x points (weak) or of points (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--launch-points", type=int, default=1 << 21,
                     help="points of consecutive reference batches that share one launch set")
+    ap.add_argument("--halo", type=float, default=0.5, help="metres of classified rows shared across vote slabs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -199,9 +208,10 @@ def main():
     import torch.distributed as dist
     from pointstowood_b200 import _lib, ops
     from pointstowood_b200 import model as M
+    from pointstowood_b200.distributed import Comm, classify_plot
     from pointstowood_b200.predicter import classify_tiles
     from pointstowood_b200.preprocessing import Voxelise
-    from pointstowood_b200.synthetic import tls_plot
+    from pointstowood_b200.synthetic import tls_plot, tls_plot_blocks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,12 +220,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
-    n_points = args.points
+    total_points = args.points * world if args.scaling == "weak" else args.points
     peaks = load_peaks()
     L = _lib.lib()
 
-    cloud_np, _ = tls_plot(n_points, 1 + rank)
-    host = torch.from_numpy(cloud_np).pin_memory()
+    # rank r holds rows lo..hi of the plot (the whole plot at N = 1).  1 M points: tls_plot(seed 1), configs[1];
+    # larger plots: 1 M-point blocks, block b = tls_plot(seed 1 + b) (configs[3])
+    lo, hi = rank * total_points // world, (rank + 1) * total_points // world
+    if total_points <= N_POINTS:
+        cloud_np = tls_plot(total_points, 1)[0][lo:hi]
+    else:
+        cloud_np = tls_plot_blocks(total_points, 1, rows=(lo, hi))[0]
+    n_local = hi - lo
+    host = torch.from_numpy(np.ascontiguousarray(cloud_np)).pin_memory()
     dev_cloud = host.cuda()
     bf16 = args.precision == "bf16"
     torch.manual_seed(141190)
@@ -224,13 +241,21 @@ def main():
     net = net.cuda().eval().set_precision("bf16" if bf16 else "fp32")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    info = {}
 
     def step(cloud):
-        store = Voxelise(cloud, minpoints=CFG["min_pts"], maxpoints=CFG["max_pts"], gridsize=CFG["grid_size"]).write_voxels()
-        prob, pred, xyz, _ = classify_tiles(net, store, CFG["batch_size"], CFG["is_wood"],
-                                            max_points_per_launch=args.launch_points, want_xyz=True)
-        label, pwood = ops.spatial_vote(xyz, prob, pred, cloud[:, :3].contiguous(), 64, 1.0)
-        return store, label, pwood
+        if world == 1:
+            store = Voxelise(cloud, minpoints=CFG["min_pts"], maxpoints=CFG["max_pts"], gridsize=CFG["grid_size"]).write_voxels()
+            prob, pred, xyz, _ = classify_tiles(net, store, CFG["batch_size"], CFG["is_wood"],
+                                                max_points_per_launch=args.launch_points, want_xyz=True)
+            label, pwood = ops.spatial_vote(xyz, prob, pred, cloud[:, :3].contiguous(), 64, 1.0)
+            info.update(tile_points=int(store.ptr[-1]), tiles=int(store.num_tiles))
+            return label, pwood
+        label, pwood, plot = classify_plot(net, cloud, CFG["min_pts"], CFG["max_pts"], CFG["grid_size"], CFG["batch_size"],
+                                           CFG["is_wood"], 1, args.launch_points, args.halo, return_plot=True)
+        info.update(tile_points=plot.tile_points, tiles=int(plot.num_tiles), traffic=dict(plot.traffic), halo=plot.halo,
+                    vote_rounds=plot.vote_rounds)
+        return label, pwood
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,10 +264,9 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        store, label, pwood = step(dev_cloud)
-    tile_points = int(store.ptr[-1])
-    out_label = torch.empty(n_points, dtype=torch.uint8).pin_memory()
-    out_pwood = torch.empty(n_points, dtype=torch.float64).pin_memory()
+        label, pwood = step(dev_cloud)
+    out_label = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    out_pwood = torch.empty(n_local, dtype=torch.float64).pin_memory()
 
     # ---- device-resident steps, dominant kernel timed live with CUDA events
     ops.KERNEL_TIMER.reset("p2w_pointnet_conv_max", "p2w_knn")
@@ -266,7 +290,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         cloud = host.cuda(non_blocking=True)
-        _, label, pwood = step(cloud)
+        label, pwood = step(cloud)
         out_label.copy_(label, non_blocking=True)
         out_pwood.copy_(pwood, non_blocking=True)
     e1.record()
@@ -274,22 +298,29 @@ def main():
     ms_e2e = e0.elapsed_time(e1) / args.steps
 
     t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    tp = torch.tensor([info.get("tile_points", 0), launches], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
     ms, ms_e2e = t.tolist()
+    tile_points, launches = (int(v) for v in tp.tolist())
 
     if rank == 0:
         traffic = load_traffic()
+        clocks = clk.summary()
+        at_max = bool(clocks["sm_mhz"] and clocks["sm_max_mhz"] and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"]
+                      and "sw_power_cap" not in clocks["reasons"])
         roof_conv = roof_knn = None
         if kt_conv["launches"]:
             per_launch_ms = kt_conv["ms"] / kt_conv["launches"]
             achieved = kt_conv["work"] / kt_conv["launches"] / per_launch_ms / 1e9              # TFLOP/s
-            peak = peaks["bf16_sustained"] if bf16 else None
+            peak = (peaks["bf16"] if at_max else peaks["bf16_sustained"]) if bf16 else None
             roof_conv = dict(kernel="conv_tc_kernel (fused gather-MLP-max, tcgen05)" if bf16 else
                              "conv_simt_kernel (fused gather-MLP-max, FP32 parity mode)",
                              bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s",
                              frac=achieved / peak if peak else None,
-                             peak_source=f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
+                             peak_source=f"{peaks['src']} " + ("burst bf16: the sampled SM clock stayed at its maximum with no power cap"
+                                                               if at_max else "sustained bf16: the SM clock dropped under the power cap"),
                              traffic=traffic.get("conv_tc_kernel") if bf16 else None,
                              work="FLOPs = 32 n_tgt (2 (C+4) H + 2 H C') per launch, unpadded (SURVEY.md 8d)",
                              launches=kt_conv["launches"], avg_launch_ms=per_launch_ms)
@@ -302,20 +333,27 @@ def main():
                             work="bytes = 12 (Nx + Ny) + 16 Ny k + 16 (B+1) per call (SURVEY.md 8d)",
                             launches=kt_knn["launches"], avg_launch_ms=per_launch_ms)
         roof = roof_conv if bf16 else roof_knn
-        line = dict(metric="points classified/sec", value=world * n_points / (ms / 1e3), unit="points/s", n_gpus=world,
-                    steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="bf16" if bf16 else "f32", data="synthetic",
-                    config=dict(workload=workload(n_points),
-                                tile_points=tile_points, tiles=int(store.num_tiles),
-                                launch_points=args.launch_points,
-                                l2="no flush needed: a step streams > 4 GB of activations (e.g. the [N0, 544] and "
-                                   "[N0, 512] FP buffers) between two launches of any kernel, 30x the 126 MB L2"),
-                    e2e=dict(value=world * n_points / (ms_e2e / 1e3), unit="points/s", h2d_bytes_per_step=int(host.numel() * 4),
-                             d2h_bytes_per_step=int(n_points * 9)),
-                    gpu_launches=int(launches), clocks=clk.summary(), roofline=roof,
+        config = dict(workload=workload(N_POINTS) if (world == 1 and total_points == N_POINTS) else
+                      workload_sharded(total_points, world),
+                      tile_points=tile_points, tiles=info.get("tiles"), launch_points=args.launch_points,
+                      l2="no flush needed: a step streams > 4 GB of activations (e.g. the [N0, 544] and "
+                         "[N0, 512] FP buffers) between two launches of any kernel, 30x the 126 MB L2")
+        if world > 1:
+            config.update(partition="rows chunked over ranks; tiles owned in contiguous ranges of whole batches; vote by x-slabs "
+                                    f"with a {info.get('halo', args.halo):g} m halo ({info.get('vote_rounds')} round(s)); results "
+                                    "identical to one GPU",
+                          collective_bytes_rank0_per_step={k: v for k, v in sorted(info.get("traffic", {}).items())})
+        line = dict(metric="points classified/sec", value=total_points / (ms / 1e3), unit="points/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling=args.scaling,
+                    vs_baseline=None, dtype="bf16" if bf16 else "f32", data="synthetic", config=config,
+                    e2e=dict(value=total_points / (ms_e2e / 1e3), unit="points/s", h2d_bytes_per_step=int(total_points * 16),
+                             d2h_bytes_per_step=int(total_points * 9)),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof,
                     roofline_knn=roof_knn if bf16 else roof_conv)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_arm(n_points, 1, budget_s=15.0)
+            sample = cpu_sample(N_POINTS, 1)
+            dt, n, n_tiles, n_rows = cpu_arm(sample)
+            line["cpu_baseline"] = cpu_baseline_dict(n / dt, os.cpu_count() or 1, n, n_tiles, n_rows, dt)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

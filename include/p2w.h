@@ -267,10 +267,18 @@ int p2w_spatial_vote(const int32_t *nbr, int64_t n, int32_t k, const float *prob
  * [1e-7, 1-1e-7] -> erfinv(2q-1)*sqrt(2); then out = 2 (v-min)/(max-min) - 1.
  * p2w_assemble5: feat [n,5] = (x, y, z, reflectance_scaled, n_z), the array the reference
  * voxelises with all five columns (:52,58).
- * p2w_priority_keys (stand-in for torch.multinomial without replacement, :116-118, which is
- * random in the reference): priority = w_i / u_i with w = refl - min(refl) + 1e-8 and u a
- * counter-based hash of (seed, point index) in (0,1]; key = (tile_rank << 32) | ~bits(priority),
- * so an ascending sort lists every oversized tile's members by descending priority. */
+ * p2w_sampling_keys (torch.multinomial without replacement, :116-118, which draws from torch's
+ * global generator in the reference): Efraimidis-Spirakis keys -log(u_i) / w_i (float64, written as
+ * their order-preserving bit pattern) with w = feat[i, col] - refl_min + 1e-8 and u a counter-based hash
+ * of (seed, point index) in (0,1]; ascending key order = the order in which sequential weighted
+ * sampling without replacement draws the members, so the first max_pts of a tile are the sample.
+ * members [m] are rows of feat; global_index (may be NULL) maps a row of feat to the point index that
+ * is hashed (a rank of a sharded plot holds a subset of the rows).
+ * p2w_replacement_picks (torch.randint, :120, clouds without reflectance): picks[t, s] =
+ * members[seg[t] + hash(seed, voxel_id[t], s) mod (seg[t+1] - seg[t])], max_pts draws WITH
+ * replacement for each of num_tiles oversized tiles.
+ * p2w_ground_min / p2w_ground_apply are the two halves of p2w_ground_normalize (a sharded plot
+ * min-reduces cell_min over the ranks in between). */
 int p2w_ground_normalize(const float *cloud, int32_t ld, int64_t n, const float *mn_xy,
                          float cell, int32_t nbx, int32_t nby, float *cell_min, float *n_z,
                          p2w_stream_t stream);
@@ -280,8 +288,16 @@ int p2w_reflectance_normalize(const int32_t *sorted_idx, int64_t n, float *v, fl
                               float *out, p2w_stream_t stream);
 int p2w_assemble5(const float *cloud, int32_t ld, const float *refl, const float *n_z, int64_t n,
                   float *feat, p2w_stream_t stream);
-int p2w_priority_keys(const float *feat, const int32_t *members, const int32_t *member_tile,
-                      int64_t m, float refl_min, uint32_t seed, uint64_t *keys, p2w_stream_t stream);
+int p2w_sampling_keys(const float *feat, int32_t ld, int32_t col, const int32_t *members,
+                      const int32_t *global_index, int64_t m, float refl_min, uint32_t seed,
+                      uint64_t *keys, p2w_stream_t stream);
+int p2w_replacement_picks(const int32_t *members, const int64_t *seg, const int64_t *voxel_id,
+                          int32_t num_tiles, int32_t max_pts, uint64_t seed, int32_t *picks,
+                          p2w_stream_t stream);
+int p2w_ground_min(const float *cloud, int32_t ld, int64_t n, const float *mn_xy, float cell,
+                   int32_t nbx, int32_t nby, float *cell_min, p2w_stream_t stream);
+int p2w_ground_apply(const float *cloud, int32_t ld, int64_t n, const float *mn_xy, float cell,
+                     int32_t nbx, int32_t nby, const float *cell_min, float *n_z, p2w_stream_t stream);
 
 #ifdef __cplusplus
 }

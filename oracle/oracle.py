@@ -55,11 +55,41 @@ def batch_to_ptr(batch, batch_size=None):
     return np.searchsorted(batch, np.arange(batch_size + 1), side="left").astype(np.int64)
 
 
+# "brute": the C restatement of torch_cluster's CUDA scan (the parity checker).  "kdtree": one KD-tree per
+# tile, single-threaded per call, leaf size 10 -- the cost profile of torch_cluster's CPU back end (nanoflann,
+# SURVEY.md Appendix A.2/A.3), used ONLY by bench.py's timed CPU arm; same neighbour sets up to ties / last ulp.
+SEARCH = "brute"
+
+
+def _kdtree_search(x, y, k, ptr_x, ptr_y, r=None):
+    from scipy.spatial import cKDTree
+    nbr = np.full((y.shape[0], k), -1, dtype=np.int64)
+    d2 = np.full((y.shape[0], k), 1e10, dtype=np.float32)
+    for b in range(len(ptr_x) - 1):
+        x0, x1, y0, y1 = int(ptr_x[b]), int(ptr_x[b + 1]), int(ptr_y[b]), int(ptr_y[b + 1])
+        if x1 == x0 or y1 == y0:
+            continue
+        tree = cKDTree(x[x0:x1], leafsize=10)
+        kk = min(k, x1 - x0)
+        d, i = tree.query(y[y0:y1], k=kk, workers=1, **({} if r is None else {"distance_upper_bound": r}))
+        d, i = d.reshape(y1 - y0, kk), i.reshape(y1 - y0, kk)
+        ok = i < (x1 - x0)
+        if r is not None:                       # radius: the hits, ascending index (CUDA order)
+            i = np.sort(np.where(ok, i, x1 - x0), axis=1)
+            ok = i < (x1 - x0)
+        nbr[y0:y1, :kk] = np.where(ok, i + x0, -1)
+        d2[y0:y1, :kk] = np.where(ok, (d * d).astype(np.float32), np.float32(1e10))
+    return nbr, d2
+
+
 def knn(x, y, k, ptr_x=None, ptr_y=None, return_d2=False):
     """[Ny,k] int64 neighbour table, -1 padded (model.py:120,149; Appendix A.2)."""
     x, y = _f32(x), _f32(y)
     ptr_x = _i64([0, x.shape[0]]) if ptr_x is None else _i64(ptr_x)
     ptr_y = _i64([0, y.shape[0]]) if ptr_y is None else _i64(ptr_y)
+    if SEARCH == "kdtree":
+        nbr, d2 = _kdtree_search(x, y, k, ptr_x, ptr_y)
+        return (nbr, d2) if return_d2 else nbr
     nbr = np.empty((y.shape[0], k), dtype=np.int64)
     d2 = np.empty((y.shape[0], k), dtype=np.float32)
     rc = lib().orc_knn(_p(x, ctypes.c_float), _p(y, ctypes.c_float), _p(ptr_x, ctypes.c_int64),
@@ -75,6 +105,9 @@ def radius(x, y, r, ptr_x=None, ptr_y=None, max_num_neighbors=32):
     x, y = _f32(x), _f32(y)
     ptr_x = _i64([0, x.shape[0]]) if ptr_x is None else _i64(ptr_x)
     ptr_y = _i64([0, y.shape[0]]) if ptr_y is None else _i64(ptr_y)
+    if SEARCH == "kdtree":
+        nbr, _ = _kdtree_search(x, y, max_num_neighbors, ptr_x, ptr_y, r=float(r))
+        return nbr, (nbr >= 0).sum(1).astype(np.int32)
     nbr = np.empty((y.shape[0], max_num_neighbors), dtype=np.int64)
     cnt = np.empty(y.shape[0], dtype=np.int32)
     lib().orc_radius(_p(x, ctypes.c_float), _p(y, ctypes.c_float), _p(ptr_x, ctypes.c_int64),

@@ -8,8 +8,9 @@ device='cuda', :43-44,83,86, and imports torch_geometric / torch_scatter); what 
 the arithmetic of the cited lines.  Where the reference is random or order-unstable the same
 deterministic choices as the CUDA path are pinned:
   * stable sort for reflectance ranks (C.9);
-  * > max_pts tiles: priority sampling w_i/u_i with a counter-based hash instead of
-    torch.multinomial (C.5), rows by descending priority;
+  * > max_pts tiles: the reference's sampling laws on a counter-based hash instead of torch's generator (C.5):
+    weighted without replacement (torch.multinomial, :118) as Efraimidis-Spirakis keys -log(u)/w, rows in
+    draw order; without reflectance max_pts uniform draws with replacement (torch.randint, :120);
   * consecutive batches of `batch_size` tiles in tile order, nothing dropped (C.4);
   * local_shift = mean accumulated in float64 (the reference's fp32 torch.mean depends on its
     vectorised summation order).
@@ -66,20 +67,41 @@ def _mix32(h: np.ndarray) -> np.ndarray:
     return h
 
 
-def priorities(refl_scaled: np.ndarray, idx: np.ndarray, refl_min: np.float32, seed: int) -> np.ndarray:
-    """w_i / u_i, w = refl - min + 1e-8 (:99,104), u = hash(seed, i) in (0, 1]."""
+def sampling_keys(refl_scaled: np.ndarray, idx: np.ndarray, refl_min: np.float32, seed: int) -> np.ndarray:
+    """Efraimidis-Spirakis keys -log(u_i) / w_i (float64), w = refl - min + 1e-8 (:99,104, FP32),
+    u = hash(seed, i) in (0, 1]: ascending key = draw order of weighted sampling without replacement."""
     with np.errstate(over="ignore"):
         w = (refl_scaled[idx] - refl_min + np.float32(1e-8)).astype(np.float32)
         h = _mix32((idx.astype(np.uint32) * np.uint32(0x9E3779B9) + np.uint32(seed & 0xFFFFFFFF)).astype(np.uint32))
-    u = ((h >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(5.9604644775390625e-08)
-    return (w / u).astype(np.float32)
+    u = ((h >> np.uint32(8)).astype(np.float64) + 1.0) * 5.9604644775390625e-08
+    return np.maximum(-np.log(u) / w.astype(np.float64), 0.0)
 
 
-def tile(feat5: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=16384, seed=SUBSAMPLE_SEED):
+def _mix64(z: np.ndarray) -> np.ndarray:
+    z = z.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        z ^= z >> np.uint64(30)
+        z = z * np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z = z * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    return z
+
+
+def replacement_picks(idx: np.ndarray, voxel_id: int, max_pts: int, seed: int, grid_ordinal: int) -> np.ndarray:
+    """:120: max_pts uniform draws WITH replacement; draw s takes member hash(seed, voxel, s) mod n."""
+    sd = np.uint64((seed & 0xFFFFFFFF) | (grid_ordinal << 32))
+    with np.errstate(over="ignore"):
+        base = _mix64(np.array([sd ^ (np.uint64(voxel_id) * np.uint64(0x9E3779B97F4A7C15))], dtype=np.uint64))[0]
+        h = _mix64(base + np.arange(max_pts, dtype=np.uint64))
+    return idx[(h % np.uint64(len(idx))).astype(np.int64)]
+
+
+def tile(feat5: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=16384, seed=SUBSAMPLE_SEED, weighted=True):
     """grid() + the > max_pts branch of write_voxels (:55-64, 116-120) -> list of index arrays."""
     tiles, grids = [], []
     refl_min = feat5[:, 3].min()
-    for size in gridsize:
+    for gi, size in enumerate(gridsize):
         ids = O.grid(feat5, np.full(5, size, np.float32))
         order = np.argsort(ids, kind="stable")
         sid = ids[order]
@@ -89,9 +111,10 @@ def tile(feat5: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=16384, see
                 continue
             idx = order[a:b]
             if len(idx) > max_pts:
-                pr = priorities(feat5[:, 3], idx, refl_min, seed)
-                sel = np.lexsort((idx, -pr.astype(np.float64)))[:max_pts]     # priority desc, index asc
-                idx = idx[sel]
+                if weighted:
+                    idx = idx[np.argsort(sampling_keys(feat5[:, 3], idx, refl_min, seed), kind="stable")[:max_pts]]
+                else:
+                    idx = replacement_picks(idx, int(sid[a]), max_pts, seed, gi)
             tiles.append(idx.astype(np.int64))
             grids.append(size)
     return tiles, np.asarray(grids, np.float32)
@@ -102,10 +125,13 @@ def preprocess(cloud: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=1638
     cloud = np.ascontiguousarray(cloud, dtype=np.float32)
     n_z = ground_normalize(cloud[:, :3])
     refl = cloud[:, 3]
-    if not np.all(refl == 0):
+    weighted = not np.all(refl == 0)                                   # reflectance_not_zero (:94)
+    if np.isnan(refl).any():
+        raise ValueError("Input reflectance tensor contains NaN values.")          # :20-21
+    if weighted:
         refl = quantile_normalize_reflectance(refl)
     feat5 = np.concatenate([cloud[:, :3], refl[:, None], n_z[:, None]], 1).astype(np.float32)
-    tiles, grids = tile(feat5, gridsize, min_pts, max_pts, seed)
+    tiles, grids = tile(feat5, gridsize, min_pts, max_pts, seed, weighted)
     return feat5, tiles, grids
 
 

@@ -112,21 +112,45 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {   // murmur3 finaliser
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
     return h;
 }
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64 finaliser
+    z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ull; z ^= z >> 27; z *= 0x94d049bb133111ebull; z ^= z >> 31;
+    return z;
+}
 
-__global__ void __launch_bounds__(256) priority_keys_kernel(const float *__restrict__ feat,
+// Efraimidis-Spirakis: ascending -log(u_i)/w_i lists the members in the order sequential weighted sampling
+// WITHOUT replacement draws them (the law of torch.multinomial, src/preprocessing.py:118).  u is a
+// counter-based hash of (seed, global point index) in (0,1]; the key is the raw bit pattern of the
+// non-negative float64, which sorts like the value.
+__global__ void __launch_bounds__(256) sampling_keys_kernel(const float *__restrict__ feat, int ld, int col,
                                                             const int32_t *__restrict__ members,
-                                                            const int32_t *__restrict__ member_tile, int64_t m,
+                                                            const int32_t *__restrict__ global_index, int64_t m,
                                                             float refl_min, uint32_t seed,
                                                             uint64_t *__restrict__ keys) {
     const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const int32_t i = members[r];
-    const float w = __fadd_rn(__fsub_rn(feat[static_cast<int64_t>(i) * 5 + 3], refl_min), 1e-8f);
-    const uint32_t h = mix32(static_cast<uint32_t>(i) * 0x9e3779b9u + seed);
-    const float u = __fmul_rn(static_cast<float>((h >> 8) + 1u), 5.9604644775390625e-08f);   // (0,1], exact
-    const float pr = __fdiv_rn(w, u);
-    keys[r] = (static_cast<uint64_t>(static_cast<uint32_t>(member_tile[r])) << 32) |
-              static_cast<uint64_t>(~sortable(pr));
+    const uint32_t g = static_cast<uint32_t>(global_index ? global_index[i] : i);
+    const float w = __fadd_rn(__fsub_rn(feat[static_cast<int64_t>(i) * ld + col], refl_min), 1e-8f);   // :99,104
+    const uint32_t h = mix32(g * 0x9e3779b9u + seed);
+    const double u = static_cast<double>((h >> 8) + 1u) * 5.9604644775390625e-08;     // (0,1], exact
+    const double key = -log(u) / static_cast<double>(w);
+    keys[r] = static_cast<uint64_t>(__double_as_longlong(key > 0.0 ? key : 0.0));
+}
+
+// torch.randint(0, n_t, (max_pts,)) of src/preprocessing.py:120: max_pts draws WITH replacement per
+// oversized tile; draw s of the tile with voxel id v takes member hash(seed, v, s) mod n_t.
+__global__ void __launch_bounds__(256) replacement_picks_kernel(const int32_t *__restrict__ members,
+                                                                const int64_t *__restrict__ seg,
+                                                                const int64_t *__restrict__ voxel_id, int num_tiles,
+                                                                int max_pts, uint64_t seed,
+                                                                int32_t *__restrict__ picks) {
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= static_cast<int64_t>(num_tiles) * max_pts) return;
+    const int t = static_cast<int>(r / max_pts);
+    const uint64_t s = static_cast<uint64_t>(r - static_cast<int64_t>(t) * max_pts);
+    const int64_t lo = seg[t], n_t = seg[t + 1] - lo;
+    const uint64_t h = mix64(mix64(seed ^ (static_cast<uint64_t>(voxel_id[t]) * 0x9e3779b97f4a7c15ull)) + s);
+    picks[r] = members[lo + static_cast<int64_t>(h % static_cast<uint64_t>(n_t))];
 }
 
 }  // namespace
@@ -135,16 +159,29 @@ __global__ void __launch_bounds__(256) priority_keys_kernel(const float *__restr
 using namespace p2w;
 
 
-extern "C" int p2w_ground_normalize(const float *cloud, int32_t ld, int64_t n, const float *mn_xy, float cell,
-                                    int32_t nbx, int32_t nby, float *cell_min, float *n_z, p2w_stream_t stream) {
-    P2W_REQUIRE(ld >= 3 && nbx >= 1 && nby >= 1 && cell > 0.f, "p2w_ground_normalize: bad arguments");
+extern "C" int p2w_ground_min(const float *cloud, int32_t ld, int64_t n, const float *mn_xy, float cell,
+                              int32_t nbx, int32_t nby, float *cell_min, p2w_stream_t stream) {
+    P2W_REQUIRE(ld >= 3 && nbx >= 1 && nby >= 1 && cell > 0.f, "p2w_ground_min: bad arguments");
     cudaStream_t st = as_stream(stream);
-    if (n == 0) return P2W_OK;
     const int64_t cells = static_cast<int64_t>(nbx + 1) * (nby + 1);
     P2W_LAUNCH(fill_kernel, (unsigned)(((cells) + 255) / 256), 256, 0, st)(cell_min, cells, kPosInf);
-    P2W_LAUNCH(ground_min_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min);
-    P2W_LAUNCH(ground_apply_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min, n_z);
-    return check_launch("p2w_ground_normalize");
+    if (n) P2W_LAUNCH(ground_min_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min);
+    return check_launch("p2w_ground_min");
+}
+
+extern "C" int p2w_ground_apply(const float *cloud, int32_t ld, int64_t n, const float *mn_xy, float cell,
+                                int32_t nbx, int32_t nby, const float *cell_min, float *n_z, p2w_stream_t stream) {
+    P2W_REQUIRE(ld >= 3 && nbx >= 1 && nby >= 1 && cell > 0.f, "p2w_ground_apply: bad arguments");
+    if (n == 0) return P2W_OK;
+    P2W_LAUNCH(ground_apply_kernel, (unsigned)(((n) + 255) / 256), 256, 0, as_stream(stream))(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min, n_z);
+    return check_launch("p2w_ground_apply");
+}
+
+extern "C" int p2w_ground_normalize(const float *cloud, int32_t ld, int64_t n, const float *mn_xy, float cell,
+                                    int32_t nbx, int32_t nby, float *cell_min, float *n_z, p2w_stream_t stream) {
+    if (n == 0) return P2W_OK;
+    const int rc = p2w_ground_min(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min, stream);
+    return rc ? rc : p2w_ground_apply(cloud, ld, n, mn_xy, cell, nbx, nby, cell_min, n_z, stream);
 }
 
 extern "C" int p2w_reflectance_keys(const float *cloud, int32_t ld, int32_t col, int64_t n, uint64_t *keys,
@@ -174,10 +211,21 @@ extern "C" int p2w_assemble5(const float *cloud, int32_t ld, const float *refl, 
     return check_launch("p2w_assemble5");
 }
 
-extern "C" int p2w_priority_keys(const float *feat, const int32_t *members, const int32_t *member_tile, int64_t m,
-                                 float refl_min, uint32_t seed, uint64_t *keys, p2w_stream_t stream) {
-    cudaStream_t st = as_stream(stream);
+extern "C" int p2w_sampling_keys(const float *feat, int32_t ld, int32_t col, const int32_t *members,
+                                 const int32_t *global_index, int64_t m, float refl_min, uint32_t seed, uint64_t *keys,
+                                 p2w_stream_t stream) {
+    P2W_REQUIRE(ld >= 1 && col >= 0 && col < ld, "p2w_sampling_keys: bad column");
     if (m == 0) return P2W_OK;
-    P2W_LAUNCH(priority_keys_kernel, (unsigned)(((m) + 255) / 256), 256, 0, st)(feat, members, member_tile, m, refl_min, seed, keys);
-    return check_launch("p2w_priority_keys");
+    P2W_LAUNCH(sampling_keys_kernel, (unsigned)(((m) + 255) / 256), 256, 0, as_stream(stream))(feat, ld, col, members, global_index, m, refl_min, seed, keys);
+    return check_launch("p2w_sampling_keys");
+}
+
+extern "C" int p2w_replacement_picks(const int32_t *members, const int64_t *seg, const int64_t *voxel_id,
+                                     int32_t num_tiles, int32_t max_pts, uint64_t seed, int32_t *picks,
+                                     p2w_stream_t stream) {
+    P2W_REQUIRE(num_tiles >= 0 && max_pts >= 1, "p2w_replacement_picks: bad sizes");
+    const int64_t total = static_cast<int64_t>(num_tiles) * max_pts;
+    if (total == 0) return P2W_OK;
+    P2W_LAUNCH(replacement_picks_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(stream))(members, seg, voxel_id, num_tiles, max_pts, seed, picks);
+    return check_launch("p2w_replacement_picks");
 }

@@ -1,40 +1,58 @@
-"""One plot on several GPUs (BASELINE.json configs[3]).
+"""One plot sharded over several GPUs (BASELINE.json configs[3]).
 
-The inference path shards with no collective inside it: tiles are independent samples (eval-mode
-BatchNorm uses running statistics) and every reference batch keeps its own voxel-grid origin.  One process
-per GPU (`torch.distributed`, NCCL):
+One process per GPU (`torch.distributed`, NCCL).  Rank r holds a CONTIGUOUS CHUNK of the plot's rows
+(rows o_r .. o_r + n_r of the file, rank order = row order) and nothing is replicated except
+metadata-sized tables and the reflectance column:
 
-1. every rank holds the cloud and runs the (cheap, deterministic) tiling, so all ranks agree on the tiles
-   and on the reference batches without any exchange;
-2. rank r classifies a CONTIGUOUS range of batches balanced by point count (contiguous, so that the
-   super-batches of `predicter.classify_tiles` still merge consecutive batches);
-3. ONE all-gather of the classified rows (xyz fp32, prob fp32, pred uint8: 17 bytes per tile point) --
-   the only exchange of the path, the device-side counterpart of the reference's `np.vstack(output_list)`
-   (src/predicter.py:217);
-4. rank r runs the spatial vote (src/predicter.py:107-142) for its slice of the original points against
-   ALL classified rows, so the result equals the single-GPU one; the per-point (label, pwood) slices are
-   all-gathered (9 bytes per point).
+1. statistics: column min / max, 5 m ground cells (src/preprocessing.py:37-53) -- all-reduce MIN over a few
+   KB; reflectance ranks (:18-30) need the global order: the column is all-gathered (4 B / point) and ranked
+   on every rank, each rank keeps its slice;
+2. tiling (:55-64): every rank sorts ITS rows by 5-D voxel id and lists its occupied voxels with their
+   counts; the lists (16 B / occupied voxel / rank) are all-gathered and merged into the plot's tile table --
+   voxels with >= min_pts members, 2 m list then 4 m list by ascending id, batches of `batch_size`
+   consecutive tiles (the composition one GPU uses, src/predicter.py:177-180), contiguous ranges of
+   whole batches balanced by points per rank;
+3. ONE all-to-all moves every tile member to the owner of its tile (24 B / tile point: x, y, z,
+   reflectance, point index, tile).  Stable on both sides, so a tile's rows arrive in ascending point
+   index -- the order one GPU sees;
+4. each rank classifies its batches (predicter.classify_tiles; no collective, tiles are independent);
+5. spatial vote (src/predicter.py:107-142), sharded by x-slabs with equal query counts: queries (12 B) and
+   classified rows (16 B: x, y, z, prob) go to their slab's rank by all-to-all, rows within `halo` of a
+   slab edge also to the neighbour.  Rows keep the global row order, so distance ties break as on one
+   GPU.  Every query's k-th neighbour distance is checked against its distance to the edge of the halo;
+   if a single query fails the bound the halo grows and the vote is redone, so the result is EXACT;
+6. (label, pwood) return to the rank that holds the row (9 B / point, all-to-all).
 
-Works on NCCL (device tensors) and, for the exchange helpers, on gloo (host tensors, CPU tests).
+The result equals the single-GPU one bit for bit (tests/test_gpu_distributed.py).  Bytes per collective
+are recorded in `ShardedPlot.traffic`.  The host-side plan (tables, routing) is plain torch and runs on
+gloo/CPU tensors too (tests/test_dist_gloo.py); the per-point work goes through `_Kernels` = libp2w.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+from torch import Tensor
 
-from . import ops
+from . import _lib, ops
 from .predicter import classify_tiles, plan_batches
-from .preprocessing import Voxelise
+from .preprocessing import SUBSAMPLE_SEED, TileStore, thin_tiles
 
-__all__ = ["shard_contiguous", "all_gather_rows", "classify_plot"]
+__all__ = ["shard_bounds", "shard_contiguous", "all_gather_rows", "merge_voxel_tables", "slab_bounds", "halo_entries",
+           "Comm", "ShardedPlot", "classify_plot", "GRID_FLAG_SHIFT"]
+
+GRID_FLAG_SHIFT = 58          # voxel ids of the g-th grid size travel as id | g << 58
+DEFAULT_HALO = 0.5            # metres; the k-th neighbour of a TLS point is centimetres away
+HIST_BINS = 4096
 
 
-def shard_contiguous(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, world_size: int, rank: int) -> List[int]:
-    """Batch indices [b0, b1) of `rank`: contiguous ranges whose point counts are as even as a prefix
-    split allows (boundary i goes where the cumulative point count crosses i/world of the total).
-    Deterministic on every rank; every batch belongs to exactly one rank."""
+# ------------------------------------------------------------------------------------------ host-side plans
+def shard_bounds(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, world_size: int) -> List[int]:
+    """[world+1] batch indices: rank r owns batches bounds[r] .. bounds[r+1], contiguous ranges whose point
+    counts are as even as a prefix split allows (boundary i sits where the cumulative point count crosses
+    i/world of the total).  Deterministic, identical on every rank."""
     pts = np.array([ptr[b] - ptr[a] for a, b in batches], dtype=np.int64)
     cum = np.concatenate([[0], np.cumsum(pts)])
     total = int(cum[-1])
@@ -42,55 +60,446 @@ def shard_contiguous(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, world_
     bounds[0] = 0
     for r in range(1, world_size + 1):                       # monotone, in range
         bounds[r] = min(max(bounds[r], bounds[r - 1]), len(batches))
-    return list(range(bounds[rank], bounds[rank + 1]))
+    return bounds
 
 
-def all_gather_rows(rows: torch.Tensor) -> torch.Tensor:
+def shard_contiguous(batches: Sequence[Tuple[int, int]], ptr: np.ndarray, world_size: int, rank: int) -> List[int]:
+    """Batch indices of `rank` (see shard_bounds); every batch belongs to exactly one rank."""
+    b = shard_bounds(batches, ptr, world_size)
+    return list(range(b[rank], b[rank + 1]))
+
+
+def merge_voxel_tables(table: Tensor, min_pts: int):
+    """table int64 [U, 2] = (flagged voxel id, member count), the concatenation of every rank's occupied
+    voxels.  Returns (gid [G] ascending distinct ids, total [G] members over all ranks, kept [G] bool,
+    ordinal [G] = index of the voxel in the plot's tile list (valid where kept)).  Ascending flagged id IS
+    the reference's tile order: first grid size first, then ascending voxel id (src/preprocessing.py:57-63)."""
+    gid, inv = torch.unique(table[:, 0], sorted=True, return_inverse=True)
+    total = torch.zeros(gid.numel(), dtype=torch.int64, device=table.device).index_add_(0, inv, table[:, 1])
+    kept = total >= min_pts
+    ordinal = torch.cumsum(kept.to(torch.int64), 0) - 1
+    return gid, total, kept, ordinal
+
+
+def slab_bounds(hist: np.ndarray, lo: float, hi: float, world_size: int) -> np.ndarray:
+    """[world-1] float32 x-coordinates that cut the plot into slabs of (nearly) equal point counts; `hist` is
+    the plot-wide histogram of x over HIST_BINS equal bins of [lo, hi]."""
+    cum = np.cumsum(hist.astype(np.float64))
+    width = (float(hi) - float(lo)) / len(hist)
+    cuts = []
+    for r in range(1, world_size):
+        b = int(np.searchsorted(cum, cum[-1] * r / world_size, side="left"))
+        cuts.append(np.float32(float(lo) + (b + 1) * width))
+    return np.maximum.accumulate(np.asarray(cuts, dtype=np.float32)) if cuts else np.zeros(0, np.float32)
+
+
+def halo_entries(x: Tensor, bounds: Tensor, halo: float, world_size: int, slots: int):
+    """Destinations of classified rows: row i goes to every slab that [x_i - halo, x_i + halo] touches, slab s
+    covering bounds[s-1] <= x < bounds[s].  Returns (keys int64 [M * slots] row-major: the destination of
+    (row, slot) or `world_size` for an unused slot, span [M] = number of slabs the row touches)."""
+    s0 = torch.searchsorted(bounds, (x - halo).contiguous(), right=True)
+    s1 = torch.searchsorted(bounds, (x + halo).contiguous(), right=True)
+    d = s0[:, None] + torch.arange(slots, device=x.device)[None, :]
+    keys = torch.where(d <= s1[:, None], d, torch.full_like(d, world_size))
+    return keys.reshape(-1).contiguous(), (s1 - s0 + 1)
+
+
+# ------------------------------------------------------------------------------------------ collectives
+class Comm:
+    """The collectives of the sharded path with their byte counts; world size 1 short-circuits."""
+
+    def __init__(self, group=None, rank: Optional[int] = None, world_size: Optional[int] = None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        if world_size is None:
+            on = dist.is_available() and dist.is_initialized()
+            world_size = dist.get_world_size(group) if on else 1
+            rank = dist.get_rank(group) if on else 0
+        self.world, self.rank = world_size, rank
+        self.traffic: Dict[str, int] = {}
+        # gloo moves host memory: device tensors are staged through the host (two ranks sharing one GPU in the tests)
+        self.stage = world_size > 1 and dist.is_initialized() and dist.get_backend(group) == "gloo"
+
+    def _in(self, t: Tensor) -> Tensor:
+        return t.cpu() if (self.stage and t.is_cuda) else t
+
+    def _note(self, what: str, nbytes: int):
+        self.traffic[what] = self.traffic.get(what, 0) + int(nbytes)
+
+    def all_reduce(self, t: Tensor, op: str, what: str) -> Tensor:
+        if self.world > 1:
+            h = self._in(t)
+            self.dist.all_reduce(h, op=getattr(self.dist.ReduceOp, op), group=self.group)
+            if h is not t:
+                t.copy_(h)
+            self._note(what, t.numel() * t.element_size())
+        return t
+
+    def all_gather_equal(self, t: Tensor, what: str) -> Tensor:
+        """[world, *t.shape] of same-shaped tensors."""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        h = self._in(t.contiguous())
+        out = h.new_empty((self.world,) + tuple(t.shape))
+        self.dist.all_gather_into_tensor(out.view(-1), h.view(-1), group=self.group)
+        self._note(what, out.numel() * out.element_size())
+        return out.to(t.device)
+
+    def all_gather_v(self, t: Tensor, counts: Sequence[int], what: str) -> Tensor:
+        """Concatenation over ranks (rank order) of tensors whose first dimensions are `counts` (known on the host)."""
+        if self.world == 1:
+            return t
+        longest = max(counts)
+        if min(counts) == longest:
+            return self.all_gather_equal(t, what).view((-1,) + tuple(t.shape[1:]))
+        padded = t.new_zeros((longest,) + tuple(t.shape[1:]))
+        padded[: t.size(0)] = t
+        out = self.all_gather_equal(padded, what)
+        return torch.cat([out[r, : counts[r]] for r in range(self.world)])
+
+    def all_to_all(self, rows: Tensor, send: Sequence[int], recv: Sequence[int], what: str) -> Tensor:
+        """rows (first dimension split by `send`, destination-major) -> what the other ranks sent here, source-major."""
+        if self.world == 1:
+            return rows
+        h = self._in(rows.contiguous())
+        out = h.new_empty((int(sum(recv)),) + tuple(rows.shape[1:]))
+        self.dist.all_to_all_single(out, h, [int(c) for c in recv], [int(c) for c in send], group=self.group)
+        self._note(what, rows.numel() * rows.element_size())
+        return out.to(rows.device)
+
+
+def all_gather_rows(rows: Tensor) -> Tensor:
     """Concatenation over ranks (rank order) of tensors that differ in their first dimension."""
-    import torch.distributed as dist
-    world = dist.get_world_size()
-    if world == 1:
+    comm = Comm()
+    if comm.world == 1:
         return rows
     count = torch.tensor([rows.size(0)], device=rows.device, dtype=torch.int64)
-    counts = [torch.empty_like(count) for _ in range(world)]
-    dist.all_gather(counts, count)
-    counts = [int(c.item()) for c in counts]
-    longest = max(counts)
-    padded = rows.new_zeros((longest,) + tuple(rows.shape[1:]))
-    padded[: rows.size(0)] = rows
-    bucket = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(bucket, padded)
-    return torch.cat([b[:c] for b, c in zip(bucket, counts)])
+    counts = comm.all_gather_equal(count, "counts").view(-1).tolist()
+    return comm.all_gather_v(rows, counts, "rows")
+
+
+# ------------------------------------------------------------------------------------------ per-point work
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Kernels:
+    """The per-point device work of the sharded path: thin wrappers over libp2w (no CPU path; the gloo tests
+    substitute an oracle-backed stand-in to exercise the exchange plan on CPU tensors)."""
+
+    def colminmax(self, a: Tensor):
+        return ops._colminmax(a)
+
+    def ground_min(self, cloud: Tensor, mn_xy: Tensor, nbx: int, nby: int) -> Tensor:
+        cell_min = torch.empty((nbx + 1) * (nby + 1), device=cloud.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2w_ground_min(cloud.data_ptr(), cloud.stride(0), cloud.size(0), mn_xy.data_ptr(), 5.0, nbx,
+                                             nby, cell_min.data_ptr(), _stream()))
+        return cell_min
+
+    def ground_apply(self, cloud: Tensor, mn_xy: Tensor, nbx: int, nby: int, cell_min: Tensor) -> Tensor:
+        n_z = torch.empty(cloud.size(0), device=cloud.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2w_ground_apply(cloud.data_ptr(), cloud.stride(0), cloud.size(0), mn_xy.data_ptr(), 5.0, nbx,
+                                               nby, cell_min.data_ptr(), n_z.data_ptr(), _stream()))
+        return n_z
+
+    def reflectance_normalize(self, column: Tensor) -> Tensor:
+        """quantile_normalize_reflectance (src/preprocessing.py:18-30) of a whole column."""
+        n = column.numel()
+        L = _lib.lib()
+        keys = torch.empty(n, device=column.device, dtype=torch.int64)
+        _lib.check(L.p2w_reflectance_keys(column.data_ptr(), 1, 0, n, keys.data_ptr(), _stream()))
+        _, order = ops.sort_pairs(keys, 32)
+        v = torch.empty(n, device=column.device, dtype=torch.float32)
+        out = torch.empty(n, device=column.device, dtype=torch.float32)
+        mnmx = torch.empty(2, device=column.device, dtype=torch.float32)
+        _lib.check(L.p2w_reflectance_normalize(order.data_ptr(), n, v.data_ptr(), mnmx.data_ptr(), out.data_ptr(), _stream()))
+        return out
+
+    def assemble5(self, cloud: Tensor, refl: Optional[Tensor], n_z: Tensor) -> Tensor:
+        feat = torch.empty((cloud.size(0), 5), device=cloud.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2w_assemble5(cloud.data_ptr(), cloud.stride(0), None if refl is None else refl.data_ptr(),
+                                            n_z.data_ptr(), cloud.size(0), feat.data_ptr(), _stream()))
+        return feat
+
+    def grid_ids(self, feat: Tensor, size: float, start: Tensor, end: Tensor) -> Tensor:
+        sz = torch.full((feat.size(1),), float(size), device=feat.device, dtype=torch.float32)
+        return ops.grid_cluster(feat, sz, start, end)
+
+    def stable_order(self, keys: Tensor, bits: int):
+        """(sorted keys, int32 positions) of non-negative int64 keys, stable."""
+        return ops.sort_pairs(keys, bits)
+
+    def segments(self, sorted_keys: Tensor, order: Tensor):
+        """(starts int64 [n+1] device (first n_unique+1 entries valid), n_unique int64 [1] device)."""
+        n = sorted_keys.numel()
+        L = _lib.lib()
+        buf = torch.empty(n + 2, device=sorted_keys.device, dtype=torch.int64)
+        ws = torch.empty(max(int(L.p2w_unique_ws_bytes(n)), 8), device=sorted_keys.device, dtype=torch.uint8)
+        _lib.check(L.p2w_unique_last(sorted_keys.data_ptr(), order.data_ptr(), n, None, None, buf[1:].data_ptr(),
+                                     buf.data_ptr(), ws.data_ptr(), _stream()))
+        return buf[1:], buf[:1]
+
+    def thin(self, *args, **kw) -> Tensor:
+        return thin_tiles(*args, **kw)
+
+    def vote(self, rows_xyz: Tensor, prob: Tensor, pred: Tensor, queries: Tensor, k: int, any_wood: float):
+        """(label, pwood, nbr [nq, k] int32) -- ops.spatial_vote with the neighbour table kept for the halo check."""
+        return ops.spatial_vote(rows_xyz, prob, pred, queries, k, any_wood, return_table=True)
+
+
+def _bits(n: int) -> int:
+    return max(1, int(max(n, 1) - 1).bit_length())
+
+
+class ShardedPlot:
+    """Tiling, member exchange and spatial vote of one plot whose rows are chunked over the ranks."""
+
+    def __init__(self, chunk: Tensor, comm: Optional[Comm] = None, min_pts: int = 128, max_pts: int = 16384,
+                 grid_size=(2.0, 4.0), batch_size: int = 8, seed: int = SUBSAMPLE_SEED, kernels: Optional[_Kernels] = None):
+        self.chunk = chunk.contiguous()
+        if self.chunk.dim() != 2 or self.chunk.size(1) < 4 or self.chunk.dtype != torch.float32:
+            raise _lib.P2WError("ShardedPlot: the chunk must be float32 [n, >= 4] (x, y, z, reflectance)")
+        self.comm = comm or Comm()
+        self.min_pts, self.max_pts, self.grid_size, self.batch_size, self.seed = min_pts, max_pts, list(grid_size), batch_size, seed
+        self.K = kernels or _Kernels()
+        self.traffic = self.comm.traffic
+        self.n_z: Optional[Tensor] = None
+
+    # ---------------------------------------------------------------- 1-3: tiling and the member exchange
+    def tile(self) -> TileStore:
+        K, comm, chunk = self.K, self.comm, self.chunk
+        W, r = comm.world, comm.rank
+        dev = chunk.device
+        n = chunk.size(0)
+        # ---- global statistics (src/preprocessing.py:41-42,94; NaN checks :20-21)
+        mn, mx = K.colminmax(chunk[:, :4])
+        mm = comm.all_reduce(torch.cat([mn, -mx]), "MIN", "all-reduce: column min / max")
+        flags = torch.stack([torch.tensor(n, device=dev), torch.isnan(chunk[:, 3]).sum(),
+                             (~torch.isfinite(chunk[:, :3])).any(dim=1).sum()]).to(torch.int64)
+        flags = comm.all_gather_equal(flags, "all-gather: row counts")
+        host = torch.cat([mm.double(), flags.view(-1).double()]).cpu().numpy()                       # sync 1
+        ext = np.stack([host[:4], -host[4:8]]).astype(np.float32)
+        flags_h = host[8:].reshape(W, 3).astype(np.int64)
+        if flags_h[:, 1].sum() > 0:
+            raise ValueError("Input reflectance tensor contains NaN values.")
+        if flags_h[:, 2].sum() > 0:
+            raise _lib.P2WError("ShardedPlot: rows with non-finite coordinates must be removed before sharding")
+        self.counts = flags_h[:, 0].tolist()
+        self.offset = int(sum(self.counts[:r]))
+        self.total = int(sum(self.counts))
+        if self.total >= 2 ** 31:
+            raise _lib.P2WError("ShardedPlot: point indices are 32-bit (fewer than 2^31 rows per plot)")
+        self.ext = ext
+        gmn = mm[:4].contiguous()
+        # histogram of x for the vote's slabs, fetched with the next host copy
+        hist = torch.histc(chunk[:, 0], bins=HIST_BINS, min=float(ext[0, 0]), max=float(ext[1, 0])) if n else \
+            torch.zeros(HIST_BINS, device=dev)
+        hist = comm.all_reduce(hist.to(torch.float64), "SUM", "all-reduce: x histogram")
+        # ---- height above ground (:37-53)
+        lo, hi = ext[0, :2], ext[1, :2] + np.float32(5.0)
+        nb = [max(1, int(math.ceil((float(hi[d]) - float(lo[d])) / 5.0))) for d in range(2)]
+        cell_min = comm.all_reduce(K.ground_min(chunk, gmn, nb[0], nb[1]), "MIN", "all-reduce: ground cells")
+        n_z = K.ground_apply(chunk, gmn, nb[0], nb[1], cell_min)
+        self.n_z = n_z
+        # ---- reflectance (:18-30): ranks are global, so the column is ranked whole on every rank
+        self.weighted = bool(ext[0, 3] != 0 or ext[1, 3] != 0)
+        refl = None
+        if self.weighted:
+            column = comm.all_gather_v(chunk[:, 3].contiguous(), self.counts, "all-gather: reflectance column")
+            refl = K.reflectance_normalize(column)[self.offset: self.offset + n].contiguous()
+        feat = K.assemble5(chunk, refl, n_z)
+        mn5, mx5 = K.colminmax(feat)
+        mm5 = comm.all_reduce(torch.cat([mn5, -mx5]), "MIN", "all-reduce: column min / max")
+        host = torch.cat([mm5.double(), hist]).cpu().numpy()                                          # sync 2
+        ext5 = np.stack([host[:5], -host[5:10]]).astype(np.float32)
+        self.bounds = slab_bounds(host[10:], float(ext[0, 0]), float(ext[1, 0]), W)
+        start5, end5 = mm5[:5].contiguous(), (-mm5[5:]).contiguous()
+        self.refl_min = float(ext5[0, 3])
+        # ---- occupied voxels of this rank per grid size (:55-64)
+        local = []
+        for gi, size in enumerate(self.grid_size):
+            cells = 1
+            for d in range(5):
+                cells *= int(np.float32(ext5[1, d] - ext5[0, d]) / np.float32(size)) + 1
+            bits = max(1, int(cells).bit_length())
+            if bits > GRID_FLAG_SHIFT:
+                raise _lib.P2WError("ShardedPlot: the 5-D voxel grid has more than 2^58 cells")
+            if n:
+                keys, order = K.stable_order(K.grid_ids(feat, size, start5, end5), bits)
+                starts, nuniq = K.segments(keys, order)
+            else:
+                keys = torch.empty(0, device=dev, dtype=torch.int64)
+                order = torch.empty(0, device=dev, dtype=torch.int32)
+                starts, nuniq = torch.zeros(1, device=dev, dtype=torch.int64), torch.zeros(1, device=dev, dtype=torch.int64)
+            local.append((keys, order, starts, nuniq))
+        nu = torch.cat([l[3] for l in local])
+        nu_all = comm.all_gather_equal(nu, "all-gather: voxel list sizes").cpu().numpy()               # sync 3
+        tables = []
+        for gi, (keys, order, starts, _) in enumerate(local):
+            u = int(nu_all[r, gi])
+            uid = keys[starts[:u]] | (gi << GRID_FLAG_SHIFT)
+            tables.append(torch.stack([uid, starts[1: u + 1] - starts[:u]], dim=1))
+        table = comm.all_gather_v(torch.cat(tables), nu_all.sum(axis=1).tolist(), "all-gather: occupied voxels")
+        gid, total, kept, ordinal = merge_voxel_tables(table, self.min_pts)
+        full = total[kept].cpu().numpy()                                                               # sync 4
+        sizes = np.minimum(full, self.max_pts)
+        T = len(sizes)
+        ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        batches = plan_batches(T, self.batch_size)
+        bb = shard_bounds(batches, ptr, W)
+        tb = np.array([batches[b][0] if b < len(batches) else T for b in bb], dtype=np.int64)      # tile bounds per rank
+        self.tile_bounds, self.tile_ptr, self.num_tiles = tb, ptr, T
+        tb_dev = _lib.to_device(tb, dev, np.int64) if dev.type == "cuda" else torch.from_numpy(tb)
+        # ---- members of kept voxels, ascending (tile, point index): already grouped by destination
+        pts, tiles = [], []
+        for gi, (keys, order, starts, _) in enumerate(local):
+            u = int(nu_all[r, gi])
+            if u == 0:
+                continue
+            g = torch.searchsorted(gid, keys[starts[:u]] | (gi << GRID_FLAG_SHIFT))
+            t_u = torch.where(kept[g], ordinal[g], torch.full_like(g, -1))
+            t_p = torch.repeat_interleave(t_u, starts[1: u + 1] - starts[:u], output_size=n)
+            sel = torch.nonzero(t_p >= 0).view(-1)
+            pts.append(order[sel].long())
+            tiles.append(t_p[sel])
+        pts = torch.cat(pts) if pts else torch.empty(0, device=dev, dtype=torch.int64)
+        tiles = torch.cat(tiles) if tiles else torch.empty(0, device=dev, dtype=torch.int64)
+        dest = torch.searchsorted(tb_dev[1:].contiguous(), tiles, right=True)
+        send = torch.bincount(dest, minlength=W)[:W]
+        cm = comm.all_gather_equal(send, "all-gather: exchange sizes").cpu().numpy()                   # sync 5
+        payload = torch.empty((pts.numel(), 6), device=dev, dtype=torch.int32)
+        payload[:, :4] = feat[pts, :4].contiguous().view(torch.int32)
+        payload[:, 4] = (pts + self.offset).to(torch.int32)
+        payload[:, 5] = tiles.to(torch.int32)
+        recv = comm.all_to_all(payload, cm[r].tolist(), cm[:, r].tolist(), "all-to-all: tile members")
+        # ---- this rank's tiles: stable regroup by tile (sources arrive in rank order = ascending point index)
+        t0, t1 = int(tb[r]), int(tb[r + 1])
+        full_loc = full[t0:t1].astype(np.int64)
+        if int(full_loc.sum()) != recv.size(0):
+            raise _lib.P2WError("ShardedPlot: the member exchange delivered a different number of rows than the tile table lists")
+        if recv.size(0):
+            _, perm = K.stable_order((recv[:, 5] - t0).to(torch.int64).contiguous(), _bits(t1 - t0))
+            recv = recv[perm.long()]
+        feat_loc = recv[:, :4].contiguous().view(torch.float32)
+        gidx = recv[:, 4].contiguous()
+        ptr_full = np.concatenate([[0], np.cumsum(full_loc)]).astype(np.int64)
+        sizes_loc = sizes[t0:t1].astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(sizes_loc)]).astype(np.int64)
+        grid_of_tile = np.asarray(self.grid_size, np.float32)[(gid[kept][t0:t1] >> GRID_FLAG_SHIFT).cpu().numpy()] \
+            if t1 > t0 else np.zeros(0, np.float32)
+        big = np.nonzero(full_loc > self.max_pts)[0]
+        if len(big) == 0:
+            members = torch.arange(recv.size(0), device=dev, dtype=torch.int64)
+        else:
+            plan = torch.as_tensor(np.stack([ptr_full[:-1] - off[:-1], sizes_loc]), device=dev)
+            members = torch.arange(int(off[-1]), device=dev) + torch.repeat_interleave(plan[0], plan[1], output_size=int(off[-1]))
+            vox_all = (gid[kept][t0:t1] & ((1 << GRID_FLAG_SHIFT) - 1))
+            gsel = (gid[kept][t0:t1] >> GRID_FLAG_SHIFT).cpu().numpy()
+            for gi in range(len(self.grid_size)):
+                bg = big[gsel[big] == gi]
+                if not len(bg):
+                    continue
+                cat = torch.cat([torch.arange(int(ptr_full[v]), int(ptr_full[v + 1]), device=dev, dtype=torch.int32) for v in bg])
+                picks = K.thin(feat_loc, 3, cat, full_loc[bg], gidx, self.refl_min, self.weighted,
+                               vox_all[torch.as_tensor(bg, device=dev)].contiguous(), self.max_pts, self.seed, gi)
+                picks = picks.view(len(bg), self.max_pts).to(torch.int64)
+                for j, v in enumerate(bg.tolist()):
+                    members[off[v]: off[v + 1]] = picks[j]
+        self.first_row = int(ptr[t0])          # global row index of this rank's first classified row
+        return TileStore(feat=feat_loc, members=members, ptr=off, grid_of_tile=grid_of_tile)
+
+    # ---------------------------------------------------------------- 5-6: the spatial vote by x-slabs
+    def vote(self, xyz: Tensor, prob: Tensor, is_wood: float = 0.5, any_wood: float = 1, halo: float = DEFAULT_HALO):
+        """xyz float32 [M,3], prob float32 [M]: this rank's classified rows in batch order.  Returns
+        (label uint8 [n], pwood float64 [n]) for the rows of this rank's chunk."""
+        K, comm, chunk = self.K, self.comm, self.chunk
+        W, r = comm.world, comm.rank
+        dev = chunk.device
+        n = chunk.size(0)
+        k = 32 if any_wood != 1 else 64                                                               # :137
+        bounds = torch.as_tensor(self.bounds, device=dev)
+        q = chunk[:, :3].contiguous()
+        if W > 1 and n:
+            dq = torch.searchsorted(bounds, q[:, 0].contiguous(), right=True)
+            _, qorder = K.stable_order(dq.contiguous(), _bits(W))
+            qorder = qorder.long()
+            qsend = torch.bincount(dq, minlength=W)[:W]
+        else:
+            qorder = torch.arange(n, device=dev)
+            qsend = torch.zeros(W, device=dev, dtype=torch.int64)
+            qsend[r] = n
+        rows = torch.cat([xyz.reshape(-1, 3), prob.reshape(-1, 1)], dim=1).contiguous()                  # 16 B per classified row
+        width = float(self.ext[1, 0]) - float(self.ext[0, 0])
+        queries = None
+        self.vote_rounds = 0
+        while True:
+            self.vote_rounds += 1
+            everything = W == 1 or halo >= width
+            slots = W if (everything or W <= 3) else 3
+            if everything:
+                keys = torch.arange(W, device=dev).repeat(rows.size(0))
+                span = torch.full((1,), W, device=dev, dtype=torch.int64)
+            else:
+                keys, span = halo_entries(rows[:, 0].contiguous(), bounds, halo, W, slots)
+            _, eorder = K.stable_order(keys, _bits(W + 1)) if keys.numel() else (None, torch.empty(0, device=dev, dtype=torch.int32))
+            rsend = torch.bincount(keys, minlength=W + 1)[:W] if keys.numel() else torch.zeros(W, device=dev, dtype=torch.int64)
+            top = span.max().view(1) if span.numel() else torch.zeros(1, device=dev, dtype=torch.int64)
+            cm = comm.all_gather_equal(torch.cat([qsend, rsend, top]), "all-gather: exchange sizes").cpu().numpy()   # sync
+            if not everything and int(cm[:, -1].max()) > slots:      # a row touches more slabs than slots: widen
+                halo = width
+                continue
+            qm, rm = cm[:, :W], cm[:, W: 2 * W]
+            if queries is None:
+                queries = comm.all_to_all(q[qorder], qm[r].tolist(), qm[:, r].tolist(), "all-to-all: vote queries")
+            entries = eorder[: int(rm[r].sum())].long()
+            got = comm.all_to_all(rows[entries // slots], rm[r].tolist(), rm[:, r].tolist(), "all-to-all: classified rows")
+            rx, rp = got[:, :3].contiguous(), got[:, 3].contiguous()
+            label, pwood, nbr = K.vote(rx, rp, (rp >= is_wood).to(torch.uint8), queries, k, float(any_wood))
+            if everything:
+                break
+            # ---- exactness: the k-th neighbour must be closer than anything this slab was not given
+            lo = float(self.bounds[r - 1]) - (halo - 1e-3) if r > 0 else -math.inf
+            hi = float(self.bounds[r]) + (halo - 1e-3) if r < W - 1 else math.inf
+            need = torch.zeros(2, device=dev, dtype=torch.float64)
+            if queries.size(0):
+                last = nbr[:, k - 1].long()
+                far = (queries - rx[last.clamp(min=0)]).double().pow(2).sum(1).sqrt() if rx.size(0) else \
+                    torch.full((queries.size(0),), math.inf, device=dev, dtype=torch.float64)
+                far = torch.where(last < 0, torch.full_like(far, math.inf), far)
+                qx = queries[:, 0].double()
+                margin = torch.minimum(qx - lo, hi - qx)
+                bad = far >= margin
+                need = torch.stack([bad.sum().double(), torch.where(bad, far - margin, torch.zeros_like(far)).max()])
+            need = comm.all_reduce(need, "MAX", "all-reduce: halo check").cpu().numpy()                # sync
+            if need[0] == 0:
+                break
+            halo = width if not np.isfinite(need[1]) else min(width, 1.25 * (halo + float(need[1])) + 0.01)
+        self.halo = halo
+        back_l = comm.all_to_all(label, qm[:, r].tolist(), qm[r].tolist(), "all-to-all: labels") if W > 1 else label
+        back_p = comm.all_to_all(pwood, qm[:, r].tolist(), qm[r].tolist(), "all-to-all: pwood") if W > 1 else pwood
+        out_l = torch.empty(n, device=dev, dtype=torch.uint8)
+        out_p = torch.empty(n, device=dev, dtype=torch.float64)
+        out_l[qorder] = back_l
+        out_p[qorder] = back_p
+        return out_l, out_p
 
 
 @torch.no_grad()
-def classify_plot(net: torch.nn.Module, cloud: torch.Tensor, min_pts: int = 128, max_pts: int = 16384,
+def classify_plot(net: torch.nn.Module, chunk: Tensor, min_pts: int = 128, max_pts: int = 16384,
                   grid_size=(2.0, 4.0), batch_size: int = 8, is_wood: float = 0.5, any_wood: float = 1,
-                  max_points_per_launch: int = 1 << 21, rank: Optional[int] = None, world_size: Optional[int] = None):
-    """cloud [N, >=4] (x, y, z, reflectance) on this rank's device -> (label uint8 [N], pwood float64 [N])
-    for the WHOLE plot on every rank.  Single process: rank 0 of 1."""
-    import torch.distributed as dist
-    if world_size is None:
-        world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        rank = dist.get_rank() if world_size > 1 else 0
-    store = Voxelise(cloud, minpoints=min_pts, maxpoints=max_pts, gridsize=grid_size).write_voxels()
-    batches = plan_batches(store.num_tiles, batch_size)
-    mine = shard_contiguous(batches, store.ptr, world_size, rank)
-    prob, pred, xyz, _ = classify_tiles(net, store, batch_size, is_wood, batch_ids=mine,
-                                        max_points_per_launch=max_points_per_launch, want_xyz=True)
+                  max_points_per_launch: int = 1 << 21, halo: float = DEFAULT_HALO, comm: Optional[Comm] = None,
+                  return_plot: bool = False):
+    """chunk [n_r, >=4] (x, y, z, reflectance): this rank's contiguous rows of the plot, on its device
+    -> (label uint8 [n_r], pwood float64 [n_r]) for the same rows.  Single process: the whole plot."""
+    plot = ShardedPlot(chunk, comm, min_pts, max_pts, grid_size, batch_size)
+    store = plot.tile()
+    prob, _, xyz, _ = classify_tiles(net, store, batch_size, is_wood, max_points_per_launch=max_points_per_launch,
+                                     want_xyz=True)
+    dev = chunk.device
     if xyz is None or xyz.numel() == 0:
-        xyz = torch.empty((0, 3), device=cloud.device, dtype=torch.float32)
-        prob = torch.empty(0, device=cloud.device, dtype=torch.float32)
-        pred = torch.empty(0, device=cloud.device, dtype=torch.uint8)
-    if world_size > 1:
-        packed = torch.cat([xyz, prob[:, None], pred[:, None].to(torch.float32)], dim=1)      # one exchange
-        packed = all_gather_rows(packed)
-        xyz, prob, pred = packed[:, :3].contiguous(), packed[:, 3].contiguous(), packed[:, 4].to(torch.uint8)
-    n = cloud.size(0)
-    lo, hi = rank * n // world_size, (rank + 1) * n // world_size
-    k = 32 if any_wood != 1 else 64
-    label, pwood = ops.spatial_vote(xyz, prob, pred, cloud[lo:hi, :3].contiguous(), k, float(any_wood))
-    if world_size > 1:
-        label = all_gather_rows(label)
-        pwood = all_gather_rows(pwood)
-    return label, pwood
+        xyz = torch.empty((0, 3), device=dev, dtype=torch.float32)
+        prob = torch.empty(0, device=dev, dtype=torch.float32)
+    label, pwood = plot.vote(xyz, prob, is_wood, any_wood, halo)
+    plot.tile_points = int(store.ptr[-1])
+    return (label, pwood, plot) if return_plot else (label, pwood)

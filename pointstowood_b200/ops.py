@@ -203,8 +203,8 @@ def radius(x: Tensor, y: Tensor, r: float, batch_x: Optional[Tensor] = None, bat
 
 def fps(src: Tensor, batch: Optional[Tensor] = None, ratio: float = 0.5, random_start: bool = True,
         batch_size: Optional[int] = None, ptr: Optional[Tensor] = None) -> Tensor:
-    """torch_cluster.fps.  random_start=True draws the first point per example from torch's
-    generator (as upstream); ties in the arg-max go to the lowest index."""
+    """torch_cluster.fps.  random_start=True (upstream's default) draws the first point of every example
+    from torch's generator as upstream does; ties in the arg-max go to the lowest index."""
     src = _req(src, torch.float32, "src", 2)
     if src.size(1) != 3:
         raise _lib.P2WError("fps: only 3-D coordinates are supported")
@@ -220,14 +220,22 @@ def fps(src: Tensor, batch: Optional[Tensor] = None, ratio: float = 0.5, random_
     m = torch.ceil(deg.to(torch.float32) * torch.tensor(ratio, dtype=torch.float32, device=src.device)).to(torch.int64)
     out_ptr = torch.cat([m.new_zeros(1), m.cumsum(0)])
     total = int(out_ptr[-1].item())
+    perm = None
     if random_start:
-        # rotate every example so that a random member comes first, run, and map back
-        raise _lib.P2WError("fps: random_start=True is not supported; pass random_start=False")
+        # upstream (torch_cluster fps_cuda): start = (rand(B) * deg).long() from torch's generator.  The kernel starts at
+        # the first row of a tile, so the drawn row and the first row trade places on the way in and on the way out.
+        first = ptr[:-1]
+        start = first + (torch.rand(deg.numel(), device=src.device) * deg.to(torch.float32)).to(torch.int64).clamp_(max=(deg - 1).clamp(min=0))
+        ok = deg > 0
+        first, start = first[ok], start[ok]
+        perm = torch.arange(src.size(0), device=src.device)
+        perm[first], perm[start] = start, first.clone()
+        src = src[perm].contiguous()
     out = torch.empty(total, device=src.device, dtype=torch.int64)
     ws = torch.empty(max(src.size(0), 1), device=src.device, dtype=torch.float32)
     _lib.check(_lib.lib().p2w_fps(_dp(src), _dp(ptr), _dp(out_ptr), ptr.numel() - 1, src.size(0), _dp(ws), _dp(out),
                                   _stream()))
-    return out
+    return out if perm is None else perm[out]
 
 
 # --------------------------------------------------------------------------- voxel grid
@@ -602,7 +610,7 @@ def pack_tiles(cloud: Tensor, index: Optional[Tensor], ptr: Tensor):
 
 
 def spatial_vote(classified_xyz: Tensor, prob: Tensor, pred: Tensor, original_xyz: Tensor, k: int = 64,
-                 any_wood: float = 1.0, cell_size: float = 0.05):
+                 any_wood: float = 1.0, cell_size: float = 0.05, return_table: bool = False):
     """PointCloudClassifier.collect_predictions (src/predicter.py:129-142) on the device: the k nearest
     classified points of every original point (one plot-wide cell-list search, FP32 distances) and
     compute_labels (:113-127).  Returns (label uint8 [N], pwood float64 [N])."""
@@ -619,7 +627,7 @@ def spatial_vote(classified_xyz: Tensor, prob: Tensor, pred: Tensor, original_xy
     pwood = torch.empty(org.size(0), device=dev, dtype=torch.float64)
     _lib.check(_lib.lib().p2w_spatial_vote(_dp(nbr), org.size(0), k, _dp(prob), _dp(pred), float(any_wood), _dp(label),
                                            _dp(pwood), _stream()))
-    return label, pwood
+    return (label, pwood, nbr) if return_table else (label, pwood)
 
 
 def writeback(logits: Tensor, pos: Tensor, ptr: Tensor, local_shift: Tensor, is_wood: float = 0.5,

@@ -178,9 +178,20 @@ def SemanticSegmentation(args):
     classifier = PointCloudClassifier(args.is_wood, any_wood=getattr(args, "any_wood", 1))
     pc = getattr(args, "pc", None)
     if pc is not None:
+        finite = getattr(args.tiles, "finite_rows", None)
+        cloud = torch.as_tensor(np.ascontiguousarray(pc.values[:, :3], dtype=np.float32) if hasattr(pc, "columns") else pc)
+        cloud = cloud.to(device)
+        if finite is None:
+            label, pwood = classifier.collect_predictions(rows, cloud)
+        else:             # rows with a non-finite coordinate were never tiled: label 0, pwood NaN
+            lab_f, pw_f = classifier.collect_predictions(rows, cloud[finite])
+            label = torch.zeros(cloud.size(0), device=device, dtype=torch.uint8).index_copy_(0, finite, lab_f)
+            pwood = torch.full((cloud.size(0),), float("nan"), device=device, dtype=torch.float64).index_copy_(0, finite, pw_f)
         if hasattr(pc, "columns"):
-            args.pc = classifier.collect_predictions(rows, pc)
+            pc = pc.drop(columns=[c for c in pc.columns if c in ("label", "pwood", "pleaf")])
+            pc.loc[:, "label"] = label.cpu().numpy().astype(np.float64)
+            pc.loc[:, "pwood"] = pwood.cpu().numpy()
+            args.pc = pc
         else:
-            cloud = torch.as_tensor(pc)
-            args.label, args.pwood = classifier.collect_predictions(rows, cloud.to(device))
+            args.label, args.pwood = label, pwood
     return args

@@ -8,11 +8,15 @@ instead of one `voxels/voxel_k.pt` file per tile (src/preprocessing.py:125) the 
 Pinned choices where the reference is random or order-unstable (the CPU
 oracle oracle/ref_pipeline.py pins the same ones):
 * reflectance ranks come from a STABLE sort (C.9);
-* tiles with more than `maxpoints` members are thinned by priority sampling (w_i / u_i, the
-  weights of :99,104 and a counter-based hash for u) instead of torch.multinomial (C.5); rows
-  are ordered by descending priority;
+* tiles with more than `maxpoints` members are thinned with the reference's sampling LAWS on a
+  counter-based hash of (seed, point index) instead of torch's global generator (C.5): with
+  reflectance, weighted sampling without replacement (torch.multinomial, :118) through
+  Efraimidis-Spirakis keys -log(u)/w, rows in draw order; without reflectance, `maxpoints` uniform
+  draws WITH replacement (torch.randint, :120);
 * tiles are listed 2 m voxels first, then 4 m voxels, each by ascending voxel id (:57-63).
-Inputs must be finite (the reference's NaN row filters, :100,123, are not reproduced).
+Non-finite input: NaN reflectance raises ValueError as the reference does (:20-21); rows with a
+non-finite coordinate join no tile (the reference's per-tile NaN row filter, :123) and get
+n_z = NaN; `Voxelise.finite_rows` lists the rows that were tiled (None: all of them).
 """
 from __future__ import annotations
 
@@ -37,6 +41,7 @@ class TileStore:
     members: Tensor         # [M] int64 device: point ids, tile-major, reference row order inside a tile
     ptr: np.ndarray         # [T+1] int64 host: tile t owns members[ptr[t]:ptr[t+1]]
     grid_of_tile: np.ndarray  # [T] float32 host: the grid size that produced the tile
+    finite_rows: Optional[Tensor] = None   # rows of the input cloud that `feat` holds (None: all; see Voxelise)
 
     @property
     def num_tiles(self) -> int:
@@ -51,6 +56,38 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def thin_tiles(feat: Tensor, refl_col: int, members: Tensor, sizes: np.ndarray, global_index: Optional[Tensor],
+               refl_min: float, weighted: bool, voxel_ids: Tensor, maxpoints: int, seed: int, grid_ordinal: int) -> Tensor:
+    """src/preprocessing.py:116-120 for a group of oversized tiles whose member rows (int32 rows of `feat`,
+    ascending point index inside a tile) are concatenated in `members`, tile t holding sizes[t] of them.
+    Returns int32 [len(sizes) * maxpoints]: the sampled rows of every tile, in draw order.
+    weighted: Efraimidis-Spirakis order of the weights feat[:, refl_col] - refl_min + 1e-8 (torch.multinomial
+    without replacement); else uniform draws with replacement (torch.randint).  `global_index` (int32 per row of
+    feat, or None when rows ARE point indices) and `voxel_ids` (int64 per tile) feed the counter-based hash, so
+    a plot gives the same sample whether it is tiled on one GPU or sharded over several."""
+    dev = feat.device
+    L = _lib.lib()
+    members = members.to(torch.int32).contiguous()
+    nbig = len(sizes)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    picks = torch.empty(nbig * maxpoints, device=dev, dtype=torch.int32)
+    if not weighted:
+        seg = _lib.to_device(offs, dev, np.int64)
+        _lib.check(L.p2w_replacement_picks(members.data_ptr(), seg.data_ptr(), voxel_ids.data_ptr(), nbig, maxpoints,
+                                           (seed & 0xFFFFFFFF) | (grid_ordinal << 32), picks.data_ptr(), _stream()))
+        return picks
+    keys = torch.empty(members.numel(), device=dev, dtype=torch.int64)
+    _lib.check(L.p2w_sampling_keys(feat.data_ptr(), feat.stride(0), refl_col, members.data_ptr(),
+                                   None if global_index is None else global_index.data_ptr(), members.numel(),
+                                   float(refl_min), seed & 0xFFFFFFFF, keys.data_ptr(), _stream()))
+    _, by_key = ops.sort_pairs(keys, 64)                                  # all members by ascending key ...
+    tile_of = torch.repeat_interleave(torch.arange(nbig, device=dev, dtype=torch.int64), _lib.to_device(sizes, dev, np.int64),
+                                      output_size=int(offs[-1]))
+    _, by_tile = ops.sort_pairs(tile_of[by_key.long()].contiguous(), max(1, int(nbig).bit_length()), values=by_key)
+    take = (_lib.to_device(offs[:-1], dev, np.int64)[:, None] + torch.arange(maxpoints, device=dev)[None, :]).reshape(-1)
+    return members[by_tile[take].long()]                                  # ... then stably by tile: (tile, key) order
+
+
 class Voxelise:
     def __init__(self, pos, vxpath=None, minpoints=512, maxpoints=16384, gridsize=(2.0, 4.0), pointspacing=0.01,
                  seed: int = SUBSAMPLE_SEED):
@@ -63,16 +100,21 @@ class Voxelise:
         self.seed = seed
         self.cloud: Optional[Tensor] = None
         self.n_z: Optional[Tensor] = None
+        self.finite_rows: Optional[Tensor] = None
         self.refl: Optional[Tensor] = None
         self._stats = None
 
     # ---- src/preprocessing.py:37-53
     def _cloud_stats(self):
-        """Column min / max of (x, y, z, reflectance): ONE host round trip serves the ground grid and the
-        `reflectance != 0` test of :94 (any non-zero <=> min or max non-zero)."""
+        """Column min / max of (x, y, z, reflectance) and the number of non-finite entries per column: ONE host
+        round trip serves the ground grid, the `reflectance != 0` test of :94 (any non-zero <=> min or max
+        non-zero) and the NaN checks (:20-21, :123)."""
         if self._stats is None:
             mn, mx = ops._colminmax(self.cloud[:, :4])
-            self._stats = (mn, torch.stack([mn, mx]).cpu().numpy())
+            bad = (~torch.isfinite(self.cloud[:, :4])).sum(0).to(torch.float32)
+            nan_refl = torch.isnan(self.cloud[:, 3]).sum().to(torch.float32).view(1)
+            host = torch.cat([mn, mx, bad, nan_refl]).cpu().numpy()
+            self._stats = (mn, host[:8].reshape(2, 4), host[8:12], host[12])
         return self._stats
 
     def gpu_ground(self) -> Tensor:
@@ -133,30 +175,24 @@ class Voxelise:
             else:
                 nvox = int(buf[0].item())
                 seg = buf[1: nvox + 2].cpu().numpy()
-            out.append((float(size), order, seg))
+            out.append((float(size), order, seg, keys))
         return out
 
-    def _thin(self, feat: Tensor, order: Tensor, seg: np.ndarray, big: np.ndarray, refl_min: float) -> List[Tensor]:
-        """Priority-sample `maxpoints` members of every oversized voxel (stand-in for :116-118)."""
-        dev = feat.device
-        L = _lib.lib()
-        pieces = [order[seg[v]: seg[v + 1]] for v in big]
-        members = torch.cat(pieces)
-        rank = torch.repeat_interleave(torch.arange(len(big), device=dev, dtype=torch.int32),
-                                       torch.as_tensor(seg[big + 1] - seg[big], device=dev))
-        keys = torch.empty(members.numel(), device=dev, dtype=torch.int64)
-        _lib.check(L.p2w_priority_keys(feat.data_ptr(), members.data_ptr(), rank.data_ptr(), members.numel(),
-                                       float(refl_min), self.seed & 0xFFFFFFFF, keys.data_ptr(), _stream()))
-        _, pos = ops.sort_pairs(keys, 32 + max(1, int(len(big)).bit_length()))
-        picked = members[pos.long()]
-        offs = np.concatenate([[0], np.cumsum(seg[big + 1] - seg[big])])
-        return [picked[offs[i]: offs[i] + self.maxpoints] for i in range(len(big))]
+    def _thin(self, feat: Tensor, order: Tensor, seg: np.ndarray, big: np.ndarray, refl_min: float, weighted: bool,
+              voxel_ids: Tensor, grid_ordinal: int) -> List[Tensor]:
+        """`maxpoints` members of every oversized voxel (:116-120)."""
+        members = torch.cat([order[seg[v]: seg[v + 1]] for v in big])
+        sizes = (seg[big + 1] - seg[big]).astype(np.int64)
+        picks = thin_tiles(feat, 3, members, sizes, None, refl_min, weighted, voxel_ids, self.maxpoints,
+                           self.seed, grid_ordinal)
+        return list(picks.view(len(big), self.maxpoints))
 
     # ---- src/preprocessing.py:79-127
     def write_voxels(self) -> TileStore:
         pos = self.pos
         if hasattr(pos, "columns"):                                  # pandas DataFrame, as in the reference
             has_nz = "n_z" in pos.columns
+            nz_col = list(pos.columns).index("n_z") if has_nz else -1          # by name, not by position
             arr = np.ascontiguousarray(pos.values, dtype=np.float32)
         else:
             has_nz = False
@@ -168,8 +204,19 @@ class Voxelise:
         if cloud.dim() != 2 or cloud.size(1) < 4:
             raise _lib.P2WError("Voxelise: the cloud needs x, y, z, reflectance columns")
         self._stats = None
-        n_z = cloud[:, -1].contiguous() if has_nz else self.gpu_ground()
+        self.finite_rows = None
+        _, _, bad, nan_refl = self._cloud_stats()
+        if nan_refl > 0:
+            raise ValueError("Input reflectance tensor contains NaN values.")             # :20-21
+        n_all = cloud.size(0)
+        if bad[:3].sum() > 0:          # rows with a non-finite coordinate reach no tile (:123)
+            self.finite_rows = torch.nonzero(torch.isfinite(cloud[:, :3]).all(dim=1)).view(-1)
+            self.cloud = cloud = cloud[self.finite_rows].contiguous()
+            self._stats = None
+        n_z = cloud[:, nz_col].contiguous() if has_nz else self.gpu_ground()
         self.n_z = n_z
+        if self.finite_rows is not None:
+            self.n_z = torch.full((n_all,), float("nan"), device=cloud.device).index_copy_(0, self.finite_rows, n_z)
         ext = self._cloud_stats()[1]
         reflectance_not_zero = bool(ext[0, 3] != 0 or ext[1, 3] != 0)
         refl = self.quantile_normalize_reflectance() if reflectance_not_zero else None
@@ -181,14 +228,12 @@ class Voxelise:
         pieces: List[Tensor] = []
         sizes: List[np.ndarray] = []
         grids: List[np.ndarray] = []
-        for size, order, seg in self.grid(feat):
+        for gi, (size, order, seg, keys) in enumerate(self.grid(feat)):
             counts = np.diff(seg)
             keep = np.nonzero(counts >= self.minpoints)[0]
             if not len(keep):
                 continue
             big = keep[counts[keep] > self.maxpoints]
-            if len(big) and not reflectance_not_zero:
-                raise NotImplementedError("oversized tiles without reflectance (torch.randint path, :120)")
             # all kept voxels of this grid in one gather: member m of tile t sits at order[seg[v_t] + m]
             tile_sizes = np.minimum(counts[keep], self.maxpoints).astype(np.int64)
             off = np.concatenate([[0], np.cumsum(tile_sizes)]).astype(np.int64)
@@ -198,7 +243,9 @@ class Voxelise:
             if len(big):                                                # thinned tiles overwrite their placeholder rows
                 refl_min = float(feat[:, 3].min().item())
                 where = {int(v): i for i, v in enumerate(keep.tolist())}
-                for v, picked in zip(big.tolist(), self._thin(feat, order, seg, big, refl_min)):
+                vox = keys[torch.as_tensor(seg[big], device=dev)].contiguous()
+                for v, picked in zip(big.tolist(), self._thin(feat, order, seg, big, refl_min, reflectance_not_zero,
+                                                             vox, gi)):
                     members[off[where[v]]: off[where[v] + 1]] = picked.to(torch.int64)
             pieces.append(members)
             sizes.append(tile_sizes)
@@ -206,7 +253,7 @@ class Voxelise:
         members = torch.cat(pieces) if pieces else torch.empty(0, dtype=torch.int64, device=dev)
         ptr = np.concatenate([[0], np.cumsum(np.concatenate(sizes))]).astype(np.int64) if sizes else np.zeros(1, np.int64)
         grids = np.concatenate(grids) if grids else np.zeros(0, np.float32)
-        return TileStore(feat=feat, members=members, ptr=ptr, grid_of_tile=grids)
+        return TileStore(feat=feat, members=members, ptr=ptr, grid_of_tile=grids, finite_rows=self.finite_rows)
 
 
 def preprocess(args) -> None:

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["tls_plot", "uniform_tiles", "write_ply"]
+__all__ = ["tls_plot", "tls_plot_blocks", "uniform_tiles", "write_ply"]
 
 
 def _cylinder(rng, n, base, axis, length, radius, noise):
@@ -100,6 +100,30 @@ def tls_plot(n_points: int, seed: int = 1, side: float | None = None):
         o += n_t
     perm = rng.permutation(n_points)          # scanners do not deliver points tree by tree
     return out[perm], lab[perm]
+
+
+def tls_plot_blocks(n_points: int, seed: int = 2, rows: tuple | None = None, block_points: int = 1_000_000):
+    """Large plots (BASELINE.json configs[3]: 100 M points) as a square arrangement of 20 x 20 m blocks of
+    `block_points` points, block b = tls_plot(block_points, seed + b) moved to its place; the rows of a block are
+    contiguous, like the scan positions merged into one TLS file.  Same areal density as tls_plot.
+    `rows = (lo, hi)` returns only rows lo .. hi of the plot (a rank of a sharded run generates its own chunk:
+    only the blocks that overlap the range are built).  Returns (xyzr float32 [hi-lo, 4], label uint8)."""
+    nblk = max(1, -(-n_points // block_points))
+    per_side = int(np.ceil(np.sqrt(nblk)))
+    side = float(np.sqrt(block_points / 2500.0))
+    lo, hi = (0, n_points) if rows is None else rows
+    parts, labs = [], []
+    for b in range(lo // block_points, min(nblk, -(-hi // block_points))):
+        nb = min(block_points, n_points - b * block_points)
+        cloud, lab = tls_plot(nb, seed + b, side=side)
+        cloud[:, 0] += np.float32((b % per_side) * side)
+        cloud[:, 1] += np.float32((b // per_side) * side)
+        a0, a1 = max(lo - b * block_points, 0), min(hi - b * block_points, nb)
+        parts.append(cloud[a0:a1])
+        labs.append(lab[a0:a1])
+    if not parts:
+        return np.zeros((0, 4), np.float32), np.zeros(0, np.uint8)
+    return np.concatenate(parts), np.concatenate(labs)
 
 
 def uniform_tiles(n_tiles: int, n_per_tile: int = 16384, side: float = 2.0, seed: int = 3):

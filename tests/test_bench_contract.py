@@ -14,11 +14,17 @@ def _bench():
 
 
 def test_cpu_arm_on_a_small_plot():
+    """The CPU arm times the whole pipeline on what it is given and reports those points over that time."""
     b = _bench()
-    base, est = b.cpu_arm(60_000, 1, budget_s=1.0)
-    assert base["kind"] == "port" and base["unit"] == "points/s" and base["cores"] >= 1
-    assert base["value"] > 0 and est > 0 and abs(base["value"] - 60_000 / est) < 1e-6 * base["value"]
-    assert "batches" in base["sample"] and "spatial vote" in base["sample"]
+    cloud = b.cpu_sample(60_000, 1, side=2.5)
+    assert 0 < len(cloud) < 60_000 and cloud[:, 0].max() < 2.5 and cloud[:, 1].max() < 2.5
+    secs, n, n_tiles, n_rows = b.cpu_arm(cloud)
+    assert n == len(cloud) and secs > 0 and n_tiles >= 1 and n_rows >= n_tiles * b.CFG["min_pts"]
+    base = b.cpu_baseline_dict(n / secs, 8, n, n_tiles, n_rows, secs)
+    assert base["kind"] == "port" and base["unit"] == "points/s" and base["cores"] == 8
+    assert "nothing extrapolated" in base["sample"] and "KD-tree" in base["sample"]
+    from oracle import oracle as O
+    assert O.SEARCH == "brute"                                  # the checker's search mode is restored
 
 
 def test_both_arms_name_the_same_workload_and_defaults_are_small():

@@ -324,3 +324,26 @@ def test_torch_ops_namespace_matches_upstream_schemas(ops):
     idx = np.sort(rng.integers(0, 50, 1000)).astype(np.int64)
     m, _ = torch.ops.p2w.scatter_max(_dev(src), _dev(idx), 0, None, 50)
     assert np.array_equal(m.cpu().numpy(), O.scatter_max(src, idx, 50))
+
+
+def test_fps_random_start_follows_torchs_generator(ops):
+    """random_start=True (upstream's default): the start row of every example is (rand(B) * deg).long() from
+    torch's CUDA generator; the rest is the deterministic farthest-point iteration from that row."""
+    rng = np.random.default_rng(12)
+    sizes = [700, 1, 333, 2048]
+    src = rng.random((sum(sizes), 3)).astype(np.float32)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    torch.manual_seed(123)
+    out = ops.fps(_dev(src), ratio=0.25, random_start=True, ptr=_dev(ptr)).cpu().numpy()
+    torch.manual_seed(123)
+    deg = torch.tensor(sizes, device="cuda")
+    start = ptr[:-1] + (torch.rand(len(sizes), device="cuda") * deg.float()).long().cpu().numpy()
+    assert (start != ptr[:-1]).any()
+    perm = np.arange(len(src))
+    perm[ptr[:-1]], perm[start] = start, ptr[:-1].copy()
+    want = perm[O.fps(src[perm], ptr, 0.25)]
+    assert np.array_equal(out, want)
+    m = np.ceil(np.asarray(sizes, np.float32) * np.float32(0.25)).astype(np.int64)
+    assert np.array_equal(out[np.concatenate([[0], np.cumsum(m)[:-1]])], start)       # first pick = the drawn row
+    out2 = ops.fps(_dev(src), ratio=0.25, random_start=True, ptr=_dev(ptr)).cpu().numpy()
+    assert not np.array_equal(out, out2)                                                # the generator moved on

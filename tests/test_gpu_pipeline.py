@@ -44,6 +44,65 @@ def test_tiling_is_bit_exact(plot):
         assert np.array_equal(members[store.ptr[t]:store.ptr[t + 1]], ref), f"tile {t} differs"
 
 
+def test_oversized_tiles_without_reflectance_use_draws_with_replacement(plot):
+    """src/preprocessing.py:120: a cloud whose reflectance is all zero thins oversized tiles with max_pts uniform
+    draws WITH replacement (torch.randint) -- same tiles as the oracle, duplicates included."""
+    cloud = plot.copy()
+    cloud[:, 3] = 0
+    kw = dict(minpoints=128, maxpoints=4096, gridsize=(2.0, 4.0))
+    store = _tile_store(cloud, **kw)
+    feat5, tiles, grids = ref_pipeline.preprocess(cloud, kw["gridsize"], kw["minpoints"], kw["maxpoints"])
+    assert np.array_equal(store.feat.cpu().numpy(), feat5)
+    assert store.num_tiles == len(tiles)
+    members = store.members.cpu().numpy()
+    big = 0
+    for t, ref in enumerate(tiles):
+        got = members[store.ptr[t]:store.ptr[t + 1]]
+        assert np.array_equal(got, ref), f"tile {t} differs"
+        if len(ref) == kw["maxpoints"] and len(np.unique(ref)) < len(ref):
+            big += 1
+    assert big >= 1, "no tile was drawn with replacement"
+
+
+def test_weighted_thinning_follows_the_sampling_law(plot):
+    """Efraimidis-Spirakis keys reproduce weighted sampling WITHOUT replacement (torch.multinomial, :118): no
+    duplicates, and members with larger weights are kept more often than members with small ones."""
+    kw = dict(minpoints=128, maxpoints=2048, gridsize=(4.0,))
+    store = _tile_store(plot, **kw)
+    feat = store.feat.cpu().numpy()
+    members = store.members.cpu().numpy()
+    sizes = np.diff(store.ptr)
+    t = int(np.argmax(sizes == kw["maxpoints"]))
+    got = members[store.ptr[t]:store.ptr[t + 1]]
+    assert len(np.unique(got)) == len(got) == kw["maxpoints"]
+    ids = ref_pipeline.O.grid(feat, np.full(5, 4.0, np.float32))
+    voxel = np.nonzero(ids == ids[got[0]])[0]
+    assert len(voxel) > kw["maxpoints"] and np.isin(got, voxel).all()
+    w = feat[voxel, 3] - feat[:, 3].min() + 1e-8
+    kept = np.isin(voxel, got)
+    assert w[kept].mean() > w[~kept].mean()
+
+
+def test_non_finite_input(plot):
+    """NaN reflectance raises like the reference (:20-21); rows with a non-finite coordinate join no tile (:123)."""
+    from pointstowood_b200.preprocessing import Voxelise
+    bad = plot[:30000].copy()
+    bad[17, 3] = np.nan
+    with pytest.raises(ValueError, match="reflectance"):
+        Voxelise(bad, minpoints=128, maxpoints=4096).write_voxels()
+    bad = plot[:30000].copy()
+    bad[[5, 999], 0] = np.nan
+    bad[12345, 2] = np.inf
+    vox = Voxelise(bad, minpoints=128, maxpoints=4096)
+    store = vox.write_voxels()
+    keep = np.setdiff1d(np.arange(len(bad)), [5, 999, 12345])
+    clean = Voxelise(bad[keep], minpoints=128, maxpoints=4096).write_voxels()
+    assert np.array_equal(store.finite_rows.cpu().numpy(), keep)
+    assert np.array_equal(store.members.cpu().numpy(), clean.members.cpu().numpy()) and np.array_equal(store.ptr, clean.ptr)
+    n_z = vox.n_z.cpu().numpy()
+    assert np.isnan(n_z[[5, 999, 12345]]).all() and np.isfinite(n_z[keep]).all()
+
+
 def test_classified_rows_match_oracle(plot):
     from pointstowood_b200 import model as M
     from pointstowood_b200.predicter import classify_tiles
