@@ -65,17 +65,29 @@ int p2w_radius(const float *x, const float *y, const int64_t *ptr_x, const int64
  * the cells of its tile's uniform grid that can hold a result (growing Chebyshev shells, exact
  * stopping bound), i.e. a few hundred candidates instead of the whole tile.  The grid is built per
  * call from the sources (bounding box + occupancy pyramid per tile, one radix sort) in `ws`
- * (p2w_grid_search_ws_bytes(nx, num_tiles) bytes, 16-byte aligned).  Pays off from a few hundred
- * sources per tile; the brute-force sweep remains the better choice for tiny tiles. */
-size_t p2w_grid_search_ws_bytes(int64_t nx, int32_t num_tiles);
+ * (p2w_grid_search_ws_bytes(nx, ny, num_tiles) bytes, 16-byte aligned).  Pays off from a few hundred
+ * sources per tile; the brute-force sweep remains the better choice for tiny tiles.
+ * k >= 5 runs one thread per query over a per-thread heap in shared memory, the queries binned by cell
+ * of the source grid (a counting sort in `ws`, hence ny in the workspace size); k <= 4 keeps the keys in
+ * registers.  p2w_grid_search_pair_evals returns (in *counter_host) the DEVICE address inside `ws` of a
+ * uint64 that the last search on that workspace left behind: the number of distance evaluations it made
+ * (bench.py's pair-evaluations / s figure); read it after synchronising the stream. */
+size_t p2w_grid_search_ws_bytes(int64_t nx, int64_t ny, int32_t num_tiles);
+int p2w_grid_search_pair_evals(const void *ws, int64_t nx, int64_t ny, int32_t num_tiles,
+                               const unsigned long long **counter_host);
 int p2w_knn_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
                  int32_t num_tiles, int64_t nx, int64_t ny, int32_t k,
                  int32_t *nbr, float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream);
 /* Same with the cell size given by the caller (cell_size > 0, enlarged until the cell table fits 4 cells
  * per source, at most 1024 cells per axis): plot-wide searches such as the spatial vote, where one
  * "tile" holds millions of points and the occupancy pyramid's 64 cells per axis are too coarse. */
+#define P2W_KNN_UNORDERED 1   /* flags: entry 0 of a row is the k-th (farthest) neighbour, the others follow in no
+                               * particular order (same SET as the ordered table; -1 in entry 0 when the tile has
+                               * fewer than k sources).  For consumers that do not need the order -- the spatial
+                               * vote -- it saves the final sort.  May be ignored (an ordered table is returned
+                               * with the k-th neighbour LAST) when k <= 4. */
 int p2w_knn_grid_ex(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
-                    int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, float cell_size,
+                    int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, float cell_size, int32_t flags,
                     int32_t *nbr, float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream);
 int p2w_radius_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
                     int32_t num_tiles, int64_t nx, int64_t ny, double r, int32_t max_nbr,

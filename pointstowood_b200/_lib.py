@@ -21,9 +21,10 @@ SIGNATURES = {
     "p2w_launch_count": (ctypes.c_longlong, []),
     "p2w_knn": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_int32, _P, _P, _P]),
     "p2w_radius": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_double, c_int32, _P, _P, _P]),
-    "p2w_grid_search_ws_bytes": (c_size_t, [c_int64, c_int32]),
+    "p2w_grid_search_ws_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "p2w_grid_search_pair_evals": (c_int32, [_P, c_int64, c_int64, c_int32, _P]),
     "p2w_knn_grid": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_int32, _P, _P, _P, c_size_t, _P]),
-    "p2w_knn_grid_ex": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_int32, c_float, _P, _P, _P, c_size_t, _P]),
+    "p2w_knn_grid_ex": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_int32, c_float, c_int32, _P, _P, _P, c_size_t, _P]),
     "p2w_spatial_vote": (c_int32, [_P, c_int64, c_int32, _P, _P, c_float, _P, _P, _P]),
     "p2w_radius_grid": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_double, c_int32, _P, _P, _P, c_size_t,
                                   _P]),

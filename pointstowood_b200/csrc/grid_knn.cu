@@ -26,6 +26,8 @@
 // segments so that every step evaluates 32 candidates, and the survivors of the threshold test
 // enter the warp-distributed top-k -- one by one, or through a bitonic sort + merge of the whole
 // step when many survive.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace p2w {
@@ -847,19 +849,309 @@ __global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__r
     }
 }
 
+// ---- k >= 5: one THREAD per query, queries binned by cell, per-thread max-heap in shared memory.
+// The warp-per-query kernel above spends its issue slots on selection: every candidate that beats the
+// current k-th key costs a ballot / shuffle insertion that occupies all 32 lanes.  Here a thread owns a
+// query and a binary max-heap of its k best keys (column `threadIdx.x` of a [k][HT + 1] shared array:
+// conflict-free for the heap walk, and conflict-free again, transposed, when a warp writes the finished
+// rows out coalesced).  A candidate costs its distance (3 FSUB, 1 FMUL, 2 FFMA) and one 64-bit compare with
+// the heap root; survivors of a 32-candidate batch are remembered in a bit mask and inserted afterwards,
+// so the warp walks the heap max-over-lanes(survivors) times per batch instead of once per surviving
+// (lane, candidate) pair.  Queries are processed in cell order (a counting sort of the queries by the cell
+// of the source grid they fall in, built with the sources' own histogram / scan), so the lanes of a warp
+// read the same few rows of the cell list: L1 broadcasts instead of 32 scattered sectors.
+// Same candidate sets, same keys, same stopping bound as above => bit-identical results.
+constexpr int HT = 128;            // threads per CTA of the heap kernel
+
+__global__ void __launch_bounds__(256) query_count_kernel(const float *__restrict__ y,
+                                                          const int64_t *__restrict__ ptr_y, int T, int64_t ny,
+                                                          const GridTile *__restrict__ grid,
+                                                          uint32_t *__restrict__ qslot, uint32_t *__restrict__ qcount) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= ny) return;
+    const int b = find_tile(ptr_y, T, i);
+    const GridTile g = grid[b];
+    const int cx = axis_cell(y[i * 3 + 0], g.ox, g.inv_h, g.nx);
+    const int cy = axis_cell(y[i * 3 + 1], g.oy, g.inv_h, g.ny);
+    const int cz = axis_cell(y[i * 3 + 2], g.oz, g.inv_h, g.nz);
+    const int64_t c = g.base + cx + g.nx * (cy + g.ny * cz);
+    qslot[i] = static_cast<uint32_t>(c);
+    atomicAdd(&qcount[c], 1u);
+}
+
+// qstart = exclusive scan continued from the sources' table, i.e. offset by the number of sources
+__global__ void __launch_bounds__(256) query_scatter_kernel(int64_t ny, const uint32_t *__restrict__ qslot,
+                                                            const uint32_t *__restrict__ qstart, uint32_t nx_total,
+                                                            uint32_t *__restrict__ qfill, uint32_t *__restrict__ qorder) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= ny) return;
+    const uint32_t c = qslot[i];
+    qorder[qstart[c] - nx_total + atomicAdd(&qfill[c], 1u)] = static_cast<uint32_t>(i);
+}
+
+// sift `nk` down from slot i of the max-heap h[0..n) (stride st)
+__device__ __forceinline__ void heap_sift(key_t *__restrict__ h, int st, int n, int i, key_t nk) {
+    for (;;) {
+        int c = 2 * i + 1;
+        if (c >= n) break;
+        key_t kc = h[c * st];
+        if (c + 1 < n) {
+            const key_t kr = h[(c + 1) * st];
+            if (kr > kc) { kc = kr; c++; }
+        }
+        if (!(kc > nk)) break;
+        h[i * st] = kc;
+        i = c;
+    }
+    h[i * st] = nk;
+}
+
+// Selection state of one query.  While fewer than k candidates have been seen they are appended unsorted
+// (`fill` of them so far; the other slots hold sentinels, the largest key); the k-th one triggers Floyd's
+// heap construction and from then on `root` is the k-th best key and a better candidate replaces the root.
+struct HeapState {
+    key_t root;
+    int fill;
+};
+
+__device__ __forceinline__ void heap_offer(key_t *__restrict__ h, int st, int k, HeapState &hs, key_t ck) {
+    if (hs.fill < k) {
+        h[hs.fill * st] = ck;
+        if (++hs.fill == k) {
+            for (int i = k / 2 - 1; i >= 0; i--) heap_sift(h, st, k, i, h[i * st]);
+            hs.root = h[0];
+        }
+    } else if (ck < hs.root) {
+        heap_sift(h, st, k, 0, ck);
+        hs.root = h[0];
+    }
+}
+
+constexpr int HB = 8;      // candidates whose loads are in flight together
+
+template <bool RADIUS>
+__device__ __forceinline__ void heap_scan(const float4 *__restrict__ spts, uint32_t a, uint32_t e, float qx, float qy,
+                                          float qz, float r2, key_t *__restrict__ h, int st, int k, HeapState &hs,
+                                          int &hits, unsigned &evals) {
+    for (uint32_t base = a; base < e; base += 32) {
+        const uint32_t n = min(e - base, 32u);
+        unsigned mask = 0;
+        for (uint32_t j0 = 0; j0 < n; j0 += HB) {
+            float4 c[HB];
+#pragma unroll
+            for (int u = 0; u < HB; u++) c[u] = __ldg(spts + base + min(j0 + u, n - 1));
+#pragma unroll
+            for (int u = 0; u < HB; u++) {
+                const float dx = __fsub_rn(c[u].x, qx), dy = __fsub_rn(c[u].y, qy), dz = __fsub_rn(c[u].z, qz);
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                bool ok = j0 + u < n;
+                key_t ck;
+                if (RADIUS) {
+                    ok = ok && d < r2;
+                    hits += ok ? 1 : 0;
+                    ck = __float_as_uint(c[u].w);
+                } else {
+                    ok = ok && d < 1e10f;
+                    ck = (static_cast<key_t>(__float_as_uint(d)) << 32) | __float_as_uint(c[u].w);
+                }
+                if (ok && ck < hs.root) mask |= 1u << (j0 + u);
+            }
+        }
+        evals += n;
+        while (mask) {
+            const uint32_t j = static_cast<uint32_t>(__ffs(mask) - 1);
+            mask &= mask - 1;
+            const float4 c = __ldg(spts + base + j);
+            key_t ck;
+            if (RADIUS) {
+                ck = __float_as_uint(c.w);
+            } else {
+                const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                ck = (static_cast<key_t>(__float_as_uint(d)) << 32) | __float_as_uint(c.w);
+            }
+            heap_offer(h, st, k, hs, ck);
+        }
+    }
+}
+
+// ORDERED: rows ascending by key (the contract of p2w_knn / torch_cluster).  Otherwise the finished heap is
+// written as it stands: entry 0 is the k-th (farthest) neighbour, the rest in no particular order (what the
+// spatial vote needs: it sorts the probabilities itself) -- this skips k root extractions per query.
+template <bool RADIUS, bool ORDERED>
+__global__ void __launch_bounds__(HT) grid_query_heap_kernel(const float4 *__restrict__ spts,
+                                                             const uint32_t *__restrict__ cell_start,
+                                                             const GridTile *__restrict__ grid,
+                                                             const float *__restrict__ y,
+                                                             const int64_t *__restrict__ ptr_x,
+                                                             const int64_t *__restrict__ ptr_y, int T, int64_t ny,
+                                                             int k, float r2, const uint32_t *__restrict__ qorder,
+                                                             int32_t *__restrict__ nbr, float *__restrict__ d2out,
+                                                             int32_t *__restrict__ cnt_out,
+                                                             unsigned long long *__restrict__ pair_evals) {
+    extern __shared__ __align__(16) unsigned char heap_raw[];
+    key_t *heap_s = reinterpret_cast<key_t *>(heap_raw);
+    constexpr int ST = HT + 1;
+    key_t *h = heap_s + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * HT + threadIdx.x;
+    const bool active = p < ny;
+    const int64_t q = active ? static_cast<int64_t>(qorder[p]) : 0;
+    for (int e = 0; e < k; e++) h[e * ST] = key_sentinel();
+    HeapState hs;
+    hs.root = key_sentinel();
+    hs.fill = 0;
+    int hits = 0;
+    unsigned evals = 0;
+    if (active) {
+        const int b = find_tile(ptr_y, T, q);
+        const int64_t s0 = ptr_x[b], s1 = ptr_x[b + 1];
+        const float qx = y[q * 3 + 0], qy = y[q * 3 + 1], qz = y[q * 3 + 2];
+        if (s1 > s0) {
+            const GridTile g = grid[b];
+            const int cx = axis_cell(qx, g.ox, g.inv_h, g.nx);
+            const int cy = axis_cell(qy, g.oy, g.inv_h, g.ny);
+            const int cz = axis_cell(qz, g.oz, g.inv_h, g.nz);
+            const int nmax = max(g.nx, max(g.ny, g.nz));
+            const float margin = 1e-5f * g.h * static_cast<float>(nmax) +
+                                 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz));
+            const float fx = g.ox + static_cast<float>(cx) * g.h, fy = g.oy + static_cast<float>(cy) * g.h,
+                        fz = g.oz + static_cast<float>(cz) * g.h;
+            const float k1 = 1.f - 1e-4f;
+            const float lox = fmaxf((qx - fx) * k1 - margin, 0.f), hix = fmaxf((fx + g.h - qx) * k1 - margin, 0.f);
+            const float loy = fmaxf((qy - fy) * k1 - margin, 0.f), hiy = fmaxf((fy + g.h - qy) * k1 - margin, 0.f);
+            const float loz = fmaxf((qz - fz) * k1 - margin, 0.f), hiz = fmaxf((fz + g.h - qz) * k1 - margin, 0.f);
+            const float hs1 = g.h * k1;
+            // ring 1: 9 rows of up to 3 cells (contiguous in the cell table), nearest rows first.  The four table
+            // entries of every row are fetched up front (independent loads); a row, or one of its outer cells,
+            // whose lower bound already exceeds the k-th distance is skipped.
+            {
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+                uint32_t r0[9], r1[9], r2c[9], r3[9];        // starts of cells x0, cx, cx + 1 and the end of x1
+#pragma unroll
+                for (int s = 0; s < 9; s++) {
+                    const int ddy = static_cast<int>((0x22161u >> (2 * s)) & 3u) - 1;   // 0,-1,1,0,0,-1,1,-1,1
+                    const int ddz = static_cast<int>((0x28215u >> (2 * s)) & 3u) - 1;   // 0,0,0,-1,1,-1,-1,1,1
+                    const int yy = cy + ddy, zz = cz + ddz;
+                    r0[s] = r1[s] = r2c[s] = r3[s] = 0u;
+                    if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+                        const uint32_t *row = cell_start + (g.base + g.nx * (yy + g.ny * zz));
+                        r0[s] = __ldg(row + x0);
+                        r1[s] = __ldg(row + cx);
+                        r2c[s] = __ldg(row + cx + 1);
+                        r3[s] = __ldg(row + x1 + 1);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 9; s++) {
+                    const int ddy = static_cast<int>((0x22161u >> (2 * s)) & 3u) - 1;
+                    const int ddz = static_cast<int>((0x28215u >> (2 * s)) & 3u) - 1;
+                    const float sy = ddy < 0 ? loy : (ddy > 0 ? hiy : 0.f);
+                    const float sz = ddz < 0 ? loz : (ddz > 0 ? hiz : 0.f);
+                    const float rb2 = sy * sy + sz * sz;
+                    const float lim = RADIUS ? r2 : __uint_as_float(static_cast<unsigned>(hs.root >> 32));
+                    if (RADIUS ? !(rb2 < lim) : rb2 > lim) continue;
+                    const bool skip_lo = RADIUS ? !(rb2 + lox * lox < lim) : rb2 + lox * lox > lim;
+                    const bool skip_hi = RADIUS ? !(rb2 + hix * hix < lim) : rb2 + hix * hix > lim;
+                    heap_scan<RADIUS>(spts, skip_lo ? r1[s] : r0[s], skip_hi ? r2c[s] : r3[s], qx, qy, qz, r2, h, ST, k, hs,
+                                      hits, evals);
+                }
+            }
+            for (int r = 1;; r++) {
+                if (r > 1) {                               // shells beyond the first ring, row by row with the same bounds
+                    for (int dz = -r; dz <= r; dz++) {
+                        const int zz = cz + dz;
+                        if (zz < 0 || zz >= g.nz) continue;
+                        const float sz = dz < 0 ? loz + static_cast<float>(-dz - 1) * hs1
+                                                : (dz > 0 ? hiz + static_cast<float>(dz - 1) * hs1 : 0.f);
+                        for (int dy = -r; dy <= r; dy++) {
+                            const int yy = cy + dy;
+                            if (yy < 0 || yy >= g.ny) continue;
+                            const float sy = dy < 0 ? loy + static_cast<float>(-dy - 1) * hs1
+                                                    : (dy > 0 ? hiy + static_cast<float>(dy - 1) * hs1 : 0.f);
+                            const float rb2 = sy * sy + sz * sz;
+                            const float lim = RADIUS ? r2 : __uint_as_float(static_cast<unsigned>(hs.root >> 32));
+                            if (RADIUS ? !(rb2 < lim) : rb2 > lim) continue;
+                            const bool rim = (dz == -r || dz == r || dy == -r || dy == r);
+                            const int64_t row = g.base + g.nx * (yy + g.ny * zz);
+                            if (rim) {
+                                const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+                                if (x0 <= x1)
+                                    heap_scan<RADIUS>(spts, __ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1),
+                                                      qx, qy, qz, r2, h, ST, k, hs, hits, evals);
+                            } else {
+                                const float sxl = lox + static_cast<float>(r - 1) * hs1, sxh = hix + static_cast<float>(r - 1) * hs1;
+                                if (cx - r >= 0 && (RADIUS ? rb2 + sxl * sxl < lim : rb2 + sxl * sxl <= lim))
+                                    heap_scan<RADIUS>(spts, __ldg(cell_start + row + cx - r), __ldg(cell_start + row + cx - r + 1),
+                                                      qx, qy, qz, r2, h, ST, k, hs, hits, evals);
+                                if (cx + r < g.nx && (RADIUS ? rb2 + sxh * sxh < lim : rb2 + sxh * sxh <= lim))
+                                    heap_scan<RADIUS>(spts, __ldg(cell_start + row + cx + r), __ldg(cell_start + row + cx + r + 1),
+                                                      qx, qy, qz, r2, h, ST, k, hs, hits, evals);
+                            }
+                        }
+                    }
+                }
+                const int bx0 = cx - r, bx1 = cx + r, by0 = cy - r, by1 = cy + r, bz0 = cz - r, bz1 = cz + r;
+                if (bx0 <= 0 && bx1 >= g.nx - 1 && by0 <= 0 && by1 >= g.ny - 1 && bz0 <= 0 && bz1 >= g.nz - 1) break;
+                float bd = 3.0e38f;
+                if (bx0 > 0) bd = fminf(bd, qx - (g.ox + static_cast<float>(bx0) * g.h));
+                if (bx1 < g.nx - 1) bd = fminf(bd, (g.ox + static_cast<float>(bx1 + 1) * g.h) - qx);
+                if (by0 > 0) bd = fminf(bd, qy - (g.oy + static_cast<float>(by0) * g.h));
+                if (by1 < g.ny - 1) bd = fminf(bd, (g.oy + static_cast<float>(by1 + 1) * g.h) - qy);
+                if (bz0 > 0) bd = fminf(bd, qz - (g.oz + static_cast<float>(bz0) * g.h));
+                if (bz1 < g.nz - 1) bd = fminf(bd, (g.oz + static_cast<float>(bz1 + 1) * g.h) - qz);
+                const float bs = bd * (1.f - 1e-4f) - margin;
+                const float lim = RADIUS ? r2 : __uint_as_float(static_cast<unsigned>(hs.root >> 32));
+                if (bs > 0.f && lim < bs * bs) break;
+            }
+        }
+        // fewer than k candidates in reach: the unsorted prefix (+ sentinels) still has to become a heap
+        if (hs.fill < k)
+            for (int i = k / 2 - 1; i >= 0; i--) heap_sift(h, ST, k, i, h[i * ST]);
+        if (ORDERED) {
+            // heap sort in place: h[0..k) ascending (the unfilled entries are sentinels, the largest keys)
+            for (int n = k - 1; n >= 1; n--) {
+                const key_t last = h[n * ST];
+                h[n * ST] = h[0];
+                heap_sift(h, ST, n, 0, last);
+            }
+        }
+    }
+    // a warp writes its 32 rows coalesced: lane e reads entry e of query t's column (transposed, conflict-free)
+    __syncwarp();
+    const int wbase = threadIdx.x & ~31;
+    for (int t = 0; t < 32; t++) {
+        const long long qq = __shfl_sync(FULL, active ? static_cast<long long>(q) : -1ll, t);
+        if (qq < 0) continue;
+        for (int e = lane; e < k; e += 32) {
+            const key_t v = heap_s[e * ST + wbase + t];
+            nbr[qq * k + e] = static_cast<int32_t>(static_cast<uint32_t>(v));
+            if (!RADIUS && d2out) d2out[qq * k + e] = __uint_as_float(static_cast<unsigned>(v >> 32));
+        }
+    }
+    if (RADIUS && active) cnt_out[q] = hits < k ? hits : k;
+    if (pair_evals) {
+        unsigned long long ev = evals;
+        for (int o = 16; o; o >>= 1) ev += __shfl_xor_sync(FULL, ev, o);
+        if (lane == 0 && ev) atomicAdd(pair_evals, ev);
+    }
+}
+
 struct GridWs {
     GridTile *grid;
-    uint32_t *slot, *cell_start, *fill, *bsum;
+    uint32_t *slot, *cell_start, *fill, *bsum, *qslot, *qorder;
     float *box;
+    unsigned long long *pair_evals;
     float4 *spts;
-    int64_t table;     // entries of cell_start / fill (bound on the total number of cells, + 1)
+    int64_t table;     // entries of one cell table (bound on the total number of cells, + 1); cell_start / fill hold
+                       // TWO tables back to back: sources, then queries (scanned as one array)
     size_t total;
 };
 
 inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 inline int64_t scan32_blocks(int64_t n) { return (n + SC_TILE - 1) / SC_TILE; }
 
-inline GridWs grid_ws(void *base, int64_t nx, int T) {
+inline GridWs grid_ws(void *base, int64_t nx, int64_t ny, int T) {
     GridWs w;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -870,27 +1162,40 @@ inline GridWs grid_ws(void *base, int64_t nx, int T) {
     w.table = 4 * nx + 64 * static_cast<int64_t>(T) + 1;       // sum over tiles of max(4 n_b, 64), + the end slot
     w.grid = static_cast<GridTile *>(take(sizeof(GridTile) * static_cast<size_t>(T)));
     w.box = static_cast<float *>(take(64));
+    w.pair_evals = static_cast<unsigned long long *>(take(64));
     w.slot = static_cast<uint32_t *>(take(4 * static_cast<size_t>(nx)));
+    w.qslot = static_cast<uint32_t *>(take(4 * static_cast<size_t>(ny)));
+    w.qorder = static_cast<uint32_t *>(take(4 * static_cast<size_t>(ny)));
     w.spts = static_cast<float4 *>(take(16 * static_cast<size_t>(nx)));
-    w.cell_start = static_cast<uint32_t *>(take(4 * static_cast<size_t>(w.table)));
-    w.fill = static_cast<uint32_t *>(take(4 * static_cast<size_t>(w.table)));
-    w.bsum = static_cast<uint32_t *>(take(4 * static_cast<size_t>(scan32_blocks(w.table) + 2)));
+    w.cell_start = static_cast<uint32_t *>(take(4 * static_cast<size_t>(2 * w.table)));
+    w.fill = static_cast<uint32_t *>(take(4 * static_cast<size_t>(2 * w.table)));
+    w.bsum = static_cast<uint32_t *>(take(4 * static_cast<size_t>(scan32_blocks(2 * w.table) + 2)));
     w.total = off;
     return w;
 }
 
+// P2W_KNN_WARP=1 keeps the warp-per-query kernel for k >= 5 (A/B measurements; results are identical)
+inline bool use_warp_kernel() {
+    static const bool v = [] { const char *e = getenv("P2W_KNN_WARP"); return e && e[0] == '1'; }();
+    return v;
+}
+
 int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y, int T, int64_t nx,
-                int64_t ny, int k, float r2, bool radius, float cell_hint, int32_t *nbr, float *d2, int32_t *cnt,
-                void *ws, size_t ws_bytes, cudaStream_t st, const char *what) {
+                int64_t ny, int k, float r2, bool radius, float cell_hint, bool unordered, int32_t *nbr, float *d2,
+                int32_t *cnt, void *ws, size_t ws_bytes, cudaStream_t st, const char *what) {
     P2W_REQUIRE(T >= 1 && nx >= 0 && ny >= 0, "%s: bad sizes", what);
-    P2W_REQUIRE(nx < (int64_t(1) << 29), "%s: nx must stay below 2^29 sources per call", what);
+    P2W_REQUIRE(nx < (int64_t(1) << 29) && ny < (int64_t(1) << 31) && nx + ny < (int64_t(1) << 32),
+                "%s: nx must stay below 2^29 sources and nx + ny below 2^32 per call", what);
     P2W_REQUIRE(T < (1 << 24), "%s: too many tiles", what);
     if (ny == 0) return P2W_OK;
-    const GridWs w = grid_ws(ws, nx, T);
+    const GridWs w = grid_ws(ws, nx, ny, T);
     P2W_REQUIRE(ws != nullptr && ws_bytes >= w.total && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0,
                 "%s: workspace too small or misaligned (%zu bytes needed)", what, w.total);
     const float tau = fmaxf(1.f, 0.45f * static_cast<float>(k));
     P2W_REQUIRE(cell_hint >= 0.f && cell_hint < 1e30f, "%s: bad cell size", what);
+    const bool small = !radius && k <= 4;
+    const bool heap = !small && !use_warp_kernel();
+    P2W_REQUIRE(!unordered || (heap && !radius), "%s: the unordered table needs the heap kernel (kNN, k >= 5)", what);
     const float *pre_box = nullptr;
     if (T == 1 && cell_hint > 0.f && nx > 65536) {          // one plot-wide tile: the box is everybody's job
         P2W_LAUNCH(box_init_kernel, 1, 32, 0, st)(w.box);
@@ -899,23 +1204,46 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
     }
     P2W_LAUNCH(grid_plan_kernel, T, 512, 0, st)(x, ptr_x, tau, cell_hint, pre_box, w.grid);
     P2W_LAUNCH(grid_base_kernel, 1, 1024, 0, st)(w.grid, T);
-    // cell_start and fill are adjacent: one memset clears both
-    cudaMemsetAsync(w.cell_start, 0, reinterpret_cast<unsigned char *>(w.fill + w.table) -
+    // cell_start and fill are adjacent: one memset clears both (each: source table, then query table)
+    cudaMemsetAsync(w.cell_start, 0, reinterpret_cast<unsigned char *>(w.fill + 2 * w.table) -
                                          reinterpret_cast<unsigned char *>(w.cell_start), st);
+    cudaMemsetAsync(w.pair_evals, 0, sizeof(unsigned long long), st);
     if (nx > 0) {
         const unsigned blocks = static_cast<unsigned>((nx + 255) / 256);
         P2W_LAUNCH(grid_count_kernel, blocks, 256, 0, st)(x, ptr_x, T, nx, w.grid, w.slot, w.cell_start);
-        const int64_t nb = scan32_blocks(w.table);
-        P2W_LAUNCH(scan32_partial_kernel, (unsigned)nb, SC_T, 0, st)(w.cell_start, w.table, w.bsum);
+        if (heap)
+            P2W_LAUNCH(query_count_kernel, (unsigned)((ny + 255) / 256), 256, 0, st)(y, ptr_y, T, ny, w.grid, w.qslot,
+                                                                                     w.cell_start + w.table);
+        const int64_t entries = heap ? 2 * w.table : w.table;
+        const int64_t nb = scan32_blocks(entries);
+        P2W_LAUNCH(scan32_partial_kernel, (unsigned)nb, SC_T, 0, st)(w.cell_start, entries, w.bsum);
         P2W_LAUNCH(scan32_single_kernel, 1, 1024, 0, st)(w.bsum, nb);
-        P2W_LAUNCH(scan32_apply_kernel, (unsigned)nb, SC_T, 0, st)(w.cell_start, w.table, w.bsum, w.cell_start);
+        P2W_LAUNCH(scan32_apply_kernel, (unsigned)nb, SC_T, 0, st)(w.cell_start, entries, w.bsum, w.cell_start);
         P2W_LAUNCH(grid_scatter_kernel, blocks, 256, 0, st)(x, nx, w.slot, w.cell_start, w.fill, w.spts);
+        if (heap)
+            P2W_LAUNCH(query_scatter_kernel, (unsigned)((ny + 255) / 256), 256, 0, st)(
+                ny, w.qslot, w.cell_start + w.table, static_cast<uint32_t>(nx), w.fill + w.table, w.qorder);
     }
-    if (!radius && k <= 4) {                              // thread per query
+    if (small) {                                          // thread per query, k best keys in registers
         const unsigned gs = static_cast<unsigned>((ny + 255) / 256);
 #define P2W_GS(KK) P2W_LAUNCH((grid_query_small_kernel<KK>), gs, 256, 0, st)(w.spts, w.cell_start, w.grid, y, ptr_x, ptr_y, T, ny, nbr, d2)
         if (k == 1) P2W_GS(1); else if (k == 2) P2W_GS(2); else if (k == 3) P2W_GS(3); else P2W_GS(4);
 #undef P2W_GS
+        return check_launch(what);
+    }
+    if (heap && nx > 0) {                                 // thread per query, heap of k keys in shared memory
+        const size_t smem = static_cast<size_t>(k) * (HT + 1) * sizeof(key_t);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(grid_query_heap_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(grid_query_heap_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(grid_query_heap_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done = true;
+        }
+        const unsigned gh = static_cast<unsigned>((ny + HT - 1) / HT);
+#define P2W_GH(R, O) P2W_LAUNCH((grid_query_heap_kernel<R, O>), gh, HT, smem, st)(w.spts, w.cell_start, w.grid, y, ptr_x, ptr_y, T, ny, k, r2, w.qorder, nbr, d2, cnt, w.pair_evals)
+        if (radius) P2W_GH(true, true); else if (unordered) P2W_GH(false, false); else P2W_GH(false, true);
+#undef P2W_GH
         return check_launch(what);
     }
     int64_t blocks = ((ny + 31) / 32 + 7) / 8;          // a warp takes 32 queries at a time
@@ -936,22 +1264,30 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
 
 using namespace p2w;
 
-extern "C" size_t p2w_grid_search_ws_bytes(int64_t nx, int32_t num_tiles) {
-    return grid_ws(nullptr, nx < 0 ? 0 : nx, num_tiles < 1 ? 1 : num_tiles).total;
+extern "C" size_t p2w_grid_search_ws_bytes(int64_t nx, int64_t ny, int32_t num_tiles) {
+    return grid_ws(nullptr, nx < 0 ? 0 : nx, ny < 0 ? 0 : ny, num_tiles < 1 ? 1 : num_tiles).total;
+}
+
+extern "C" int p2w_grid_search_pair_evals(const void *ws, int64_t nx, int64_t ny, int32_t num_tiles,
+                                          const unsigned long long **counter) {
+    P2W_REQUIRE(ws != nullptr && counter != nullptr, "p2w_grid_search_pair_evals: null argument");
+    *counter = grid_ws(const_cast<void *>(ws), nx, ny, num_tiles < 1 ? 1 : num_tiles).pair_evals;
+    return P2W_OK;
 }
 
 extern "C" int p2w_knn_grid_ex(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
-                               int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, float cell_size, int32_t *nbr,
-                               float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream) {
+                               int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, float cell_size, int32_t flags,
+                               int32_t *nbr, float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream) {
     P2W_REQUIRE(k >= 1 && k <= P2W_MAX_K, "p2w_knn_grid: k=%d outside [1,%d]", k, P2W_MAX_K);
-    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, false, cell_size, nbr, d2, nullptr, ws, ws_bytes,
-                       as_stream(stream), "p2w_knn_grid");
+    const bool unordered = (flags & P2W_KNN_UNORDERED) && k >= 5 && !use_warp_kernel();   // otherwise: ordered (a valid answer)
+    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, false, cell_size, unordered, nbr, d2, nullptr, ws,
+                       ws_bytes, as_stream(stream), "p2w_knn_grid");
 }
 
 extern "C" int p2w_knn_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
                             int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, int32_t *nbr, float *d2, void *ws,
                             size_t ws_bytes, p2w_stream_t stream) {
-    return p2w_knn_grid_ex(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, nbr, d2, ws, ws_bytes, stream);
+    return p2w_knn_grid_ex(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, 0, nbr, d2, ws, ws_bytes, stream);
 }
 
 extern "C" int p2w_radius_grid(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y,
@@ -960,6 +1296,6 @@ extern "C" int p2w_radius_grid(const float *x, const float *y, const int64_t *pt
     P2W_REQUIRE(max_nbr >= 1 && max_nbr <= P2W_MAX_K, "p2w_radius_grid: max_num_neighbors=%d outside [1,%d]", max_nbr,
                 P2W_MAX_K);
     const float r2 = static_cast<float>(r * r);   // upstream passes r*r (double) into a float argument
-    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, max_nbr, r2, true, 0.f, nbr, nullptr, cnt, ws, ws_bytes,
+    return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, max_nbr, r2, true, 0.f, false, nbr, nullptr, cnt, ws, ws_bytes,
                        as_stream(stream), "p2w_radius_grid");
 }

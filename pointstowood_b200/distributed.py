@@ -265,6 +265,22 @@ class ShardedPlot:
         self.K = kernels or _Kernels()
         self.traffic = self.comm.traffic
         self.n_z: Optional[Tensor] = None
+        self.timing = False           # True: CUDA events at the phase boundaries (phase_ms() after a synchronise)
+        self._marks: List[Tuple[str, object]] = []
+
+    def _mark(self, name: str) -> None:
+        if self.timing and self.chunk.is_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
+
+    def phase_ms(self) -> Dict[str, float]:
+        """Device time between consecutive marks (name = the phase that ENDS at the mark)."""
+        torch.cuda.synchronize()
+        out: Dict[str, float] = {}
+        for (_, a), (name, b) in zip(self._marks[:-1], self._marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
     # ---------------------------------------------------------------- 1-3: tiling and the member exchange
     def tile(self) -> TileStore:
@@ -272,6 +288,7 @@ class ShardedPlot:
         W, r = comm.world, comm.rank
         dev = chunk.device
         n = chunk.size(0)
+        self._mark("start")
         # ---- global statistics (src/preprocessing.py:41-42,94; NaN checks :20-21)
         mn, mx = K.colminmax(chunk[:, :4])
         mm = comm.all_reduce(torch.cat([mn, -mx]), "MIN", "all-reduce: column min / max")
@@ -296,6 +313,7 @@ class ShardedPlot:
         hist = torch.histc(chunk[:, 0], bins=HIST_BINS, min=float(ext[0, 0]), max=float(ext[1, 0])) if n else \
             torch.zeros(HIST_BINS, device=dev)
         hist = comm.all_reduce(hist.to(torch.float64), "SUM", "all-reduce: x histogram")
+        self._mark("tile: statistics")
         # ---- height above ground (:37-53)
         lo, hi = ext[0, :2], ext[1, :2] + np.float32(5.0)
         nb = [max(1, int(math.ceil((float(hi[d]) - float(lo[d])) / 5.0))) for d in range(2)]
@@ -308,6 +326,7 @@ class ShardedPlot:
         if self.weighted:
             column = comm.all_gather_v(chunk[:, 3].contiguous(), self.counts, "all-gather: reflectance column")
             refl = K.reflectance_normalize(column)[self.offset: self.offset + n].contiguous()
+        self._mark("tile: ground + reflectance ranks")
         feat = K.assemble5(chunk, refl, n_z)
         mn5, mx5 = K.colminmax(feat)
         mm5 = comm.all_reduce(torch.cat([mn5, -mx5]), "MIN", "all-reduce: column min / max")
@@ -333,6 +352,7 @@ class ShardedPlot:
                 order = torch.empty(0, device=dev, dtype=torch.int32)
                 starts, nuniq = torch.zeros(1, device=dev, dtype=torch.int64), torch.zeros(1, device=dev, dtype=torch.int64)
             local.append((keys, order, starts, nuniq))
+        self._mark("tile: voxel ids, sort, segments")
         nu = torch.cat([l[3] for l in local])
         nu_all = comm.all_gather_equal(nu, "all-gather: voxel list sizes").cpu().numpy()               # sync 3
         tables = []
@@ -351,6 +371,7 @@ class ShardedPlot:
         tb = np.array([batches[b][0] if b < len(batches) else T for b in bb], dtype=np.int64)      # tile bounds per rank
         self.tile_bounds, self.tile_ptr, self.num_tiles = tb, ptr, T
         tb_dev = _lib.to_device(tb, dev, np.int64) if dev.type == "cuda" else torch.from_numpy(tb)
+        self._mark("tile: merged voxel table + ownership")
         # ---- members of kept voxels, ascending (tile, point index): already grouped by destination
         pts, tiles = [], []
         for gi, (keys, order, starts, _) in enumerate(local):
@@ -372,7 +393,9 @@ class ShardedPlot:
         payload[:, :4] = feat[pts, :4].contiguous().view(torch.int32)
         payload[:, 4] = (pts + self.offset).to(torch.int32)
         payload[:, 5] = tiles.to(torch.int32)
+        self._mark("tile: routing plan")
         recv = comm.all_to_all(payload, cm[r].tolist(), cm[:, r].tolist(), "all-to-all: tile members")
+        self._mark("tile: member all-to-all")
         # ---- this rank's tiles: stable regroup by tile (sources arrive in rank order = ascending point index)
         t0, t1 = int(tb[r]), int(tb[r + 1])
         full_loc = full[t0:t1].astype(np.int64)
@@ -407,6 +430,7 @@ class ShardedPlot:
                 for j, v in enumerate(bg.tolist()):
                     members[off[v]: off[v + 1]] = picks[j]
         self.first_row = int(ptr[t0])          # global row index of this rank's first classified row
+        self._mark("tile: regroup + thinning")
         return TileStore(feat=feat_loc, members=members, ptr=off, grid_of_tile=grid_of_tile)
 
     # ---------------------------------------------------------------- 5-6: the spatial vote by x-slabs
@@ -418,6 +442,7 @@ class ShardedPlot:
         dev = chunk.device
         n = chunk.size(0)
         k = 32 if any_wood != 1 else 64                                                               # :137
+        self._mark("classify")
         bounds = torch.as_tensor(self.bounds, device=dev)
         q = chunk[:, :3].contiguous()
         if W > 1 and n:
@@ -432,6 +457,8 @@ class ShardedPlot:
         rows = torch.cat([xyz.reshape(-1, 3), prob.reshape(-1, 1)], dim=1).contiguous()                  # 16 B per classified row
         width = float(self.ext[1, 0]) - float(self.ext[0, 0])
         queries = None
+        pending = None                 # queries still to be answered (None: all of them)
+        label = pwood = None
         self.vote_rounds = 0
         while True:
             self.vote_rounds += 1
@@ -455,25 +482,44 @@ class ShardedPlot:
             entries = eorder[: int(rm[r].sum())].long()
             got = comm.all_to_all(rows[entries // slots], rm[r].tolist(), rm[:, r].tolist(), "all-to-all: classified rows")
             rx, rp = got[:, :3].contiguous(), got[:, 3].contiguous()
-            label, pwood, nbr = K.vote(rx, rp, (rp >= is_wood).to(torch.uint8), queries, k, float(any_wood))
+            self._mark("vote: routing + all-to-alls")
+            # later rounds only redo the queries that failed the bound (a handful of isolated points)
+            todo = queries if pending is None else queries[pending]
+            lab_t, pw_t, nbr = K.vote(rx, rp, (rp >= is_wood).to(torch.uint8), todo, k, float(any_wood))
+            if pending is None:
+                label, pwood = lab_t, pw_t
+            else:
+                label[pending] = lab_t
+                pwood[pending] = pw_t
+            self._mark("vote: search + vote")
             if everything:
                 break
             # ---- exactness: the k-th neighbour must be closer than anything this slab was not given
             lo = float(self.bounds[r - 1]) - (halo - 1e-3) if r > 0 else -math.inf
             hi = float(self.bounds[r]) + (halo - 1e-3) if r < W - 1 else math.inf
             need = torch.zeros(2, device=dev, dtype=torch.float64)
-            if queries.size(0):
-                last = nbr[:, k - 1].long()
-                far = (queries - rx[last.clamp(min=0)]).double().pow(2).sum(1).sqrt() if rx.size(0) else \
-                    torch.full((queries.size(0),), math.inf, device=dev, dtype=torch.float64)
-                far = torch.where(last < 0, torch.full_like(far, math.inf), far)
-                qx = queries[:, 0].double()
+            bad = None
+            if todo.size(0):
+                # the k-th neighbour sits in the first or in the last column (unordered / ordered table)
+                ends = nbr[:, [0, k - 1]].long()
+                if rx.size(0):
+                    far = (todo[:, None, :] - rx[ends.clamp(min=0)]).double().pow(2).sum(2).sqrt().max(dim=1).values
+                else:
+                    far = torch.full((todo.size(0),), math.inf, device=dev, dtype=torch.float64)
+                far = torch.where((ends < 0).any(dim=1), torch.full_like(far, math.inf), far)
+                qx = todo[:, 0].double()
                 margin = torch.minimum(qx - lo, hi - qx)
                 bad = far >= margin
                 need = torch.stack([bad.sum().double(), torch.where(bad, far - margin, torch.zeros_like(far)).max()])
             need = comm.all_reduce(need, "MAX", "all-reduce: halo check").cpu().numpy()                # sync
+            self._mark("vote: halo check")
             if need[0] == 0:
                 break
+            if bad is None:
+                pending = torch.empty(0, device=dev, dtype=torch.int64)
+            else:
+                sel = torch.nonzero(bad).view(-1)
+                pending = sel if pending is None else pending[sel]
             halo = width if not np.isfinite(need[1]) else min(width, 1.25 * (halo + float(need[1])) + 0.01)
         self.halo = halo
         back_l = comm.all_to_all(label, qm[:, r].tolist(), qm[r].tolist(), "all-to-all: labels") if W > 1 else label
@@ -482,6 +528,7 @@ class ShardedPlot:
         out_p = torch.empty(n, device=dev, dtype=torch.float64)
         out_l[qorder] = back_l
         out_p[qorder] = back_p
+        self._mark("vote: results home")
         return out_l, out_p
 
 
@@ -489,10 +536,11 @@ class ShardedPlot:
 def classify_plot(net: torch.nn.Module, chunk: Tensor, min_pts: int = 128, max_pts: int = 16384,
                   grid_size=(2.0, 4.0), batch_size: int = 8, is_wood: float = 0.5, any_wood: float = 1,
                   max_points_per_launch: int = 1 << 21, halo: float = DEFAULT_HALO, comm: Optional[Comm] = None,
-                  return_plot: bool = False):
+                  return_plot: bool = False, timing: bool = False):
     """chunk [n_r, >=4] (x, y, z, reflectance): this rank's contiguous rows of the plot, on its device
     -> (label uint8 [n_r], pwood float64 [n_r]) for the same rows.  Single process: the whole plot."""
     plot = ShardedPlot(chunk, comm, min_pts, max_pts, grid_size, batch_size)
+    plot.timing = timing
     store = plot.tile()
     prob, _, xyz, _ = classify_tiles(net, store, batch_size, is_wood, max_points_per_launch=max_points_per_launch,
                                      want_xyz=True)

@@ -114,15 +114,27 @@ def _use_grid(method: Optional[str], nx: int, tiles: int, k: int = 32) -> bool:
     return method == "grid"
 
 
-def _grid_ws(nx: int, tiles: int, dev) -> Tensor:
-    return torch.empty(int(_lib.lib().p2w_grid_search_ws_bytes(nx, tiles)), device=dev, dtype=torch.uint8)
+def _grid_ws(nx: int, ny: int, tiles: int, dev) -> Tensor:
+    return torch.empty(int(_lib.lib().p2w_grid_search_ws_bytes(nx, ny, tiles)), device=dev, dtype=torch.uint8)
+
+
+def grid_search_pair_evals(ws: Tensor, nx: int, ny: int, tiles: int) -> Tensor:
+    """uint64 counter (as an int64 tensor view of `ws`) of the distance evaluations of the last cell-list search that
+    used `ws`; valid once the stream has been synchronised."""
+    import ctypes
+    addr = ctypes.c_void_p()
+    _lib.check(_lib.lib().p2w_grid_search_pair_evals(ws.data_ptr(), nx, ny, tiles, ctypes.byref(addr)))
+    off = addr.value - ws.data_ptr()
+    return ws[off: off + 8].view(torch.int64)
 
 
 def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return_d2: bool = False,
-              method: Optional[str] = None, cell_size: float = 0.0):
+              method: Optional[str] = None, cell_size: float = 0.0, unordered: bool = False):
     """[Ny, k] int32 table of the k nearest x rows of every y row inside its tile, ordered by
     (FP32 squared distance, index); -1 padded.  No host sync.  method: 'sweep' (tile-resident brute
-    force), 'grid' (per-tile cell list) or None (pick by sources per tile); same result either way."""
+    force), 'grid' (per-tile cell list) or None (pick by sources per tile); same result either way.
+    unordered (cell list only): the same neighbour SET per row, the k-th neighbour in column 0 OR in column k - 1
+    and the rest in no particular order (P2W_KNN_UNORDERED: saves the final sort for consumers like the vote)."""
     x = _req(x, torch.float32, "x", 2)
     y = _req(y, torch.float32, "y", 2)
     if x.size(1) != 3 or y.size(1) != 3:
@@ -136,10 +148,10 @@ def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return
     work = 12.0 * (x.size(0) + y.size(0)) + 16.0 * y.size(0) * k + 16.0 * ptr_x.numel()
     L = _lib.lib()
     if _use_grid(method, x.size(0), T, k):
-        ws = _grid_ws(x.size(0), T, x.device)
+        ws = _grid_ws(x.size(0), y.size(0), T, x.device)
         _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn_grid_ex, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T,
-                                     x.size(0), y.size(0), k, float(cell_size), _dp(nbr), _dp(d2), _dp(ws), ws.numel(),
-                                     _stream()))
+                                     x.size(0), y.size(0), k, float(cell_size), 1 if unordered else 0, _dp(nbr), _dp(d2),
+                                     _dp(ws), ws.numel(), _stream()))
     else:
         _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T, x.size(0),
                                      y.size(0), k, _dp(nbr), _dp(d2), _stream()))
@@ -159,7 +171,7 @@ def radius_table(x: Tensor, y: Tensor, r: float, ptr_x: Tensor, ptr_y: Tensor, m
     cnt = torch.empty((y.size(0),), device=x.device, dtype=torch.int32)
     L = _lib.lib()
     if _use_grid(method, x.size(0), T) and max_num_neighbors <= 128:
-        ws = _grid_ws(x.size(0), T, x.device)
+        ws = _grid_ws(x.size(0), y.size(0), T, x.device)
         _lib.check(L.p2w_radius_grid(_dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T, x.size(0), y.size(0), float(r),
                                      max_num_neighbors, _dp(nbr), _dp(cnt), _dp(ws), ws.numel(), _stream()))
     else:
@@ -622,7 +634,7 @@ def spatial_vote(classified_xyz: Tensor, prob: Tensor, pred: Tensor, original_xy
     dev = xyz.device
     px = _lib.to_device([0, xyz.size(0)], dev, np.int64)
     py = _lib.to_device([0, org.size(0)], dev, np.int64)
-    nbr = knn_table(xyz, org, k, px, py, method="grid", cell_size=cell_size)
+    nbr = knn_table(xyz, org, k, px, py, method="grid", cell_size=cell_size, unordered=True)   # the vote sorts for itself
     label = torch.empty(org.size(0), device=dev, dtype=torch.uint8)
     pwood = torch.empty(org.size(0), device=dev, dtype=torch.float64)
     _lib.check(_lib.lib().p2w_spatial_vote(_dp(nbr), org.size(0), k, _dp(prob), _dp(pred), float(any_wood), _dp(label),

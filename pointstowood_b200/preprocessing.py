@@ -121,7 +121,7 @@ class Voxelise:
         cloud = self.cloud
         n = cloud.size(0)
         L = _lib.lib()
-        mn, ext = self._cloud_stats()
+        mn, ext = self._cloud_stats()[:2]
         lo = ext[0, :2]
         hi = ext[1, :2] + np.float32(5.0)      # x_max + grid_resolution, rounded in fp32 like the tensor op
         nb = [max(1, int(math.ceil((float(hi[d]) - float(lo[d])) / 5.0))) for d in range(2)]

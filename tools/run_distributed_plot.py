@@ -50,7 +50,9 @@ e1.record()
 torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-res = dict(points=n, world=world, ms=t.item(), points_per_s=n / t.item() * 1e3, tiles=int(plot.num_tiles), halo=plot.halo,
+label, pwood, plot = classify_plot(net, chunk, halo=args.halo, return_plot=True, timing=True)
+phases = plot.phase_ms()
+res = dict(phases_ms_rank0={k: round(v, 3) for k, v in phases.items()}, points=n, world=world, ms=t.item(), points_per_s=n / t.item() * 1e3, tiles=int(plot.num_tiles), halo=plot.halo,
            vote_rounds=plot.vote_rounds, collective_bytes_rank0=dict(plot.traffic))
 if args.check:
     whole = torch.from_numpy(tls_plot_blocks(n, 1)[0]).cuda()
