@@ -270,6 +270,7 @@ def main():
 
     # ---- device-resident steps, dominant kernel timed live with CUDA events
     ops.KERNEL_TIMER.reset("p2w_pointnet_conv_max", "p2w_knn")
+    ops.PAIR_EVALS.clear()
     barrier()
     launches0 = L.p2w_launch_count()
     with ClockSampler(local) as clk:
@@ -282,6 +283,7 @@ def main():
     launches = L.p2w_launch_count() - launches0
     ms = ev0.elapsed_time(ev1) / args.steps
     kt_conv, kt_knn = ops.KERNEL_TIMER.summary("p2w_pointnet_conv_max"), ops.KERNEL_TIMER.summary("p2w_knn")
+    pair_evals = sum(int(v.item()) for v in ops.PAIR_EVALS.values())
     ops.KERNEL_TIMER.reset()
 
     # ---- end to end through the host-facing API (pinned host in, host out)
@@ -332,6 +334,13 @@ def main():
                             traffic=traffic.get("grid_query_kernel"),
                             work="bytes = 12 (Nx + Ny) + 16 Ny k + 16 (B+1) per call (SURVEY.md 8d)",
                             launches=kt_knn["launches"], avg_launch_ms=per_launch_ms)
+            # the bound that actually applies: a distance is 6 FP32 instructions (3 FSUB, FMUL,
+            # 2 FFMA); 148 SMs x 128 lanes x the sampled SM clock
+            issue_bound = 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 6.0
+            roof_knn.update(pair_evals_per_s=pair_evals / (kt_knn["ms"] / 1e3), fp32_issue_bound_pair_evals_per_s=issue_bound,
+                            frac_fp32_issue=pair_evals / (kt_knn["ms"] / 1e3) / issue_bound,
+                            pair_evals_per_query="all cell-list searches of the step: SA1 radius, SA2 / SA3 k = 32, four k = 2 "
+                                                 "interpolation searches, the vote's k = 64")
         roof = roof_conv if bf16 else roof_knn
         config = dict(workload=workload(N_POINTS) if (world == 1 and total_points == N_POINTS) else
                       workload_sharded(total_points, world),

@@ -485,7 +485,7 @@ constexpr int SMALL_K = 6;        // up to this k a crowded step is reduced by k
 template <int S, bool RADIUS>
 __device__ __forceinline__ void scan_segments(int len, uint32_t start, const float4 *__restrict__ spts, float qx,
                                               float qy, float qz, float r2, int k, int lane, TopK64<S> &top,
-                                              key_t &thr, int &hits) {
+                                              key_t &thr, int &hits, unsigned long long &evals) {
     int incl = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -494,6 +494,7 @@ __device__ __forceinline__ void scan_segments(int len, uint32_t start, const flo
     }
     const int total = __shfl_sync(FULL, incl, 31);
     const int excl = incl - len;
+    evals += static_cast<unsigned long long>(total);
     for (int base = 0; base < total; base += 32) {
         const int t = base + lane;
         int sg = 0;   // number of segments that end at or before t
@@ -572,8 +573,10 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
                                                          const int64_t *__restrict__ ptr_x,
                                                          const int64_t *__restrict__ ptr_y, int T, int64_t ny,
                                                          int k, float r2, int32_t *__restrict__ nbr,
-                                                         float *__restrict__ d2out, int32_t *__restrict__ cnt_out) {
+                                                         float *__restrict__ d2out, int32_t *__restrict__ cnt_out,
+                                                         unsigned long long *__restrict__ pair_evals) {
     const int lane = threadIdx.x & 31;
+    unsigned long long evals = 0;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const int64_t nchunks = (ny + 31) >> 5;
     // a warp takes 32 consecutive queries at a time: coalesced loads, one tile lookup per lane
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
                         const int lo = stage == 0 ? 0 : (stage == 1 ? 7 : 19), hi = stage == 0 ? 7 : (stage == 1 ? 19 : 27);
                         const float lim = RADIUS ? r2 : __uint_as_float(static_cast<unsigned>(thr >> 32));
                         const bool use = lane >= lo && lane < hi && (RADIUS ? b2 < lim : b2 <= lim);
-                        scan_segments<S, RADIUS>(use ? len : 0, a, spts, qx, qy, qz, r2, k, lane, top, thr, hits);
+                        scan_segments<S, RADIUS>(use ? len : 0, a, spts, qx, qy, qz, r2, k, lane, top, thr, hits, evals);
                     }
                 }
                 for (int r = 1;; r++) {
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
                                     }
                                 }
                             }
-                            scan_segments<S, RADIUS>(len, start, spts, qx, qy, qz, r2, k, lane, top, thr, hits);
+                            scan_segments<S, RADIUS>(len, start, spts, qx, qy, qz, r2, k, lane, top, thr, hits, evals);
                         }
                     }
                     // every source of the tile seen?
@@ -714,6 +717,7 @@ __global__ void __launch_bounds__(256, 3) grid_query_kernel(const float4 *__rest
             if (RADIUS && lane == 0) cnt_out[q] = hits < k ? hits : k;
         }
     }
+    if (pair_evals && lane == 0 && evals) atomicAdd(pair_evals, evals);
 }
 
 // ---- k <= 4 (the k = 2 search inside knn_interpolate, src/model.py:149): one THREAD per query.
@@ -739,7 +743,8 @@ __device__ __forceinline__ void small_insert(key_t (&best)[K], key_t ck) {
 
 template <int K>
 __device__ __forceinline__ void small_scan(const float4 *__restrict__ spts, uint32_t a, uint32_t e, float qx, float qy,
-                                           float qz, key_t (&best)[K]) {
+                                           float qz, key_t (&best)[K], unsigned &evals) {
+    evals += e - a;
     for (uint32_t i = a; i < e; i++) {
         const float4 c = __ldg(spts + i);
         const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
@@ -755,9 +760,11 @@ __global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__r
                                                                const float *__restrict__ y,
                                                                const int64_t *__restrict__ ptr_x,
                                                                const int64_t *__restrict__ ptr_y, int T, int64_t ny,
-                                                               int32_t *__restrict__ nbr, float *__restrict__ d2out) {
+                                                               int32_t *__restrict__ nbr, float *__restrict__ d2out,
+                                                               unsigned long long *__restrict__ pair_evals) {
     const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q >= ny) return;
+    unsigned evals = 0;
     const int b = find_tile(ptr_y, T, q);
     const int64_t s0 = ptr_x[b], s1 = ptr_x[b + 1];
     const float qx = y[q * 3 + 0], qy = y[q * 3 + 1], qz = y[q * 3 + 2];
@@ -801,7 +808,7 @@ __global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__r
 #pragma unroll
         for (int s = 0; s < 9; s++) {
             if (rb2[s] > __uint_as_float(static_cast<unsigned>(best[K - 1] >> 32))) continue;
-            small_scan<K>(spts, ra[s], re[s], qx, qy, qz, best);
+            small_scan<K>(spts, ra[s], re[s], qx, qy, qz, best, evals);
         }
         for (int r = 1;; r++) {
             if (r > 1) {                               // rare: shells beyond the first ring, row by row
@@ -817,14 +824,14 @@ __global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__r
                             const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
                             if (x0 <= x1)
                                 small_scan<K>(spts, __ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1), qx, qy,
-                                              qz, best);
+                                              qz, best, evals);
                         } else {
                             if (cx - r >= 0)
                                 small_scan<K>(spts, __ldg(cell_start + row + cx - r), __ldg(cell_start + row + cx - r + 1),
-                                              qx, qy, qz, best);
+                                              qx, qy, qz, best, evals);
                             if (cx + r < g.nx)
                                 small_scan<K>(spts, __ldg(cell_start + row + cx + r), __ldg(cell_start + row + cx + r + 1),
-                                              qx, qy, qz, best);
+                                              qx, qy, qz, best, evals);
                         }
                     }
                 }
@@ -846,6 +853,11 @@ __global__ void __launch_bounds__(256) grid_query_small_kernel(const float4 *__r
     for (int i = 0; i < K; i++) {
         nbr[q * K + i] = static_cast<int32_t>(static_cast<uint32_t>(best[i]));
         if (d2out) d2out[q * K + i] = __uint_as_float(static_cast<unsigned>(best[i] >> 32));
+    }
+    if (pair_evals) {                       // the warp's active lanes add up, one atomic per warp
+        const unsigned act = __activemask();
+        const unsigned total = __reduce_add_sync(act, evals);
+        if ((threadIdx.x & 31) == __ffs(act) - 1 && total) atomicAdd(pair_evals, static_cast<unsigned long long>(total));
     }
 }
 
@@ -927,57 +939,14 @@ __device__ __forceinline__ void heap_offer(key_t *__restrict__ h, int st, int k,
     }
 }
 
-constexpr int HB = 8;      // candidates whose loads are in flight together
-
-template <bool RADIUS>
-__device__ __forceinline__ void heap_scan(const float4 *__restrict__ spts, uint32_t a, uint32_t e, float qx, float qy,
-                                          float qz, float r2, key_t *__restrict__ h, int st, int k, HeapState &hs,
-                                          int &hits, unsigned &evals) {
-    for (uint32_t base = a; base < e; base += 32) {
-        const uint32_t n = min(e - base, 32u);
-        unsigned mask = 0;
-        for (uint32_t j0 = 0; j0 < n; j0 += HB) {
-            float4 c[HB];
-#pragma unroll
-            for (int u = 0; u < HB; u++) c[u] = __ldg(spts + base + min(j0 + u, n - 1));
-#pragma unroll
-            for (int u = 0; u < HB; u++) {
-                const float dx = __fsub_rn(c[u].x, qx), dy = __fsub_rn(c[u].y, qy), dz = __fsub_rn(c[u].z, qz);
-                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                bool ok = j0 + u < n;
-                key_t ck;
-                if (RADIUS) {
-                    ok = ok && d < r2;
-                    hits += ok ? 1 : 0;
-                    ck = __float_as_uint(c[u].w);
-                } else {
-                    ok = ok && d < 1e10f;
-                    ck = (static_cast<key_t>(__float_as_uint(d)) << 32) | __float_as_uint(c[u].w);
-                }
-                if (ok && ck < hs.root) mask |= 1u << (j0 + u);
-            }
-        }
-        evals += n;
-        while (mask) {
-            const uint32_t j = static_cast<uint32_t>(__ffs(mask) - 1);
-            mask &= mask - 1;
-            const float4 c = __ldg(spts + base + j);
-            key_t ck;
-            if (RADIUS) {
-                ck = __float_as_uint(c.w);
-            } else {
-                const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
-                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                ck = (static_cast<key_t>(__float_as_uint(d)) << 32) | __float_as_uint(c.w);
-            }
-            heap_offer(h, st, k, hs, ck);
-        }
-    }
-}
+constexpr int HB = 4;      // candidates whose loads are in flight together
 
 // ORDERED: rows ascending by key (the contract of p2w_knn / torch_cluster).  Otherwise the finished heap is
 // written as it stands: entry 0 is the k-th (farthest) neighbour, the rest in no particular order (what the
 // spatial vote needs: it sorts the probabilities itself) -- this skips k root extractions per query.
+// The kernel is ONE loop nest (rings > rows > row parts > candidate batches) with a single copy of the scan
+// body: the lanes of a warp diverge on trip counts, and a body replicated per ring-1 row thrashed the
+// instruction cache (ncu: "no instruction" was the top stall).
 template <bool RADIUS, bool ORDERED>
 __global__ void __launch_bounds__(HT) grid_query_heap_kernel(const float4 *__restrict__ spts,
                                                              const uint32_t *__restrict__ cell_start,
@@ -1021,72 +990,94 @@ __global__ void __launch_bounds__(HT) grid_query_heap_kernel(const float4 *__res
             const float lox = fmaxf((qx - fx) * k1 - margin, 0.f), hix = fmaxf((fx + g.h - qx) * k1 - margin, 0.f);
             const float loy = fmaxf((qy - fy) * k1 - margin, 0.f), hiy = fmaxf((fy + g.h - qy) * k1 - margin, 0.f);
             const float loz = fmaxf((qz - fz) * k1 - margin, 0.f), hiz = fmaxf((fz + g.h - qz) * k1 - margin, 0.f);
-            const float hs1 = g.h * k1;
-            // ring 1: 9 rows of up to 3 cells (contiguous in the cell table), nearest rows first.  The four table
-            // entries of every row are fetched up front (independent loads); a row, or one of its outer cells,
-            // whose lower bound already exceeds the k-th distance is skipped.
-            {
-                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-                uint32_t r0[9], r1[9], r2c[9], r3[9];        // starts of cells x0, cx, cx + 1 and the end of x1
-#pragma unroll
-                for (int s = 0; s < 9; s++) {
-                    const int ddy = static_cast<int>((0x22161u >> (2 * s)) & 3u) - 1;   // 0,-1,1,0,0,-1,1,-1,1
-                    const int ddz = static_cast<int>((0x28215u >> (2 * s)) & 3u) - 1;   // 0,0,0,-1,1,-1,-1,1,1
-                    const int yy = cy + ddy, zz = cz + ddz;
-                    r0[s] = r1[s] = r2c[s] = r3[s] = 0u;
-                    if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
-                        const uint32_t *row = cell_start + (g.base + g.nx * (yy + g.ny * zz));
-                        r0[s] = __ldg(row + x0);
-                        r1[s] = __ldg(row + cx);
-                        r2c[s] = __ldg(row + cx + 1);
-                        r3[s] = __ldg(row + x1 + 1);
+            const float hs1 = g.h * k1;             // a further whole cell in between adds at least this much
+#pragma unroll 1
+            for (int r = 1;; r++) {
+                // shell r as rows along x.  Ring 1: its 9 rows, nearest first, each the cells cx-1..cx+1.  Shell r > 1:
+                // (2r+1)^2 rows; a rim row is new over cx-r..cx+r, an interior row only in its two end cells.
+                const int side = 2 * r + 1, nrows = side * side;
+#pragma unroll 1
+                for (int s = 0; s < nrows; s++) {
+                    int dy, dz;
+                    if (r == 1) {
+                        dy = static_cast<int>((0x22161u >> (2 * s)) & 3u) - 1;   // 0,-1,1,0,0,-1,1,-1,1
+                        dz = static_cast<int>((0x28215u >> (2 * s)) & 3u) - 1;   // 0,0,0,-1,1,-1,-1,1,1
+                    } else {
+                        dy = s % side - r;
+                        dz = s / side - r;
                     }
-                }
-#pragma unroll
-                for (int s = 0; s < 9; s++) {
-                    const int ddy = static_cast<int>((0x22161u >> (2 * s)) & 3u) - 1;
-                    const int ddz = static_cast<int>((0x28215u >> (2 * s)) & 3u) - 1;
-                    const float sy = ddy < 0 ? loy : (ddy > 0 ? hiy : 0.f);
-                    const float sz = ddz < 0 ? loz : (ddz > 0 ? hiz : 0.f);
+                    const int yy = cy + dy, zz = cz + dz;
+                    if (yy < 0 || yy >= g.ny || zz < 0 || zz >= g.nz) continue;
+                    const float sy = dy < 0 ? loy + static_cast<float>(-dy - 1) * hs1
+                                            : (dy > 0 ? hiy + static_cast<float>(dy - 1) * hs1 : 0.f);
+                    const float sz = dz < 0 ? loz + static_cast<float>(-dz - 1) * hs1
+                                            : (dz > 0 ? hiz + static_cast<float>(dz - 1) * hs1 : 0.f);
                     const float rb2 = sy * sy + sz * sz;
                     const float lim = RADIUS ? r2 : __uint_as_float(static_cast<unsigned>(hs.root >> 32));
                     if (RADIUS ? !(rb2 < lim) : rb2 > lim) continue;
-                    const bool skip_lo = RADIUS ? !(rb2 + lox * lox < lim) : rb2 + lox * lox > lim;
-                    const bool skip_hi = RADIUS ? !(rb2 + hix * hix < lim) : rb2 + hix * hix > lim;
-                    heap_scan<RADIUS>(spts, skip_lo ? r1[s] : r0[s], skip_hi ? r2c[s] : r3[s], qx, qy, qz, r2, h, ST, k, hs,
-                                      hits, evals);
-                }
-            }
-            for (int r = 1;; r++) {
-                if (r > 1) {                               // shells beyond the first ring, row by row with the same bounds
-                    for (int dz = -r; dz <= r; dz++) {
-                        const int zz = cz + dz;
-                        if (zz < 0 || zz >= g.nz) continue;
-                        const float sz = dz < 0 ? loz + static_cast<float>(-dz - 1) * hs1
-                                                : (dz > 0 ? hiz + static_cast<float>(dz - 1) * hs1 : 0.f);
-                        for (int dy = -r; dy <= r; dy++) {
-                            const int yy = cy + dy;
-                            if (yy < 0 || yy >= g.ny) continue;
-                            const float sy = dy < 0 ? loy + static_cast<float>(-dy - 1) * hs1
-                                                    : (dy > 0 ? hiy + static_cast<float>(dy - 1) * hs1 : 0.f);
-                            const float rb2 = sy * sy + sz * sz;
-                            const float lim = RADIUS ? r2 : __uint_as_float(static_cast<unsigned>(hs.root >> 32));
-                            if (RADIUS ? !(rb2 < lim) : rb2 > lim) continue;
-                            const bool rim = (dz == -r || dz == r || dy == -r || dy == r);
-                            const int64_t row = g.base + g.nx * (yy + g.ny * zz);
-                            if (rim) {
-                                const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
-                                if (x0 <= x1)
-                                    heap_scan<RADIUS>(spts, __ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1),
-                                                      qx, qy, qz, r2, h, ST, k, hs, hits, evals);
-                            } else {
-                                const float sxl = lox + static_cast<float>(r - 1) * hs1, sxh = hix + static_cast<float>(r - 1) * hs1;
-                                if (cx - r >= 0 && (RADIUS ? rb2 + sxl * sxl < lim : rb2 + sxl * sxl <= lim))
-                                    heap_scan<RADIUS>(spts, __ldg(cell_start + row + cx - r), __ldg(cell_start + row + cx - r + 1),
-                                                      qx, qy, qz, r2, h, ST, k, hs, hits, evals);
-                                if (cx + r < g.nx && (RADIUS ? rb2 + sxh * sxh < lim : rb2 + sxh * sxh <= lim))
-                                    heap_scan<RADIUS>(spts, __ldg(cell_start + row + cx + r), __ldg(cell_start + row + cx + r + 1),
-                                                      qx, qy, qz, r2, h, ST, k, hs, hits, evals);
+                    // the end cells are r - 1 whole cells plus the gap inside the own cell away along x
+                    const float sxl = lox + static_cast<float>(r - 1) * hs1, sxh = hix + static_cast<float>(r - 1) * hs1;
+                    const bool reach_lo = RADIUS ? rb2 + sxl * sxl < lim : rb2 + sxl * sxl <= lim;
+                    const bool reach_hi = RADIUS ? rb2 + sxh * sxh < lim : rb2 + sxh * sxh <= lim;
+                    const uint32_t *row = cell_start + (g.base + g.nx * (yy + g.ny * zz));
+                    const bool rim = r == 1 || dz == -r || dz == r || dy == -r || dy == r;
+                    uint32_t a0 = 0, e0 = 0, a1 = 0, e1 = 0;
+                    if (rim) {
+                        int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+                        if (r == 1) {                      // ring 1 drops an end cell that cannot hold a result
+                            if (x0 < cx && !reach_lo) x0 = cx;
+                            if (x1 > cx && !reach_hi) x1 = cx;
+                        }
+                        a0 = __ldg(row + x0);
+                        e0 = __ldg(row + x1 + 1);
+                    } else {
+                        if (cx - r >= 0 && reach_lo) { a0 = __ldg(row + cx - r); e0 = __ldg(row + cx - r + 1); }
+                        if (cx + r < g.nx && reach_hi) { a1 = __ldg(row + cx + r); e1 = __ldg(row + cx + r + 1); }
+                    }
+#pragma unroll 1
+                    for (int part = 0; part < 2; part++) {
+                        const uint32_t a = part ? a1 : a0, e = part ? e1 : e0;
+#pragma unroll 1
+                        for (uint32_t base = a; base < e; base += 32) {
+                            const uint32_t n = min(e - base, 32u);
+                            unsigned mask = 0;
+#pragma unroll 1
+                            for (uint32_t j0 = 0; j0 < n; j0 += HB) {
+                                float4 c[HB];
+#pragma unroll
+                                for (int u = 0; u < HB; u++) c[u] = __ldg(spts + base + min(j0 + u, n - 1));
+#pragma unroll
+                                for (int u = 0; u < HB; u++) {
+                                    const float dx = __fsub_rn(c[u].x, qx), dy2 = __fsub_rn(c[u].y, qy), dz2 = __fsub_rn(c[u].z, qz);
+                                    const float d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
+                                    bool ok = j0 + u < n;
+                                    key_t ck;
+                                    if (RADIUS) {
+                                        ok = ok && d < r2;
+                                        hits += ok ? 1 : 0;
+                                        ck = __float_as_uint(c[u].w);
+                                    } else {
+                                        ok = ok && d < 1e10f;
+                                        ck = (static_cast<key_t>(__float_as_uint(d)) << 32) | __float_as_uint(c[u].w);
+                                    }
+                                    if (ok && ck < hs.root) mask |= 1u << (j0 + u);
+                                }
+                            }
+                            evals += n;
+#pragma unroll 1
+                            while (mask) {
+                                const uint32_t j = static_cast<uint32_t>(__ffs(mask) - 1);
+                                mask &= mask - 1;
+                                const float4 c = __ldg(spts + base + j);
+                                key_t ck;
+                                if (RADIUS) {
+                                    ck = __float_as_uint(c.w);
+                                } else {
+                                    const float dx = __fsub_rn(c.x, qx), dy2 = __fsub_rn(c.y, qy), dz2 = __fsub_rn(c.z, qz);
+                                    const float d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
+                                    ck = (static_cast<key_t>(__float_as_uint(d)) << 32) | __float_as_uint(c.w);
+                                }
+                                heap_offer(h, ST, k, hs, ck);
                             }
                         }
                     }
@@ -1180,6 +1171,11 @@ inline bool use_warp_kernel() {
     return v;
 }
 
+inline bool force_heap_kernel() {
+    static const bool v = [] { const char *e = getenv("P2W_KNN_HEAP"); return e && e[0] == '1'; }();
+    return v;
+}
+
 int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int64_t *ptr_y, int T, int64_t nx,
                 int64_t ny, int k, float r2, bool radius, float cell_hint, bool unordered, int32_t *nbr, float *d2,
                 int32_t *cnt, void *ws, size_t ws_bytes, cudaStream_t st, const char *what) {
@@ -1194,8 +1190,14 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
     const float tau = fmaxf(1.f, 0.45f * static_cast<float>(k));
     P2W_REQUIRE(cell_hint >= 0.f && cell_hint < 1e30f, "%s: bad cell size", what);
     const bool small = !radius && k <= 4;
-    const bool heap = !small && !use_warp_kernel();
-    P2W_REQUIRE(!unordered || (heap && !radius), "%s: the unordered table needs the heap kernel (kNN, k >= 5)", what);
+    // Kernel choice, measured on B200 (profiles/r2_knn_ab.txt): the per-thread heap wins the RADIUS search at the
+    // bench shapes (SA1: 1.21 -> 0.89 ms) and every search on uniform 16 384-point tiles (1.4-2.1x), but on the
+    // real SA2 / SA3 kNN (sub-sampled surfaces, ~750 sources per tile) its lanes diverge on candidate counts and on
+    // ring-2 walks and the warp-wide kernel stays ahead (0.83 vs 1.12 ms); at k = 64 (the vote) two thirds of the
+    // ~200 candidates enter a 6-level heap and it loses as well.  P2W_KNN_HEAP=1 / P2W_KNN_WARP=1 force one kernel
+    // for every k >= 5 (A/B runs; results are identical).
+    const bool heap = !small && !use_warp_kernel() && ((radius && k <= 32) || force_heap_kernel());
+    if (!heap) unordered = false;                       // the other kernels always order (a valid answer to the flag)
     const float *pre_box = nullptr;
     if (T == 1 && cell_hint > 0.f && nx > 65536) {          // one plot-wide tile: the box is everybody's job
         P2W_LAUNCH(box_init_kernel, 1, 32, 0, st)(w.box);
@@ -1226,7 +1228,7 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
     }
     if (small) {                                          // thread per query, k best keys in registers
         const unsigned gs = static_cast<unsigned>((ny + 255) / 256);
-#define P2W_GS(KK) P2W_LAUNCH((grid_query_small_kernel<KK>), gs, 256, 0, st)(w.spts, w.cell_start, w.grid, y, ptr_x, ptr_y, T, ny, nbr, d2)
+#define P2W_GS(KK) P2W_LAUNCH((grid_query_small_kernel<KK>), gs, 256, 0, st)(w.spts, w.cell_start, w.grid, y, ptr_x, ptr_y, T, ny, nbr, d2, w.pair_evals)
         if (k == 1) P2W_GS(1); else if (k == 2) P2W_GS(2); else if (k == 3) P2W_GS(3); else P2W_GS(4);
 #undef P2W_GS
         return check_launch(what);
@@ -1249,7 +1251,7 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
     int64_t blocks = ((ny + 31) / 32 + 7) / 8;          // a warp takes 32 queries at a time
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const unsigned gb = static_cast<unsigned>(blocks);
-#define P2W_GQ(S, R) P2W_LAUNCH((grid_query_kernel<S, R>), gb, 256, 0, st)(w.spts, w.cell_start, w.grid, y, ptr_x, ptr_y, T, ny, k, r2, nbr, d2, cnt)
+#define P2W_GQ(S, R) P2W_LAUNCH((grid_query_kernel<S, R>), gb, 256, 0, st)(w.spts, w.cell_start, w.grid, y, ptr_x, ptr_y, T, ny, k, r2, nbr, d2, cnt, w.pair_evals)
     if (radius) {
         if (k <= 32) P2W_GQ(1, true); else if (k <= 64) P2W_GQ(2, true); else P2W_GQ(4, true);
     } else {
@@ -1279,7 +1281,7 @@ extern "C" int p2w_knn_grid_ex(const float *x, const float *y, const int64_t *pt
                                int32_t num_tiles, int64_t nx, int64_t ny, int32_t k, float cell_size, int32_t flags,
                                int32_t *nbr, float *d2, void *ws, size_t ws_bytes, p2w_stream_t stream) {
     P2W_REQUIRE(k >= 1 && k <= P2W_MAX_K, "p2w_knn_grid: k=%d outside [1,%d]", k, P2W_MAX_K);
-    const bool unordered = (flags & P2W_KNN_UNORDERED) && k >= 5 && !use_warp_kernel();   // otherwise: ordered (a valid answer)
+    const bool unordered = (flags & P2W_KNN_UNORDERED) != 0;
     return grid_search(x, y, ptr_x, ptr_y, num_tiles, nx, ny, k, 0.f, false, cell_size, unordered, nbr, d2, nullptr, ws,
                        ws_bytes, as_stream(stream), "p2w_knn_grid");
 }

@@ -68,6 +68,7 @@ class _KernelTimer:
 
 
 KERNEL_TIMER = _KernelTimer()
+PAIR_EVALS = {}          # device -> int64 [1]: distance evaluations of the timed cell-list searches (bench.py)
 
 
 def _dp(t: Optional[Tensor]) -> Optional[int]:
@@ -152,6 +153,9 @@ def knn_table(x: Tensor, y: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor, return
         _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn_grid_ex, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T,
                                      x.size(0), y.size(0), k, float(cell_size), 1 if unordered else 0, _dp(nbr), _dp(d2),
                                      _dp(ws), ws.numel(), _stream()))
+        if "p2w_knn" in KERNEL_TIMER.targets:            # bench.py's probe: pair evaluations next to the time
+            acc = PAIR_EVALS.setdefault(x.device, torch.zeros(1, device=x.device, dtype=torch.int64))
+            acc += grid_search_pair_evals(ws, x.size(0), y.size(0), T)
     else:
         _lib.check(KERNEL_TIMER.call("p2w_knn", work, L.p2w_knn, _dp(x), _dp(y), _dp(ptr_x), _dp(ptr_y), T, x.size(0),
                                      y.size(0), k, _dp(nbr), _dp(d2), _stream()))

@@ -65,6 +65,17 @@ def line(name, x, y, px, py, k, **kw):
 
 def main():
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "uniform32":                     # one case for ncu
+        pos, ptr = uniform_tiles(64, 16384, 2.0, 3)
+        x, p = dev(pos), dev(ptr)
+        return line("uniform 16384-point tiles, queries = sources", x, x, p, p, 32)
+    if only == "vote":
+        plot, _ = tls_plot(1_000_000, 1)
+        q = dev(plot[:, :3])
+        rows = dev(np.concatenate([plot[:, :3], plot[::-1, :3]]))
+        one = lambda n: torch.tensor([0, n], device="cuda", dtype=torch.int64)
+        return line("spatial vote, unordered table", rows, q, one(rows.size(0)), one(q.size(0)), 64, cell=0.05, unordered=True)
     for B in (8, 64):
         pos, ptr = uniform_tiles(B, 16384, 2.0, 3)
         x, p = dev(pos), dev(ptr)
