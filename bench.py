@@ -23,7 +23,7 @@ median pwood, class votes).  File I/O (src/io.py) is outside the region on both 
             the WHOLE pipeline on a bounded sample -- every point of the 5 x 5 m corner of the plot -- and
             the value is those points over that time: nothing extrapolated.
 N > 1 (torchrun): ONE plot sharded over the ranks (pointstowood_b200/distributed.py): rank r holds a chunk of
-the rows, tiles are owned in contiguous ranges of whole batches, the vote runs on x-slabs with a halo; the
+the rows, whole batches of tiles are dealt round to the ranks, the vote runs on x-slabs with a halo; the
 result equals the single-GPU one.  `--scaling weak` (default): the plot has N x --points points (per-GPU work
 fixed); `--scaling strong`: --points points in total (BASELINE.json configs[3]: --points 100000000 --gpus 8).
 Time = max over ranks.
@@ -348,7 +348,7 @@ def main():
                       l2="no flush needed: a step streams > 4 GB of activations (e.g. the [N0, 544] and "
                          "[N0, 512] FP buffers) between two launches of any kernel, 30x the 126 MB L2")
         if world > 1:
-            config.update(partition="rows chunked over ranks; tiles owned in contiguous ranges of whole batches; vote by x-slabs "
+            config.update(partition="rows chunked over ranks; whole batches of tiles dealt round to the ranks; vote by x-slabs "
                                     f"with a {info.get('halo', args.halo):g} m halo ({info.get('vote_rounds')} round(s)); results "
                                     "identical to one GPU",
                           collective_bytes_rank0_per_step={k: v for k, v in sorted(info.get("traffic", {}).items())})

@@ -10,16 +10,16 @@ metadata-sized tables and the reflectance column:
 2. tiling (:55-64): every rank sorts ITS rows by 5-D voxel id and lists its occupied voxels with their
    counts; the lists (16 B / occupied voxel / rank) are all-gathered and merged into the plot's tile table --
    voxels with >= min_pts members, 2 m list then 4 m list by ascending id, batches of `batch_size`
-   consecutive tiles (the composition one GPU uses, src/predicter.py:177-180), contiguous ranges of
-   whole batches balanced by points per rank;
+   consecutive tiles (the composition one GPU uses, src/predicter.py:177-180), whole batches dealt round
+   to the ranks (batch b to rank b mod world: the same mix of small and large tiles everywhere);
 3. ONE all-to-all moves every tile member to the owner of its tile (24 B / tile point: x, y, z,
    reflectance, point index, tile).  Stable on both sides, so a tile's rows arrive in ascending point
    index -- the order one GPU sees;
 4. each rank classifies its batches (predicter.classify_tiles; no collective, tiles are independent);
 5. spatial vote (src/predicter.py:107-142), sharded by x-slabs with equal query counts: queries (12 B) and
-   classified rows (16 B: x, y, z, prob) go to their slab's rank by all-to-all, rows within `halo` of a
-   slab edge also to the neighbour.  Rows keep the global row order, so distance ties break as on one
-   GPU.  Every query's k-th neighbour distance is checked against its distance to the edge of the halo;
+   classified rows (20 B: x, y, z, prob, row id) go to their slab's rank by all-to-all, rows within `halo` of a
+   slab edge also to the neighbour.  Rows carry their global row id and are sorted by it on arrival, so
+   distance ties break as on one GPU.  Every query's k-th neighbour distance is checked against its distance to the edge of the halo;
    if a single query fails the bound the halo grows and the vote is redone, so the result is EXACT;
 6. (label, pwood) return to the rank that holds the row (9 B / point, all-to-all).
 
@@ -248,6 +248,13 @@ class _Kernels:
         return ops.spatial_vote(rows_xyz, prob, pred, queries, k, any_wood, return_table=True)
 
 
+def _to_dev(a, dev, dtype=np.int64) -> Tensor:
+    """Small host array to `dev` without blocking the host on CUDA (pinned staging); plain tensor on CPU."""
+    if dev.type == "cuda":
+        return _lib.to_device(a, dev, dtype)
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dtype)))
+
+
 def _bits(n: int) -> int:
     return max(1, int(max(n, 1) - 1).bit_length())
 
@@ -362,17 +369,21 @@ class ShardedPlot:
             tables.append(torch.stack([uid, starts[1: u + 1] - starts[:u]], dim=1))
         table = comm.all_gather_v(torch.cat(tables), nu_all.sum(axis=1).tolist(), "all-gather: occupied voxels")
         gid, total, kept, ordinal = merge_voxel_tables(table, self.min_pts)
-        full = total[kept].cpu().numpy()                                                               # sync 4
+        kept_host = torch.stack([total[kept], gid[kept]]).cpu().numpy()                                # sync 4
+        full, gid_kept = kept_host[0], kept_host[1]
         sizes = np.minimum(full, self.max_pts)
         T = len(sizes)
         ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-        batches = plan_batches(T, self.batch_size)
-        bb = shard_bounds(batches, ptr, W)
-        tb = np.array([batches[b][0] if b < len(batches) else T for b in bb], dtype=np.int64)      # tile bounds per rank
-        self.tile_bounds, self.tile_ptr, self.num_tiles = tb, ptr, T
-        tb_dev = _lib.to_device(tb, dev, np.int64) if dev.type == "cuda" else torch.from_numpy(tb)
+        # ownership: batch b of the plot (tiles b*B .. b*B+B-1) belongs to rank b mod W.  Consecutive batches are
+        # neighbours in the voxel order and cost about the same, so dealing them round gives every rank the same mix of
+        # 2 m and 4 m tiles (contiguous ranges balanced by points left the ranks 10 % apart in time).
+        B = self.batch_size
+        nbatch = (T + B - 1) // B
+        mine = [np.arange(b * B, min(b * B + B, T), dtype=np.int64) for b in range(r, nbatch, W)]
+        local_tiles = np.concatenate(mine) if mine else np.zeros(0, np.int64)       # global tile ids of this rank, ascending
+        self.local_tiles, self.tile_ptr, self.num_tiles = local_tiles, ptr, T
         self._mark("tile: merged voxel table + ownership")
-        # ---- members of kept voxels, ascending (tile, point index): already grouped by destination
+        # ---- members of kept voxels, ascending (tile, point index)
         pts, tiles = [], []
         for gi, (keys, order, starts, _) in enumerate(local):
             u = int(nu_all[r, gi])
@@ -386,9 +397,12 @@ class ShardedPlot:
             tiles.append(t_p[sel])
         pts = torch.cat(pts) if pts else torch.empty(0, device=dev, dtype=torch.int64)
         tiles = torch.cat(tiles) if tiles else torch.empty(0, device=dev, dtype=torch.int64)
-        dest = torch.searchsorted(tb_dev[1:].contiguous(), tiles, right=True)
+        dest = (tiles // B) % W
         send = torch.bincount(dest, minlength=W)[:W]
         cm = comm.all_gather_equal(send, "all-gather: exchange sizes").cpu().numpy()                   # sync 5
+        if W > 1 and pts.numel():                      # group by destination; stable, so (tile, point index) order survives
+            _, by_dest = K.stable_order(dest.contiguous(), _bits(W))
+            pts, tiles = pts[by_dest.long()], tiles[by_dest.long()]
         payload = torch.empty((pts.numel(), 6), device=dev, dtype=torch.int32)
         payload[:, :4] = feat[pts, :4].contiguous().view(torch.int32)
         payload[:, 4] = (pts + self.offset).to(torch.int32)
@@ -397,39 +411,46 @@ class ShardedPlot:
         recv = comm.all_to_all(payload, cm[r].tolist(), cm[:, r].tolist(), "all-to-all: tile members")
         self._mark("tile: member all-to-all")
         # ---- this rank's tiles: stable regroup by tile (sources arrive in rank order = ascending point index)
-        t0, t1 = int(tb[r]), int(tb[r + 1])
-        full_loc = full[t0:t1].astype(np.int64)
+        full_loc = full[local_tiles].astype(np.int64)
         if int(full_loc.sum()) != recv.size(0):
             raise _lib.P2WError("ShardedPlot: the member exchange delivered a different number of rows than the tile table lists")
         if recv.size(0):
-            _, perm = K.stable_order((recv[:, 5] - t0).to(torch.int64).contiguous(), _bits(t1 - t0))
+            t_recv = recv[:, 5].to(torch.int64)
+            lt = ((t_recv // B) // W) * B + t_recv % B              # local ordinal of a global tile (all but the last batch are full)
+            _, perm = K.stable_order(lt.contiguous(), _bits(len(local_tiles)))
             recv = recv[perm.long()]
         feat_loc = recv[:, :4].contiguous().view(torch.float32)
         gidx = recv[:, 4].contiguous()
         ptr_full = np.concatenate([[0], np.cumsum(full_loc)]).astype(np.int64)
-        sizes_loc = sizes[t0:t1].astype(np.int64)
+        sizes_loc = sizes[local_tiles].astype(np.int64)
         off = np.concatenate([[0], np.cumsum(sizes_loc)]).astype(np.int64)
-        grid_of_tile = np.asarray(self.grid_size, np.float32)[(gid[kept][t0:t1] >> GRID_FLAG_SHIFT).cpu().numpy()] \
-            if t1 > t0 else np.zeros(0, np.float32)
+        gid_loc = gid_kept[local_tiles]
+        grid_of_tile = np.asarray(self.grid_size, np.float32)[gid_loc >> GRID_FLAG_SHIFT]
         big = np.nonzero(full_loc > self.max_pts)[0]
         if len(big) == 0:
             members = torch.arange(recv.size(0), device=dev, dtype=torch.int64)
         else:
-            plan = torch.as_tensor(np.stack([ptr_full[:-1] - off[:-1], sizes_loc]), device=dev)
+            plan = _to_dev(np.stack([ptr_full[:-1] - off[:-1], sizes_loc]), dev)
             members = torch.arange(int(off[-1]), device=dev) + torch.repeat_interleave(plan[0], plan[1], output_size=int(off[-1]))
-            vox_all = (gid[kept][t0:t1] & ((1 << GRID_FLAG_SHIFT) - 1))
-            gsel = (gid[kept][t0:t1] >> GRID_FLAG_SHIFT).cpu().numpy()
+            vox_all = gid_loc & ((1 << GRID_FLAG_SHIFT) - 1)
+            gsel = gid_loc >> GRID_FLAG_SHIFT
             for gi in range(len(self.grid_size)):
                 bg = big[gsel[big] == gi]
                 if not len(bg):
                     continue
                 cat = torch.cat([torch.arange(int(ptr_full[v]), int(ptr_full[v + 1]), device=dev, dtype=torch.int32) for v in bg])
                 picks = K.thin(feat_loc, 3, cat, full_loc[bg], gidx, self.refl_min, self.weighted,
-                               vox_all[torch.as_tensor(bg, device=dev)].contiguous(), self.max_pts, self.seed, gi)
+                               _to_dev(vox_all[bg], dev), self.max_pts, self.seed, gi)
                 picks = picks.view(len(bg), self.max_pts).to(torch.int64)
                 for j, v in enumerate(bg.tolist()):
                     members[off[v]: off[v + 1]] = picks[j]
-        self.first_row = int(ptr[t0])          # global row index of this rank's first classified row
+        # global row id of every classified row of this rank (its position in the single-GPU, tile-major row order):
+        # the vote sorts the rows it receives by it, so equal distances break ties exactly as on one GPU
+        plan = _to_dev(np.stack([ptr[local_tiles] - off[:-1], sizes_loc]), dev)
+        self.global_rows = (torch.arange(int(off[-1]), device=dev) +
+                            torch.repeat_interleave(plan[0], plan[1], output_size=int(off[-1]))).to(torch.int32)
+        if int(ptr[-1]) >= 2 ** 31:
+            raise _lib.P2WError("ShardedPlot: classified rows are indexed in 32 bits (fewer than 2^31 tile points per plot)")
         self._mark("tile: regroup + thinning")
         return TileStore(feat=feat_loc, members=members, ptr=off, grid_of_tile=grid_of_tile)
 
@@ -443,7 +464,7 @@ class ShardedPlot:
         n = chunk.size(0)
         k = 32 if any_wood != 1 else 64                                                               # :137
         self._mark("classify")
-        bounds = torch.as_tensor(self.bounds, device=dev)
+        bounds = _to_dev(self.bounds, dev, np.float32)
         q = chunk[:, :3].contiguous()
         if W > 1 and n:
             dq = torch.searchsorted(bounds, q[:, 0].contiguous(), right=True)
@@ -454,7 +475,10 @@ class ShardedPlot:
             qorder = torch.arange(n, device=dev)
             qsend = torch.zeros(W, device=dev, dtype=torch.int64)
             qsend[r] = n
-        rows = torch.cat([xyz.reshape(-1, 3), prob.reshape(-1, 1)], dim=1).contiguous()                  # 16 B per classified row
+        # 20 B per classified row: x, y, z, prob, global row id
+        rows = torch.cat([xyz.reshape(-1, 3), prob.reshape(-1, 1)], dim=1).contiguous().view(torch.int32)
+        rows = torch.cat([rows, self.global_rows.view(-1, 1)], dim=1).contiguous()
+        row_bits = max(1, int(self.tile_ptr[-1]).bit_length())
         width = float(self.ext[1, 0]) - float(self.ext[0, 0])
         queries = None
         pending = None                 # queries still to be answered (None: all of them)
@@ -468,7 +492,7 @@ class ShardedPlot:
                 keys = torch.arange(W, device=dev).repeat(rows.size(0))
                 span = torch.full((1,), W, device=dev, dtype=torch.int64)
             else:
-                keys, span = halo_entries(rows[:, 0].contiguous(), bounds, halo, W, slots)
+                keys, span = halo_entries(xyz[:, 0].contiguous(), bounds, halo, W, slots)
             _, eorder = K.stable_order(keys, _bits(W + 1)) if keys.numel() else (None, torch.empty(0, device=dev, dtype=torch.int32))
             rsend = torch.bincount(keys, minlength=W + 1)[:W] if keys.numel() else torch.zeros(W, device=dev, dtype=torch.int64)
             top = span.max().view(1) if span.numel() else torch.zeros(1, device=dev, dtype=torch.int64)
@@ -481,7 +505,10 @@ class ShardedPlot:
                 queries = comm.all_to_all(q[qorder], qm[r].tolist(), qm[:, r].tolist(), "all-to-all: vote queries")
             entries = eorder[: int(rm[r].sum())].long()
             got = comm.all_to_all(rows[entries // slots], rm[r].tolist(), rm[:, r].tolist(), "all-to-all: classified rows")
-            rx, rp = got[:, :3].contiguous(), got[:, 3].contiguous()
+            if W > 1 and got.size(0):                      # back into the single-GPU row order
+                _, by_row = K.stable_order(got[:, 4].to(torch.int64).contiguous(), row_bits)
+                got = got[by_row.long()]
+            rx, rp = got[:, :3].contiguous().view(torch.float32), got[:, 3].contiguous().view(torch.float32)
             self._mark("vote: routing + all-to-alls")
             # later rounds only redo the queries that failed the bound (a handful of isolated points)
             todo = queries if pending is None else queries[pending]

@@ -107,10 +107,10 @@ def _vote(rows, prob, pred, queries, k):
             torch.from_numpy(nbr.astype(np.int32)))
 
 
-def _fake_prob(xyz, first_row):
+def _fake_prob(xyz, rows):
     """A stand-in for the network: depends on the coordinates AND on the global row, so duplicated points
     (one row per tile that holds them) carry different values, as real classifications do."""
-    rows = np.arange(len(xyz)) + first_row
+    rows = np.asarray(rows, dtype=np.int64)
     return ((np.sin(xyz[:, 0] * 3.1) * np.cos(xyz[:, 2] * 1.7) * 0.5 + 0.5) * 0.8 + 0.2 * ((rows * 2654435761) % 1000) / 1000.0).astype(np.float32)
 
 
@@ -128,7 +128,7 @@ def _single(cloud, weighted):
     feat5, tiles, _ = ref_pipeline.preprocess(cloud, PARAMS["grid_size"], PARAMS["min_pts"], PARAMS["max_pts"])
     members = np.concatenate(tiles)
     xyz = feat5[members, :3]
-    prob = _fake_prob(xyz, 0)
+    prob = _fake_prob(xyz, np.arange(len(xyz)))
     label, pwood, _ = _vote(xyz, prob, (prob >= 0.5).astype(np.uint8), cloud[:, :3].copy(), 64)
     return feat5, tiles, label.numpy(), pwood.numpy()
 
@@ -143,13 +143,12 @@ def _worker(rank, world, port, out, weighted, halo):
     chunk = torch.from_numpy(cloud[cuts[rank]:cuts[rank + 1]].copy())
     plot = ShardedPlot(chunk, Comm(), kernels=_oracle_kernels(), **PARAMS)
     store = plot.tile()
-    t0, t1 = int(plot.tile_bounds[rank]), int(plot.tile_bounds[rank + 1])
     feat = store.feat.numpy()
     members = store.members.numpy()
     xyz = feat[members, :3]
-    prob = torch.from_numpy(_fake_prob(xyz, plot.first_row))
+    prob = torch.from_numpy(_fake_prob(xyz, plot.global_rows.numpy()))
     label, pwood = plot.vote(torch.from_numpy(xyz.copy()), prob, 0.5, 1, halo)
-    out.put(dict(rank=rank, t0=t0, t1=t1, ptr=store.ptr.copy(), rows=feat[members].copy(), label=label.numpy(),
+    out.put(dict(rank=rank, local_tiles=plot.local_tiles.copy(), ptr=store.ptr.copy(), rows=feat[members].copy(), label=label.numpy(),
                  pwood=pwood.numpy(), lo=cuts[rank], hi=cuts[rank + 1], num_tiles=plot.num_tiles, rounds=plot.vote_rounds,
                  traffic=dict(plot.traffic), n_z=plot.n_z.numpy()))
     dist.barrier()
@@ -178,10 +177,11 @@ def test_sharded_plot_equals_single_process(world, weighted, halo):
     assert max(sizes) == PARAMS["max_pts"], "the fixture must exercise the thinning of oversized tiles"
     got = _run(world, weighted, halo)
     assert all(g["num_tiles"] == len(tiles) for g in got)
-    assert got[0]["t0"] == 0 and got[-1]["t1"] == len(tiles)
+    assert sorted(np.concatenate([g["local_tiles"] for g in got]).tolist()) == list(range(len(tiles)))     # a partition
     for g in got:
-        assert g["t0"] % PARAMS["batch_size"] == 0                        # ranks own whole batches
-        mine = tiles[g["t0"]:g["t1"]]
+        B = PARAMS["batch_size"]
+        assert all((t // B) % world == g["rank"] for t in g["local_tiles"])  # whole batches, dealt round
+        mine = [tiles[t] for t in g["local_tiles"]]
         assert np.array_equal(np.diff(g["ptr"]), [len(t) for t in mine])
         want = feat5[np.concatenate(mine), :4] if mine else np.zeros((0, 4), np.float32)
         assert np.array_equal(g["rows"], want)                              # same members, same order, same values

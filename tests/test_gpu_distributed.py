@@ -69,7 +69,7 @@ def _worker(rank, world, port, out, halo):
     chunk = torch.from_numpy(cloud[cuts[rank]:cuts[rank + 1]].copy()).cuda()
     label, pwood, plot = classify_plot(_net(), chunk, **KW, halo=halo, return_plot=True)
     out.put(dict(rank=rank, lo=cuts[rank], hi=cuts[rank + 1], label=label.cpu().numpy(), pwood=pwood.cpu().numpy(),
-                 rounds=plot.vote_rounds, tiles=plot.num_tiles, own=int(plot.tile_bounds[rank + 1] - plot.tile_bounds[rank]),
+                 rounds=plot.vote_rounds, tiles=plot.num_tiles, own=len(plot.local_tiles),
                  traffic=dict(plot.traffic)))
     dist.barrier()
     dist.destroy_process_group()
