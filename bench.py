@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--launch-points", type=int, default=1 << 21,
                     help="points of consecutive reference batches that share one launch set")
-    ap.add_argument("--halo", type=float, default=0.5, help="metres of classified rows shared across vote slabs")
+    ap.add_argument("--halo", type=float, default=1.0, help="metres of classified rows shared across vote slabs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -298,6 +298,12 @@ int p2w_reflectance_keys(const float *cloud, int32_t ld, int32_t col, int64_t n,
                          p2w_stream_t stream);
 int p2w_reflectance_normalize(const int32_t *sorted_idx, int64_t n, float *v, float *mnmx_ws,
                               float *out, p2w_stream_t stream);
+/* The two halves of p2w_reflectance_normalize for a plot ranked in key ranges over several GPUs: the values
+ * erfinv(2q-1)*sqrt(2) of the sorted positions p -> global rank rank0 + p of n_total (v[sorted_idx[p]], and
+ * their min / max in mnmx[0..1]), then -- after the ranks have min / max-reduced mnmx -- the affine map. */
+int p2w_reflectance_values(const int32_t *sorted_idx, int64_t n, int64_t rank0, int64_t n_total,
+                           float *v, float *mnmx, p2w_stream_t stream);
+int p2w_reflectance_scale(const float *v, int64_t n, const float *mnmx, float *out, p2w_stream_t stream);
 int p2w_assemble5(const float *cloud, int32_t ld, const float *refl, const float *n_z, int64_t n,
                   float *feat, p2w_stream_t stream);
 int p2w_sampling_keys(const float *feat, int32_t ld, int32_t col, const int32_t *members,

@@ -43,6 +43,13 @@ def ground_normalize(xyz: np.ndarray) -> np.ndarray:
     return (z - mins[cid]).astype(np.float32)
 
 
+def quantile_values(ranks: np.ndarray, n: int) -> np.ndarray:
+    """:24-26: rank -> (rank + 1) / (n + 1) clamped -> erfinv(2q - 1) * sqrt(2), all in FP32."""
+    q = (np.asarray(ranks).astype(np.float32) + np.float32(1.0)) / np.float32(n + 1)
+    q = np.clip(q, np.float32(1e-7), np.float32(1.0) - np.float32(1e-7))
+    return (torch.erfinv(torch.from_numpy(np.float32(2.0) * q - np.float32(1.0))) * torch.sqrt(torch.tensor(2.0))).numpy()
+
+
 def quantile_normalize_reflectance(refl: np.ndarray) -> np.ndarray:
     """:18-30 with a stable sort."""
     refl = np.ascontiguousarray(refl, dtype=np.float32)
@@ -50,9 +57,7 @@ def quantile_normalize_reflectance(refl: np.ndarray) -> np.ndarray:
     order = np.argsort(refl, kind="stable")
     ranks = np.empty(n, dtype=np.int64)
     ranks[order] = np.arange(n)
-    q = (ranks.astype(np.float32) + np.float32(1.0)) / np.float32(n + 1)
-    q = np.clip(q, np.float32(1e-7), np.float32(1.0) - np.float32(1e-7))
-    v = (torch.erfinv(torch.from_numpy(np.float32(2.0) * q - np.float32(1.0))) * torch.sqrt(torch.tensor(2.0))).numpy()
+    v = quantile_values(ranks, n)
     mn, mx = v.min(), v.max()
     return (np.float32(2.0) * (v - mn) / (mx - mn) - np.float32(1.0)).astype(np.float32)
 

@@ -59,6 +59,8 @@ SIGNATURES = {
     "p2w_ground_normalize": (c_int32, [_P, c_int32, c_int64, _P, c_float, c_int32, c_int32, _P, _P, _P]),
     "p2w_reflectance_keys": (c_int32, [_P, c_int32, c_int32, c_int64, _P, _P]),
     "p2w_reflectance_normalize": (c_int32, [_P, c_int64, _P, _P, _P, _P]),
+    "p2w_reflectance_values": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "p2w_reflectance_scale": (c_int32, [_P, c_int64, _P, _P, _P]),
     "p2w_assemble5": (c_int32, [_P, c_int32, _P, _P, c_int64, _P, _P]),
     "p2w_sampling_keys": (c_int32, [_P, c_int32, c_int32, _P, _P, c_int64, c_float, ctypes.c_uint32, _P, _P]),
     "p2w_replacement_picks": (c_int32, [_P, _P, _P, c_int32, c_int32, ctypes.c_uint64, _P, _P]),

@@ -69,13 +69,15 @@ __global__ void __launch_bounds__(256) refl_keys_kernel(const float *__restrict_
     if (i < n) keys[i] = sortable(cloud[i * ld + col]);
 }
 
+// sorted position p of this call holds global rank rank0 + p of n_total values (a sharded plot ranks a key range per GPU)
 __global__ void __launch_bounds__(256) refl_normal_kernel(const int32_t *__restrict__ sorted_idx, int64_t n,
-                                                          float *__restrict__ v, float *__restrict__ mnmx) {
+                                                          int64_t rank0, int64_t n_total, float *__restrict__ v,
+                                                          float *__restrict__ mnmx) {
     const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     float val = 0.f;
     const bool ok = p < n;
     if (ok) {
-        float q = __fdiv_rn(__fadd_rn(static_cast<float>(p), 1.0f), static_cast<float>(n + 1));
+        float q = __fdiv_rn(__fadd_rn(static_cast<float>(rank0 + p), 1.0f), static_cast<float>(n_total + 1));
         q = fminf(fmaxf(q, 1e-7f), 1.0f - 1e-7f);
         val = __fmul_rn(erfinvf(__fsub_rn(__fmul_rn(2.0f, q), 1.0f)), 1.41421354f);
         v[sorted_idx[p]] = val;
@@ -192,15 +194,27 @@ extern "C" int p2w_reflectance_keys(const float *cloud, int32_t ld, int32_t col,
     return check_launch("p2w_reflectance_keys");
 }
 
+extern "C" int p2w_reflectance_values(const int32_t *sorted_idx, int64_t n, int64_t rank0, int64_t n_total, float *v,
+                                      float *mnmx, p2w_stream_t stream) {
+    P2W_REQUIRE(rank0 >= 0 && rank0 + n <= n_total, "p2w_reflectance_values: ranks outside [0, n_total)");
+    cudaStream_t st = as_stream(stream);
+    P2W_LAUNCH(fill_kernel, 1, 32, 0, st)(mnmx, 1, kPosInf);
+    P2W_LAUNCH(fill_kernel, 1, 32, 0, st)(mnmx + 1, 1, kNegInf);
+    if (n) P2W_LAUNCH(refl_normal_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(sorted_idx, n, rank0, n_total, v, mnmx);
+    return check_launch("p2w_reflectance_values");
+}
+
+extern "C" int p2w_reflectance_scale(const float *v, int64_t n, const float *mnmx, float *out, p2w_stream_t stream) {
+    if (n == 0) return P2W_OK;
+    P2W_LAUNCH(refl_scale_kernel, (unsigned)(((n) + 255) / 256), 256, 0, as_stream(stream))(v, n, mnmx, out);
+    return check_launch("p2w_reflectance_scale");
+}
+
 extern "C" int p2w_reflectance_normalize(const int32_t *sorted_idx, int64_t n, float *v, float *mnmx_ws, float *out,
                                          p2w_stream_t stream) {
-    cudaStream_t st = as_stream(stream);
     if (n == 0) return P2W_OK;
-    P2W_LAUNCH(fill_kernel, 1, 32, 0, st)(mnmx_ws, 1, kPosInf);
-    P2W_LAUNCH(fill_kernel, 1, 32, 0, st)(mnmx_ws + 1, 1, kNegInf);
-    P2W_LAUNCH(refl_normal_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(sorted_idx, n, v, mnmx_ws);
-    P2W_LAUNCH(refl_scale_kernel, (unsigned)(((n) + 255) / 256), 256, 0, st)(v, n, mnmx_ws, out);
-    return check_launch("p2w_reflectance_normalize");
+    const int rc = p2w_reflectance_values(sorted_idx, n, 0, n, v, mnmx_ws, stream);
+    return rc ? rc : p2w_reflectance_scale(v, n, mnmx_ws, out, stream);
 }
 
 extern "C" int p2w_assemble5(const float *cloud, int32_t ld, const float *refl, const float *n_z, int64_t n,

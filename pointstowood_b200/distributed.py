@@ -2,11 +2,11 @@
 
 One process per GPU (`torch.distributed`, NCCL).  Rank r holds a CONTIGUOUS CHUNK of the plot's rows
 (rows o_r .. o_r + n_r of the file, rank order = row order) and nothing is replicated except
-metadata-sized tables and the reflectance column:
+metadata-sized tables:
 
 1. statistics: column min / max, 5 m ground cells (src/preprocessing.py:37-53) -- all-reduce MIN over a few
-   KB; reflectance ranks (:18-30) need the global order: the column is all-gathered (4 B / point) and ranked
-   on every rank, each rank keeps its slice;
+   KB; reflectance ranks (:18-30) need the global order: a distributed sort by key ranges (8 B / point out,
+   4 B / point back, all-to-all), stable in the point index like one sort of the whole column;
 2. tiling (:55-64): every rank sorts ITS rows by 5-D voxel id and lists its occupied voxels with their
    counts; the lists (16 B / occupied voxel / rank) are all-gathered and merged into the plot's tile table --
    voxels with >= min_pts members, 2 m list then 4 m list by ascending id, batches of `batch_size`
@@ -44,8 +44,10 @@ __all__ = ["shard_bounds", "shard_contiguous", "all_gather_rows", "merge_voxel_t
            "Comm", "ShardedPlot", "classify_plot", "GRID_FLAG_SHIFT"]
 
 GRID_FLAG_SHIFT = 58          # voxel ids of the g-th grid size travel as id | g << 58
-DEFAULT_HALO = 0.5            # metres; the k-th neighbour of a TLS point is centimetres away
+DEFAULT_HALO = 1.0            # metres; the k-th neighbour of a TLS point is centimetres away (0.5 m needed a second
+                              # round for a handful of isolated points on the 16 M and 100 M-point plots)
 HIST_BINS = 4096
+REFL_BINS = 4096              # top 12 bits of the 32-bit reflectance key
 
 
 # ------------------------------------------------------------------------------------------ host-side plans
@@ -203,17 +205,24 @@ class _Kernels:
                                                nby, cell_min.data_ptr(), n_z.data_ptr(), _stream()))
         return n_z
 
-    def reflectance_normalize(self, column: Tensor) -> Tensor:
-        """quantile_normalize_reflectance (src/preprocessing.py:18-30) of a whole column."""
-        n = column.numel()
-        L = _lib.lib()
-        keys = torch.empty(n, device=column.device, dtype=torch.int64)
-        _lib.check(L.p2w_reflectance_keys(column.data_ptr(), 1, 0, n, keys.data_ptr(), _stream()))
-        _, order = ops.sort_pairs(keys, 32)
-        v = torch.empty(n, device=column.device, dtype=torch.float32)
-        out = torch.empty(n, device=column.device, dtype=torch.float32)
-        mnmx = torch.empty(2, device=column.device, dtype=torch.float32)
-        _lib.check(L.p2w_reflectance_normalize(order.data_ptr(), n, v.data_ptr(), mnmx.data_ptr(), out.data_ptr(), _stream()))
+    def reflectance_keys(self, cloud: Tensor) -> Tensor:
+        """int64 [n]: order-preserving 32-bit keys of the reflectance column (src/preprocessing.py:22's sort key)."""
+        keys = torch.empty(cloud.size(0), device=cloud.device, dtype=torch.int64)
+        _lib.check(_lib.lib().p2w_reflectance_keys(cloud.data_ptr(), cloud.stride(0), 3, cloud.size(0), keys.data_ptr(), _stream()))
+        return keys
+
+    def reflectance_values(self, order: Tensor, rank0: int, n_total: int):
+        """(v [n] with v[order[p]] = the normal score of global rank rank0 + p, mnmx [2] = min / max of v) (:24-26)."""
+        n = order.numel()
+        v = torch.empty(n, device=order.device, dtype=torch.float32)
+        mnmx = torch.empty(2, device=order.device, dtype=torch.float32)
+        _lib.check(_lib.lib().p2w_reflectance_values(order.data_ptr(), n, rank0, n_total, v.data_ptr(), mnmx.data_ptr(), _stream()))
+        return v, mnmx
+
+    def reflectance_scale(self, v: Tensor, mnmx: Tensor) -> Tensor:
+        """2 (v - min) / (max - min) - 1 (:27-29)."""
+        out = torch.empty_like(v)
+        _lib.check(_lib.lib().p2w_reflectance_scale(v.data_ptr(), v.numel(), mnmx.data_ptr(), out.data_ptr(), _stream()))
         return out
 
     def assemble5(self, cloud: Tensor, refl: Optional[Tensor], n_z: Tensor) -> Tensor:
@@ -289,6 +298,42 @@ class ShardedPlot:
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
 
+    # ---------------------------------------------------------------- reflectance ranks (src/preprocessing.py:18-30)
+    def _rank_reflectance(self, keys: Tensor, hist: np.ndarray) -> Tensor:
+        """quantile_normalize_reflectance over the whole plot without gathering it: rank r sorts the keys of ONE key
+        range (ranges cut from the plot-wide histogram so that they hold equal counts).  Keys travel to their range's
+        rank in point order and are sorted stably there, so equal reflectances rank by point index as one stable
+        sort of the whole column would; a value's global rank is its range's offset + its sorted position, the
+        normal scores go back the way the keys came, and min / max are reduced over the ranks before the affine map."""
+        K, comm = self.K, self.comm
+        W, r = comm.world, comm.rank
+        dev, n = keys.device, keys.numel()
+        if W == 1:
+            _, order = K.stable_order(keys, 32)
+            v, mnmx = K.reflectance_values(order, 0, n)
+            return K.reflectance_scale(v, mnmx)
+        cum = np.cumsum(hist)
+        cuts = np.array([np.searchsorted(cum, cum[-1] * i / W, side="left") + 1 for i in range(1, W)], dtype=np.int64)
+        cuts = np.maximum.accumulate(cuts)                                    # first bin of ranges 1 .. W-1
+        dest = torch.searchsorted(_to_dev(cuts, dev), (keys >> 20).contiguous(), right=True)
+        send = torch.bincount(dest, minlength=W)[:W]
+        cm = comm.all_gather_equal(send, "all-gather: exchange sizes").cpu().numpy()                   # sync
+        if n:
+            _, by_dest = K.stable_order(dest.contiguous(), _bits(W))
+            by_dest = by_dest.long()
+        else:
+            by_dest = torch.empty(0, device=dev, dtype=torch.int64)
+        got = comm.all_to_all(keys[by_dest], cm[r].tolist(), cm[:, r].tolist(),
+                              "all-to-all: reflectance keys")
+        _, order = K.stable_order(got, 32) if got.numel() else (None, torch.empty(0, device=dev, dtype=torch.int32))
+        rank0 = int(cm[:, :r].sum())
+        v, mnmx = K.reflectance_values(order, rank0, self.total)
+        mm = comm.all_reduce(torch.stack([mnmx[0], -mnmx[1]]), "MIN", "all-reduce: reflectance min / max")
+        back = comm.all_to_all(v, cm[:, r].tolist(), cm[r].tolist(), "all-to-all: reflectance scores")
+        home = torch.empty(n, device=dev, dtype=torch.float32)
+        home[by_dest] = back
+        return K.reflectance_scale(home, torch.stack([mm[0], -mm[1]]).contiguous())
+
     # ---------------------------------------------------------------- 1-3: tiling and the member exchange
     def tile(self) -> TileStore:
         K, comm, chunk = self.K, self.comm, self.chunk
@@ -302,9 +347,15 @@ class ShardedPlot:
         flags = torch.stack([torch.tensor(n, device=dev), torch.isnan(chunk[:, 3]).sum(),
                              (~torch.isfinite(chunk[:, :3])).any(dim=1).sum()]).to(torch.int64)
         flags = comm.all_gather_equal(flags, "all-gather: row counts")
-        host = torch.cat([mm.double(), flags.view(-1).double()]).cpu().numpy()                       # sync 1
+        # reflectance keys and their plot-wide histogram (top 12 of 32 bits): the splitters of the distributed ranking
+        rkeys = K.reflectance_keys(chunk) if n else torch.empty(0, device=dev, dtype=torch.int64)
+        rhist = torch.bincount(rkeys >> 20, minlength=REFL_BINS)[:REFL_BINS].to(torch.float64) if W > 1 else \
+            torch.zeros(REFL_BINS, device=dev, dtype=torch.float64)
+        rhist = comm.all_reduce(rhist, "SUM", "all-reduce: reflectance histogram")
+        host = torch.cat([mm.double(), flags.view(-1).double(), rhist]).cpu().numpy()                 # sync 1
         ext = np.stack([host[:4], -host[4:8]]).astype(np.float32)
-        flags_h = host[8:].reshape(W, 3).astype(np.int64)
+        flags_h = host[8: 8 + 3 * W].reshape(W, 3).astype(np.int64)
+        rhist_h = host[8 + 3 * W:]
         if flags_h[:, 1].sum() > 0:
             raise ValueError("Input reflectance tensor contains NaN values.")
         if flags_h[:, 2].sum() > 0:
@@ -329,10 +380,7 @@ class ShardedPlot:
         self.n_z = n_z
         # ---- reflectance (:18-30): ranks are global, so the column is ranked whole on every rank
         self.weighted = bool(ext[0, 3] != 0 or ext[1, 3] != 0)
-        refl = None
-        if self.weighted:
-            column = comm.all_gather_v(chunk[:, 3].contiguous(), self.counts, "all-gather: reflectance column")
-            refl = K.reflectance_normalize(column)[self.offset: self.offset + n].contiguous()
+        refl = self._rank_reflectance(rkeys, rhist_h) if self.weighted else None
         self._mark("tile: ground + reflectance ranks")
         feat = K.assemble5(chunk, refl, n_z)
         mn5, mx5 = K.colminmax(feat)

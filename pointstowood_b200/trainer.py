@@ -148,21 +148,62 @@ def make_training_batch(cloud: Tensor, labels: Tensor, tiles, tile_ids, device=N
     return M.make_data(pos, refl, batch, sf, ptr=bptr, local_shift=shift.reshape(-1), y=labels[members].float())
 
 
+def broadcast_module_(net: nn.Module, src: int = 0) -> None:
+    """Every parameter AND buffer (BatchNorm running statistics) of `net` from rank `src` to all ranks, in a few
+    flat buckets per dtype.  Replicas of a data-parallel run must start from the same weights: averaging gradients
+    keeps equal what starts equal, nothing more."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    tensors = [p.data for p in net.parameters()] + [b.data for b in net.buffers()]
+    by_dtype: Dict[torch.dtype, List[Tensor]] = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for group in by_dtype.values():
+        flat = torch.cat([t.reshape(-1) for t in group])
+        dist.broadcast(flat, src=src)
+        o = 0
+        for t in group:
+            t.copy_(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
+
+
 def SemanticTraining(args):
     """src/trainer.py:96-320 reduced to the optimisation loop: args.net (optional), args.batches (an iterable
-    of collated batches with .y), args.num_epochs; AdamW(lr 1e-4, wd 1e-2) + Poly1FocalLoss(mean, gamma 2,
-    alpha None, label_smoothing 0.1) as the reference; data-parallel when torch.distributed is initialised."""
+    of collated batches with .y), args.num_epochs; AdamW(lr 1e-4, wd 1e-2) + OneCycleLR(max_lr 1e-4, total_steps =
+    num_epochs, pct_start 0.05, cos, div_factor 100) stepped once per epoch (:122-123,219) + Poly1FocalLoss(mean,
+    gamma 2, alpha None, label_smoothing 0.1) as the reference.  Data-parallel when torch.distributed is
+    initialised: rank 0's parameters and buffers are broadcast before the first step (a fresh Net is built under
+    the reference's seed 141190, src/trainer.py:25-26), gradients are averaged every step, BatchNorm statistics stay
+    local to a rank during training and RANK 0's are the ones that are saved.  With args.wdir / args.model the
+    final weights are written by rank 0 as {'model_state_dict': ...} (:304-306), the format load_model reads."""
     device = torch.device("cuda")
-    net = getattr(args, "net", None) or M.Net(num_classes=1).to(device)
+    net = getattr(args, "net", None)
+    if net is None:
+        torch.manual_seed(141190)
+        net = M.Net(num_classes=1).to(device)
     freeze_constant_gate(net)
+    broadcast_module_(net, src=0)
     criterion = Poly1FocalLoss(reduction="mean", gamma=2.0, alpha=None, label_smoothing=0.1)
     optimizer = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-2)
+    epochs = int(getattr(args, "num_epochs", 1))
+    scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=1e-4, total_steps=max(epochs, 2), pct_start=0.05,
+                                                    anneal_strategy="cos", div_factor=100)
     allreduce = GradientAllReduce(list(net.parameters()))
-    history = []
-    for _ in range(getattr(args, "num_epochs", 1)):
+    history, lrs = [], []
+    for epoch in range(epochs):
+        lrs.append(optimizer.param_groups[0]["lr"])
         for data in args.batches:
             out = train_step(net, optimizer, criterion, data, allreduce,
                              autocast_bf16=getattr(args, "autocast_bf16", False))
             history.append(float(out["loss"]))
-    args.net, args.history = net, history
+        if epoch + 1 < max(epochs, 2):
+            scheduler.step()
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    if rank == 0 and getattr(args, "wdir", None) and getattr(args, "model", None):
+        import os
+        os.makedirs(os.path.join(args.wdir, "model"), exist_ok=True)
+        torch.save({"model_state_dict": net.state_dict()}, os.path.join(args.wdir, "model", args.model))
+    args.net, args.history, args.lr_history = net, history, lrs
     return args

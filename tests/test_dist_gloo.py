@@ -133,3 +133,34 @@ def test_gradient_all_reduce_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in got)
+
+
+def _worker_broadcast(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pointstowood_b200.trainer import broadcast_module_
+    torch.manual_seed(100 + rank)                                       # replicas that start DIFFERENT
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 1))
+    net[1].running_mean.uniform_(-1, 1)
+    net[1].num_batches_tracked.fill_(3 + rank)
+    broadcast_module_(net, src=0)
+    flat = torch.cat([t.detach().double().reshape(-1) for t in list(net.parameters()) + list(net.buffers())])
+    got = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(got, flat)
+    out.put((rank, bool(all(torch.equal(g, got[0]) for g in got)), int(net[1].num_batches_tracked)))
+    dist.destroy_process_group()
+
+
+def test_replicas_start_from_rank_0_weights_and_buffers():
+    """SemanticTraining's first collective: parameters and BatchNorm buffers of rank 0 on every rank."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_broadcast, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in got) and all(nbt == 3 for _, _, nbt in got)

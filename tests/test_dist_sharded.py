@@ -50,8 +50,20 @@ def _oracle_kernels():
             cid = self._cells(c[:, 0], mn_xy[0].item(), nbx) * (nby + 1) + self._cells(c[:, 1], mn_xy[1].item(), nby)
             return torch.from_numpy((c[:, 2] - cell_min.numpy()[cid]).astype(np.float32))
 
-        def reflectance_normalize(self, column):
-            return torch.from_numpy(ref_pipeline.quantile_normalize_reflectance(column.numpy()))
+        def reflectance_keys(self, cloud):
+            b = cloud[:, 3].contiguous().numpy().view(np.uint32).astype(np.int64)
+            return torch.from_numpy(np.where(b & 0x80000000, (~b) & 0xFFFFFFFF, b | 0x80000000))
+
+        def reflectance_values(self, order, rank0, n_total):
+            o = order.numpy().astype(np.int64)
+            v = np.empty(len(o), np.float32)
+            v[o] = ref_pipeline.quantile_values(rank0 + np.arange(len(o)), n_total)
+            mnmx = np.array([v.min() if len(v) else np.inf, v.max() if len(v) else -np.inf], np.float32)
+            return torch.from_numpy(v), torch.from_numpy(mnmx)
+
+        def reflectance_scale(self, v, mnmx):
+            mn, mx = mnmx.numpy().astype(np.float32)
+            return torch.from_numpy((np.float32(2.0) * (v.numpy() - mn) / (mx - mn) - np.float32(1.0)).astype(np.float32))
 
         def assemble5(self, cloud, refl, n_z):
             r = cloud[:, 3] if refl is None else refl
@@ -191,6 +203,8 @@ def test_sharded_plot_equals_single_process(world, weighted, halo):
     if halo < 0.1:                 # a 2 cm halo cannot hold the 64 nearest rows: the bound check must have widened it
         assert got[0]["rounds"] > 1
     assert any("all-to-all: tile members" in g["traffic"] for g in got)
+    if weighted:
+        assert all("all-to-all: reflectance keys" in g["traffic"] for g in got)
 
 
 def test_slab_bounds_and_halo_entries():

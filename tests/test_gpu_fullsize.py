@@ -165,8 +165,48 @@ def test_one_million_point_plot_properties():
     p2, q2, l2, w2 = run(1 << 21)
     assert torch.equal(p1, p2) and torch.equal(q1, q2) and torch.equal(l1, l2) and torch.equal(w1, w2), "non-deterministic"
     p3, q3, l3, w3 = run(1 << 19)                           # four launch sets instead of one
-    # (bf16 GEMMs may pick another blocking for another row count: probabilities move in the last bf16 bits)
-    assert (q1 == q3).float().mean().item() >= 0.995 and (p1 - p3).abs().max().item() <= 5e-2
-    assert (l1 == l3).float().mean().item() >= 0.995
+    # north_star, bf16: 1e-2 on the probabilities, 99.9 % of the labels (measured on B200: identical, tools/parity_bf16.py;
+    # a GEMM that picked another blocking for another row count would move a probability in its last bf16 bits)
+    assert (q1 == q3).float().mean().item() >= 0.999 and (p1 - p3).abs().max().item() <= 1e-2
+    assert (l1 == l3).float().mean().item() >= 0.999
     assert bool(((w1 >= 0) & (w1 <= 1)).all()) and bool((l1 <= 1).all()) and bool(torch.isfinite(p1).all())
     assert p1.numel() == int(a.ptr[-1]) and l1.numel() == len(cloud)
+
+
+def test_bf16_matches_fp32_and_the_oracle_on_the_whole_plot():
+    """The benchmarked precision at the benchmark's size (BASELINE.json north_star): bf16 against fp32 on EVERY tile
+    point of the 1 M-point plot -- |dp| <= 1e-2 and >= 99.9 % equal labels at --is-wood 0.5 -- and both against the
+    CPU oracle on four full batches spread over the tile list (fp32 1e-3, bf16 1e-2).  Seeded random weights (the
+    checkpoint is not shipped).  Measured on B200 (profiles/r2_parity_bf16.txt): max |dp| 1.2e-3, labels identical."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle import ref_model, ref_pipeline
+    from pointstowood_b200 import model as M
+    from pointstowood_b200.predicter import classify_tiles
+    from pointstowood_b200.preprocessing import Voxelise
+    from pointstowood_b200.synthetic import tls_plot
+    cloud, _ = tls_plot(1_000_000, 1)
+    dev = torch.from_numpy(cloud).cuda()
+    sd = ref_model.seeded_state_dict()
+    net = M.Net(num_classes=1)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    store = Voxelise(dev, minpoints=128, maxpoints=16384, gridsize=(2.0, 4.0)).write_voxels()
+    res = {}
+    for prec in ("fp32", "bf16"):
+        prob, pred, _, _ = classify_tiles(net.set_precision(prec), store, 8, 0.5)
+        res[prec] = (prob.float().cpu().numpy(), pred.cpu().numpy())
+    d = np.abs(res["bf16"][0] - res["fp32"][0])
+    assert d.size == int(store.ptr[-1]) > 1_900_000
+    assert d.max() <= 1e-2, f"bf16 differs from fp32 by {d.max()}"
+    assert (res["bf16"][1] == res["fp32"][1]).mean() >= 0.999
+    feat, members = store.feat.cpu().numpy(), store.members.cpu().numpy()
+    tiles = [members[store.ptr[t]:store.ptr[t + 1]] for t in range(store.num_tiles)]
+    nb = (store.num_tiles + 7) // 8
+    for b in np.linspace(0, nb - 1, 4).round().astype(int):
+        ref = ref_pipeline.classify(sd, feat, tiles[b * 8:(b + 1) * 8], 8, 0.5)
+        lo, hi = int(store.ptr[b * 8]), int(store.ptr[min((b + 1) * 8, store.num_tiles)])
+        for prec, tol in (("fp32", 1e-3), ("bf16", 1e-2)):
+            err = np.abs(res[prec][0][lo:hi] - ref[:, 4].astype(np.float32)).max()
+            assert err <= tol, f"{prec} differs from the oracle by {err} on batch {b}"
+            assert (res[prec][1][lo:hi] == ref[:, 3].astype(np.uint8)).mean() >= 0.999

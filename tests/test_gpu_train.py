@@ -98,3 +98,27 @@ def test_training_batch_from_tile_store(mods):
     data = trainer_mod.make_training_batch(dev, torch.from_numpy(label).cuda(), store, [0, 1, 2])
     assert data.pos.size(0) == data.y.numel() == int(store.ptr[3]) and data.sf.numel() == 3
     assert set(torch.unique(data.y).tolist()) <= {0.0, 1.0}
+
+
+def test_semantic_training_schedule_and_checkpoint(mods, golden_dir, tmp_path):
+    """src/trainer.py:120-123,219,304-306: OneCycleLR from 1e-6 stepped per epoch, final weights saved as
+    {'model_state_dict': ...} -- the file load_model reads back."""
+    from types import SimpleNamespace
+    model_mod, trainer_mod = mods
+    _, data, _ = _fixture_batch(model_mod, golden_dir)
+    args = SimpleNamespace(net=_net(model_mod, trainer_mod), batches=[data], num_epochs=40, wdir=str(tmp_path), model="m.pth")
+    out = trainer_mod.SemanticTraining(args)
+    assert len(out.history) == 40 and np.isfinite(out.history).all()
+    # torch's OneCycleLR(max_lr 1e-4, total_steps 40, pct_start 0.05, cos, div_factor 100): 1e-6, 1e-4, then cosine decay
+    assert abs(out.lr_history[0] - 1e-6) < 1e-11 and abs(out.lr_history[1] - 1e-4) < 1e-11
+    assert max(out.lr_history) <= 1e-4 + 1e-12 and out.lr_history[-1] < out.lr_history[2] < out.lr_history[1]
+    ckpt = torch.load(os.path.join(str(tmp_path), "model", "m.pth"), map_location="cpu")
+    assert set(ckpt) == {"model_state_dict"}
+    fresh = model_mod.Net(num_classes=1)
+    model_mod.load_model(os.path.join(str(tmp_path), "model", "m.pth"), fresh, torch.device("cpu"))
+    for k, v in out.net.state_dict().items():
+        assert torch.equal(v.cpu(), fresh.state_dict()[k]), k
+    # a fresh Net is built under the reference's seed: two calls without args.net start from identical weights
+    a = trainer_mod.SemanticTraining(SimpleNamespace(net=None, batches=[], num_epochs=1)).net
+    b = trainer_mod.SemanticTraining(SimpleNamespace(net=None, batches=[], num_epochs=1)).net
+    assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))

@@ -25,7 +25,7 @@ from pointstowood_b200.synthetic import tls_plot_blocks  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("points", type=int, nargs="?", default=4_000_000)
 ap.add_argument("--check", action="store_true")
-ap.add_argument("--halo", type=float, default=0.5)
+ap.add_argument("--halo", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=2)
 args = ap.parse_args()
 
