@@ -10,6 +10,8 @@
 // tensor never exists in HBM.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace p2w {
@@ -372,9 +374,23 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
                        const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
                        bool packed, const int64_t *tgt_index);
 size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out);
+// conv_tc_g2.cu: the two-gather-group variant, used for hidden <= 64 (SA1) unless P2W_CONV_G2=0
+int p2w_conv_tc2_launch(const void *x, int x_bf16, const float *pos_src, const float *pos_tgt, const int32_t *nbr,
+                        int64_t n_src, int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out,
+                        const float *w1, const float *b1, const float *w2, const float *b2, const float *bn_scale,
+                        const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
+                        bool packed, const int64_t *tgt_index);
+size_t p2w_conv_tc2_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out);
+static bool use_g2(int hidden) {
+    static const int v = [] { const char *e = getenv("P2W_CONV_G2"); return e ? atoi(e) : 1; }();
+    return v != 0 && hidden <= 64;
+}
 
 extern "C" size_t p2w_pointnet_conv_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out, int32_t mode) {
-    if (mode == P2W_CONV_BF16_TC) return p2w_conv_tc_ws_bytes(c_in, hidden, c_out);
+    if (mode == P2W_CONV_BF16_TC) {
+        const size_t a = p2w_conv_tc_ws_bytes(c_in, hidden, c_out), b = p2w_conv_tc2_ws_bytes(c_in, hidden, c_out);
+        return a > b ? a : b;
+    }
     return sizeof(float) * (static_cast<size_t>(c_in + 4) * hidden + static_cast<size_t>(hidden) * c_out) + 256;
 }
 
@@ -397,6 +413,10 @@ static int conv_dispatch(const void *xv, int32_t x_dtype, const float *pos_src, 
                 "p2w_pointnet_conv_max: workspace too small");
     if (n_tgt == 0) return P2W_OK;
     cudaStream_t st = as_stream(stream);
+    if (mode == P2W_CONV_BF16_TC && use_g2(hidden))
+        return p2w_conv_tc2_launch(xv, x_dtype == P2W_BF16, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out,
+                                   w1, b1, w2, b2, bn_scale, bn_shift, outv, out_dtype == P2W_BF16, ws, ws_bytes, st,
+                                   packed, tgt_index);
     if (mode == P2W_CONV_BF16_TC)
         return p2w_conv_tc_launch(xv, x_dtype == P2W_BF16, pos_src, pos_tgt, nbr, n_src, n_tgt, k, c_in, hidden, c_out,
                                   w1, b1, w2, b2, bn_scale, bn_shift, outv, out_dtype == P2W_BF16, ws, ws_bytes, st,

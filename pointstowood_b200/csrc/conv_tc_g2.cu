@@ -1,3 +1,5 @@
+// conv_tc_g2.cu -- the H <= 64 (SA1) instantiation of conv_tc.cu: TWO gather groups, register reallocation and
+// pipelined TMEM loads in epilogue 2 (see the comments at the role split); everything else as in
 // conv_tc.cu -- K5 on the 5th-generation tensor cores: fused gather -> per-edge MLP -> max with
 // BF16 operands, FP32 accumulation in TMEM (tcgen05.mma, cta_group::1, M=128 x N=128 x K=16).
 //
@@ -202,7 +204,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K1p, int H, int stages, in
     return L;
 }
 
-__global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(THREADS, 2) conv_tc2_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const SmemLayout L = smem_layout(p.K1p, p.H, p.stages, p.msg_bufs);
     const int MB = p.msg_bufs;
@@ -416,8 +418,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcParams 
                 for (int o = 16; o; o >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(FULL, nrm, o));
                 const float den = nrm + 1e-8f;
                 uint4 g;
-                g.x = pack_bf16(dx / den, dy / den);
-                g.y = pack_bf16(dz / den, ps0.w);
+                const float inv = 1.f / den;        // one division; the quotients are rounded to bf16 right below
+                g.x = pack_bf16(dx * inv, dy * inv);
+                g.y = pack_bf16(dz * inv, ps0.w);
                 g.z = 0x00003F80u;                 // column C+4 = 1.0: carries b1 through the contraction
                 g.w = 0;
                 *reinterpret_cast<uint4 *>(msg + CPR * LBO1 + n * 16) = g;
@@ -640,7 +643,7 @@ inline TcPlan tc_plan(int c_in, int hidden, int c_out) {
 using namespace p2w;
 
 #ifdef P2W_CONV_INSTRUMENT
-extern "C" int p2wdbg_conv_timeline(long long *dst_host, int n) {
+extern "C" int p2wdbg_conv2_timeline(long long *dst_host, int n) {
     static long long host[16 * 512];
     cudaMemcpyFromSymbol(host, g_timeline, sizeof(host));
     int cnt = 0;
@@ -653,9 +656,9 @@ extern "C" int p2wdbg_conv_timeline(long long *dst_host, int n) {
 }
 #endif
 
-size_t p2w_conv_tc_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out) { return tc_plan(c_in, hidden, c_out).total; }
+size_t p2w_conv_tc2_ws_bytes(int32_t c_in, int32_t hidden, int32_t c_out) { return tc_plan(c_in, hidden, c_out).total; }
 
-int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
+int p2w_conv_tc2_launch(const void *x, int x_bf16, const float *pos_src, const float *pos_tgt, const int32_t *nbr, int64_t n_src,
                        int64_t n_tgt, int32_t k, int32_t c_in, int32_t hidden, int32_t c_out, const float *w1,
                        const float *b1, const float *w2, const float *b2, const float *bn_scale,
                        const float *bn_shift, void *out, int out_bf16, void *ws, size_t ws_bytes, cudaStream_t st,
@@ -739,12 +742,12 @@ int p2w_conv_tc_launch(const void *x, int x_bf16, const float *pos_src, const fl
         if (sm_count <= 0) sm_count = kNumSMs;
     }
     if (L.total > smem_set) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
         smem_set = L.total;
     }
     const int per_sm = (L.total <= 113 * 1024) ? 2 : 1;     // TMEM: 2 x 256 columns fit one SM
     int grid = sm_count * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    P2W_LAUNCH(conv_tc_kernel, grid, THREADS, L.total, st)(p);
+    P2W_LAUNCH(conv_tc2_kernel, grid, THREADS, L.total, st)(p);
     return check_launch("p2w_pointnet_conv_max(bf16)");
 }

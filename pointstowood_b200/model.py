@@ -318,9 +318,11 @@ class Net(nn.Module):
     def engine(self):
         """The eval-mode executor for the current weights / precision (re-folded when either changes)."""
         from .engine import InferenceEngine
-        tensors = list(self.parameters()) + list(self.buffers())
+        tensors = getattr(self, "_engine_tensors", None)
+        if tensors is None:          # the module tree is fixed: walk it once (the walk alone cost ~0.5 ms per forward)
+            tensors = self._engine_tensors = list(self.parameters()) + list(self.buffers())
         key = (self.inference_dtype, self.conv_mode, tensors[0].device, sum(t._version for t in tensors),
-               tuple(t.data_ptr() for t in tensors[:4]))
+               tensors[0].data_ptr(), tensors[-1].data_ptr())
         if self._engine is None or self._engine[0] != key:
             self._engine = (key, InferenceEngine(self, self.inference_dtype, self.conv_mode))
         return self._engine[1]
