@@ -168,7 +168,8 @@ class InferenceEngine:
             if lvl["res"] == 0.04:                                     # src/model.py:117-118
                 nbr, _ = ops.radius_table(pos, pos[idx], lvl["res"] * 2, ptr, ptr_t, lvl["k"])
             else:
-                nbr = ops.knn_table(pos, pos[idx], lvl["k"], ptr, ptr_t)
+                # the fused conv takes a max over a row: the neighbour SET is all it needs (P2W_KNN_UNORDERED)
+                nbr = ops.knn_table(pos, pos[idx], lvl["k"], ptr, ptr_t, unordered=True)
             pos4, back = ops.sa_prepare(pos, refl, ptr, sf)
             if self.conv_mode == ops.CONV_BF16_TC:          # targets addressed through idx: no pos4[idx] gather
                 # the kernel rounds the rows to bf16 as it gathers them (each ~14 times): round them once instead

@@ -347,3 +347,29 @@ def test_fps_random_start_follows_torchs_generator(ops):
     assert np.array_equal(out[np.concatenate([[0], np.cumsum(m)[:-1]])], start)       # first pick = the drawn row
     out2 = ops.fps(_dev(src), ratio=0.25, random_start=True, ptr=_dev(ptr)).cpu().numpy()
     assert not np.array_equal(out, out2)                                                # the generator moved on
+
+
+@pytest.mark.parametrize("k", [16, 32, 64])
+def test_unordered_knn_table_is_the_same_set(ops, k):
+    """P2W_KNN_UNORDERED: every row holds the same neighbours as the ordered table, and its k-th neighbour sits in
+    the first or in the last column (the heap kernel leaves its root first; the ordered kernels may ignore the flag)."""
+    from pointstowood_b200.synthetic import tls_plot
+    cloud, _ = tls_plot(120_000, 9, side=7.0)
+    rng = np.random.default_rng(4)
+    tid = (cloud[:, 0] > 3.5).astype(np.int64) * 2 + (cloud[:, 1] > 3.5)
+    order = np.argsort(tid, kind="stable")
+    x = np.ascontiguousarray(cloud[order, :3])
+    x[:40] = x[0]                                                 # a cluster of identical points: d = 0 ties
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(tid, minlength=4))]).astype(np.int64)
+    qsel = np.sort(rng.choice(len(x), 40_000, replace=False))
+    y = x[qsel] + (rng.random((len(qsel), 3)) < 0.5) * np.float32(1e-3)      # half of the queries ARE sources
+    y = y.astype(np.float32)
+    ptr_y = np.searchsorted(qsel, ptr).astype(np.int64)
+    dx, dy, dpx, dpy = _dev(x), _dev(y), _dev(ptr), _dev(ptr_y)
+    want, d2 = ops.knn_table(dx, dy, k, dpx, dpy, return_d2=True, method="grid")
+    got = ops.knn_table(dx, dy, k, dpx, dpy, method="grid", unordered=True)
+    assert torch.equal(torch.sort(got, dim=1).values, torch.sort(want, dim=1).values)
+    kth = want[:, k - 1]
+    assert bool(((got[:, 0] == kth) | (got[:, k - 1] == kth)).all())
+    ref = O.knn(x, y[:2000], k, ptr, np.minimum(ptr_y, 2000))
+    assert np.array_equal(np.sort(got[:2000].cpu().numpy(), 1), np.sort(ref, 1))
