@@ -575,17 +575,18 @@ class ShardedPlot:
             need = torch.zeros(2, device=dev, dtype=torch.float64)
             bad = None
             if todo.size(0):
-                # the k-th neighbour sits in the first or in the last column (unordered / ordered table)
+                # the k-th neighbour sits in the first or in the last column (unordered / ordered table); FP32 is enough:
+                # the bound carries a millimetre of slack
                 ends = nbr[:, [0, k - 1]].long()
                 if rx.size(0):
-                    far = (todo[:, None, :] - rx[ends.clamp(min=0)]).double().pow(2).sum(2).sqrt().max(dim=1).values
+                    far = (todo[:, None, :] - rx[ends.clamp(min=0)]).pow(2).sum(2).sqrt().max(dim=1).values
                 else:
-                    far = torch.full((todo.size(0),), math.inf, device=dev, dtype=torch.float64)
+                    far = torch.full((todo.size(0),), math.inf, device=dev, dtype=torch.float32)
                 far = torch.where((ends < 0).any(dim=1), torch.full_like(far, math.inf), far)
-                qx = todo[:, 0].double()
+                qx = todo[:, 0]
                 margin = torch.minimum(qx - lo, hi - qx)
                 bad = far >= margin
-                need = torch.stack([bad.sum().double(), torch.where(bad, far - margin, torch.zeros_like(far)).max()])
+                need = torch.stack([bad.sum().double(), torch.where(bad, far - margin, torch.zeros_like(far)).max().double()])
             need = comm.all_reduce(need, "MAX", "all-reduce: halo check").cpu().numpy()                # sync
             self._mark("vote: halo check")
             if need[0] == 0:
