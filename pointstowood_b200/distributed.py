@@ -417,10 +417,21 @@ class ShardedPlot:
             tables.append(torch.stack([uid, starts[1: u + 1] - starts[:u]], dim=1))
         table = comm.all_gather_v(torch.cat(tables), nu_all.sum(axis=1).tolist(), "all-gather: occupied voxels")
         gid, total, kept, ordinal = merge_voxel_tables(table, self.min_pts)
-        kept_host = torch.stack([total[kept], gid[kept]]).cpu().numpy()                                # sync 4
-        full, gid_kept = kept_host[0], kept_host[1]
+        # this rank's share of every kept voxel, per grid size (before the host copy, so that ONE copy brings the tile
+        # table AND the number of members this rank will send)
+        mine_u = []
+        for gi, (keys, order, starts, _) in enumerate(local):
+            u = int(nu_all[r, gi])
+            g = torch.searchsorted(gid, keys[starts[:u]] | (gi << GRID_FLAG_SHIFT))
+            t_u = torch.where(kept[g], ordinal[g], torch.full_like(g, -1)) if u else g
+            cnt_u = starts[1: u + 1] - starts[:u]
+            kept_cnt = torch.where(t_u >= 0, cnt_u, torch.zeros_like(cnt_u))
+            mine_u.append((t_u, kept_cnt, starts[:u]))
+        sent = torch.stack([m[1].sum() for m in mine_u])
+        kept_host = torch.cat([total[kept], gid[kept], sent]).cpu().numpy()                           # sync 4
+        T = (len(kept_host) - len(mine_u)) // 2
+        full, gid_kept, sent_h = kept_host[:T], kept_host[T: 2 * T], kept_host[2 * T:]
         sizes = np.minimum(full, self.max_pts)
-        T = len(sizes)
         ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         # ownership: batch b of the plot (tiles b*B .. b*B+B-1) belongs to rank b mod W.  Consecutive batches are
         # neighbours in the voxel order and cost about the same, so dealing them round gives every rank the same mix of
@@ -434,15 +445,15 @@ class ShardedPlot:
         # ---- members of kept voxels, ascending (tile, point index)
         pts, tiles = [], []
         for gi, (keys, order, starts, _) in enumerate(local):
-            u = int(nu_all[r, gi])
-            if u == 0:
+            t_u, kept_cnt, st_u = mine_u[gi]
+            m = int(sent_h[gi])
+            if m == 0:
                 continue
-            g = torch.searchsorted(gid, keys[starts[:u]] | (gi << GRID_FLAG_SHIFT))
-            t_u = torch.where(kept[g], ordinal[g], torch.full_like(g, -1))
-            t_p = torch.repeat_interleave(t_u, starts[1: u + 1] - starts[:u], output_size=n)
-            sel = torch.nonzero(t_p >= 0).view(-1)
-            pts.append(order[sel].long())
-            tiles.append(t_p[sel])
+            # member j of kept voxel u sits at order[starts[u] + j]; dropped voxels repeat zero times
+            src0 = st_u - (torch.cumsum(kept_cnt, 0) - kept_cnt)
+            src = torch.arange(m, device=dev) + torch.repeat_interleave(src0, kept_cnt, output_size=m)
+            pts.append(order[src].long())
+            tiles.append(torch.repeat_interleave(t_u, kept_cnt, output_size=m))
         pts = torch.cat(pts) if pts else torch.empty(0, device=dev, dtype=torch.int64)
         tiles = torch.cat(tiles) if tiles else torch.empty(0, device=dev, dtype=torch.int64)
         dest = (tiles // B) % W
