@@ -153,8 +153,10 @@ class Voxelise:
         n = feat.size(0)
         mn, mx = ops._colminmax(feat)
         ext = torch.stack([mn, mx]).cpu().numpy()                       # one round trip for every grid size
+        self._feat_ext = ext
         L = _lib.lib()
-        for size in self.gridsize:
+        queued = []
+        for size in self.gridsize:                                       # all grid sizes are enqueued first ...
             cells = 1
             for d in range(feat.size(1)):
                 cells *= int(np.float32(ext[1, d] - ext[0, d]) / np.float32(size)) + 1
@@ -167,6 +169,8 @@ class Voxelise:
             ws = torch.empty(max(int(L.p2w_unique_ws_bytes(n)), 8), device=feat.device, dtype=torch.uint8)
             _lib.check(L.p2w_unique_last(keys.data_ptr(), order.data_ptr(), n, None, None, buf[1:].data_ptr(),
                                          buf.data_ptr(), ws.data_ptr(), _stream()))
+            queued.append((size, cells, keys, order, buf))
+        for size, cells, keys, order, buf in queued:                     # ... then read back: one wait for all of them
             bound = min(int(cells), n)                                   # occupied voxels <= cells of the box
             if bound <= (1 << 22):
                 host = buf[: bound + 2].cpu().numpy()
@@ -241,7 +245,7 @@ class Voxelise:
             src = torch.arange(int(off[-1]), device=dev) + torch.repeat_interleave(plan[0], plan[1], output_size=int(off[-1]))
             members = order[src].to(torch.int64)
             if len(big):                                                # thinned tiles overwrite their placeholder rows
-                refl_min = float(feat[:, 3].min().item())
+                refl_min = float(self._feat_ext[0, 3])                    # min of the normalised reflectance (:99)
                 where = {int(v): i for i, v in enumerate(keep.tolist())}
                 vox = keys[torch.as_tensor(seg[big], device=dev)].contiguous()
                 for v, picked in zip(big.tolist(), self._thin(feat, order, seg, big, refl_min, reflectance_not_zero,
