@@ -47,7 +47,7 @@ GRID_FLAG_SHIFT = 58          # voxel ids of the g-th grid size travel as id | g
 DEFAULT_HALO = 1.0            # metres; the k-th neighbour of a TLS point is centimetres away (0.5 m needed a second
                               # round for a handful of isolated points on the 16 M and 100 M-point plots)
 HIST_BINS = 4096
-REFL_BINS = 4096              # top 12 bits of the 32-bit reflectance key
+REFL_SAMPLE = 4096            # keys per rank in the splitter sample of the distributed reflectance ranking
 
 
 # ------------------------------------------------------------------------------------------ host-side plans
@@ -264,6 +264,14 @@ def _to_dev(a, dev, dtype=np.int64) -> Tensor:
     return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dtype)))
 
 
+def _sorted_counts(sorted_keys: Tensor, nbins: int) -> Tensor:
+    """int64 [nbins]: how many of the SORTED non-negative keys equal 0 .. nbins-1 (nbins is the world size: a
+    histogram kernel would serialise a million atomics on two to eight counters; the stable sort that groups the
+    rows by destination has the boundaries for free)."""
+    edges = torch.searchsorted(sorted_keys, torch.arange(nbins + 1, device=sorted_keys.device, dtype=sorted_keys.dtype))
+    return edges[1:] - edges[:-1]
+
+
 def _bits(n: int) -> int:
     return max(1, int(max(n, 1) - 1).bit_length())
 
@@ -299,12 +307,14 @@ class ShardedPlot:
         return out
 
     # ---------------------------------------------------------------- reflectance ranks (src/preprocessing.py:18-30)
-    def _rank_reflectance(self, keys: Tensor, hist: np.ndarray) -> Tensor:
+    def _rank_reflectance(self, keys: Tensor) -> Tensor:
         """quantile_normalize_reflectance over the whole plot without gathering it: rank r sorts the keys of ONE key
-        range (ranges cut from the plot-wide histogram so that they hold equal counts).  Keys travel to their range's
-        rank in point order and are sorted stably there, so equal reflectances rank by point index as one stable
-        sort of the whole column would; a value's global rank is its range's offset + its sorted position, the
-        normal scores go back the way the keys came, and min / max are reduced over the ranks before the affine map."""
+        range.  The ranges come from a sample (REFL_SAMPLE evenly spaced keys per rank, all-gathered and sorted on every
+        rank: the same splitters everywhere, ranges of nearly equal counts; any splitters give the exact result).  Keys
+        travel to their range's rank in point order and are sorted stably there, so equal reflectances rank by point
+        index as one stable sort of the whole column would; a value's global rank is its range's offset + its sorted
+        position, the normal scores go back the way the keys came, and min / max are reduced over the ranks before
+        the affine map."""
         K, comm = self.K, self.comm
         W, r = comm.world, comm.rank
         dev, n = keys.device, keys.numel()
@@ -312,17 +322,21 @@ class ShardedPlot:
             _, order = K.stable_order(keys, 32)
             v, mnmx = K.reflectance_values(order, 0, n)
             return K.reflectance_scale(v, mnmx)
-        cum = np.cumsum(hist)
-        cuts = np.array([np.searchsorted(cum, cum[-1] * i / W, side="left") + 1 for i in range(1, W)], dtype=np.int64)
-        cuts = np.maximum.accumulate(cuts)                                    # first bin of ranges 1 .. W-1
-        dest = torch.searchsorted(_to_dev(cuts, dev), (keys >> 20).contiguous(), right=True)
-        send = torch.bincount(dest, minlength=W)[:W]
-        cm = comm.all_gather_equal(send, "all-gather: exchange sizes").cpu().numpy()                   # sync
         if n:
-            _, by_dest = K.stable_order(dest.contiguous(), _bits(W))
+            sample = keys[(torch.arange(REFL_SAMPLE, device=dev) * n) // REFL_SAMPLE]
+        else:
+            sample = torch.full((REFL_SAMPLE,), (1 << 32) - 1, device=dev, dtype=torch.int64)
+        pool, _ = K.stable_order(comm.all_gather_equal(sample, "all-gather: reflectance sample").view(-1).contiguous(), 32)
+        cuts = pool[(torch.arange(1, W, device=dev) * pool.numel()) // W].contiguous()      # first key of ranges 1 .. W-1
+        dest = torch.searchsorted(cuts, keys, right=True)
+        if n:
+            sorted_dest, by_dest = K.stable_order(dest.contiguous(), _bits(W))
             by_dest = by_dest.long()
+            send = _sorted_counts(sorted_dest, W)
         else:
             by_dest = torch.empty(0, device=dev, dtype=torch.int64)
+            send = torch.zeros(W, device=dev, dtype=torch.int64)
+        cm = comm.all_gather_equal(send, "all-gather: exchange sizes").cpu().numpy()                   # sync
         got = comm.all_to_all(keys[by_dest], cm[r].tolist(), cm[:, r].tolist(),
                               "all-to-all: reflectance keys")
         _, order = K.stable_order(got, 32) if got.numel() else (None, torch.empty(0, device=dev, dtype=torch.int32))
@@ -347,15 +361,10 @@ class ShardedPlot:
         flags = torch.stack([torch.tensor(n, device=dev), torch.isnan(chunk[:, 3]).sum(),
                              (~torch.isfinite(chunk[:, :3])).any(dim=1).sum()]).to(torch.int64)
         flags = comm.all_gather_equal(flags, "all-gather: row counts")
-        # reflectance keys and their plot-wide histogram (top 12 of 32 bits): the splitters of the distributed ranking
         rkeys = K.reflectance_keys(chunk) if n else torch.empty(0, device=dev, dtype=torch.int64)
-        rhist = torch.bincount(rkeys >> 20, minlength=REFL_BINS)[:REFL_BINS].to(torch.float64) if W > 1 else \
-            torch.zeros(REFL_BINS, device=dev, dtype=torch.float64)
-        rhist = comm.all_reduce(rhist, "SUM", "all-reduce: reflectance histogram")
-        host = torch.cat([mm.double(), flags.view(-1).double(), rhist]).cpu().numpy()                 # sync 1
+        host = torch.cat([mm.double(), flags.view(-1).double()]).cpu().numpy()                        # sync 1
         ext = np.stack([host[:4], -host[4:8]]).astype(np.float32)
         flags_h = host[8: 8 + 3 * W].reshape(W, 3).astype(np.int64)
-        rhist_h = host[8 + 3 * W:]
         if flags_h[:, 1].sum() > 0:
             raise ValueError("Input reflectance tensor contains NaN values.")
         if flags_h[:, 2].sum() > 0:
@@ -380,7 +389,7 @@ class ShardedPlot:
         self.n_z = n_z
         # ---- reflectance (:18-30): ranks are global, so the column is ranked whole on every rank
         self.weighted = bool(ext[0, 3] != 0 or ext[1, 3] != 0)
-        refl = self._rank_reflectance(rkeys, rhist_h) if self.weighted else None
+        refl = self._rank_reflectance(rkeys) if self.weighted else None
         self._mark("tile: ground + reflectance ranks")
         feat = K.assemble5(chunk, refl, n_z)
         mn5, mx5 = K.colminmax(feat)
@@ -457,11 +466,14 @@ class ShardedPlot:
         pts = torch.cat(pts) if pts else torch.empty(0, device=dev, dtype=torch.int64)
         tiles = torch.cat(tiles) if tiles else torch.empty(0, device=dev, dtype=torch.int64)
         dest = (tiles // B) % W
-        send = torch.bincount(dest, minlength=W)[:W]
+        if pts.numel():                                # group by destination; stable, so (tile, point index) order survives
+            sorted_dest, by_dest = K.stable_order(dest.contiguous(), _bits(W))
+            send = _sorted_counts(sorted_dest, W)
+            if W > 1:
+                pts, tiles = pts[by_dest.long()], tiles[by_dest.long()]
+        else:
+            send = torch.zeros(W, device=dev, dtype=torch.int64)
         cm = comm.all_gather_equal(send, "all-gather: exchange sizes").cpu().numpy()                   # sync 5
-        if W > 1 and pts.numel():                      # group by destination; stable, so (tile, point index) order survives
-            _, by_dest = K.stable_order(dest.contiguous(), _bits(W))
-            pts, tiles = pts[by_dest.long()], tiles[by_dest.long()]
         payload = torch.empty((pts.numel(), 6), device=dev, dtype=torch.int32)
         payload[:, :4] = feat[pts, :4].contiguous().view(torch.int32)
         payload[:, 4] = (pts + self.offset).to(torch.int32)
@@ -527,9 +539,9 @@ class ShardedPlot:
         q = chunk[:, :3].contiguous()
         if W > 1 and n:
             dq = torch.searchsorted(bounds, q[:, 0].contiguous(), right=True)
-            _, qorder = K.stable_order(dq.contiguous(), _bits(W))
+            sorted_dq, qorder = K.stable_order(dq.contiguous(), _bits(W))
             qorder = qorder.long()
-            qsend = torch.bincount(dq, minlength=W)[:W]
+            qsend = _sorted_counts(sorted_dq, W)
         else:
             qorder = torch.arange(n, device=dev)
             qsend = torch.zeros(W, device=dev, dtype=torch.int64)
@@ -552,8 +564,12 @@ class ShardedPlot:
                 span = torch.full((1,), W, device=dev, dtype=torch.int64)
             else:
                 keys, span = halo_entries(xyz[:, 0].contiguous(), bounds, halo, W, slots)
-            _, eorder = K.stable_order(keys, _bits(W + 1)) if keys.numel() else (None, torch.empty(0, device=dev, dtype=torch.int32))
-            rsend = torch.bincount(keys, minlength=W + 1)[:W] if keys.numel() else torch.zeros(W, device=dev, dtype=torch.int64)
+            if keys.numel():
+                sorted_keys, eorder = K.stable_order(keys, _bits(W + 1))
+                rsend = _sorted_counts(sorted_keys, W)
+            else:
+                eorder = torch.empty(0, device=dev, dtype=torch.int32)
+                rsend = torch.zeros(W, device=dev, dtype=torch.int64)
             top = span.max().view(1) if span.numel() else torch.zeros(1, device=dev, dtype=torch.int64)
             cm = comm.all_gather_equal(torch.cat([qsend, rsend, top]), "all-gather: exchange sizes").cpu().numpy()   # sync
             if not everything and int(cm[:, -1].max()) > slots:      # a row touches more slabs than slots: widen

@@ -27,6 +27,7 @@ ap.add_argument("points", type=int, nargs="?", default=4_000_000)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--halo", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--timeline", action="store_true", help="rank 0: CUPTI kernel list of one sharded pass (torch.profiler)")
 args = ap.parse_args()
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -63,6 +64,25 @@ if args.check:
                          float(plot.num_tiles == store.num_tiles)], device="cuda", dtype=torch.float64)
     dist.all_reduce(same, op=dist.ReduceOp.SUM)
     res.update(label_agreement=same[0].item() / n, pwood_identical=same[1].item() / n, same_tile_count=same[2].item() == world)
+if args.timeline:
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        classify_plot(net, chunk, halo=args.halo)
+        torch.cuda.synchronize()
+    if rank == 0:
+        ev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for e in ev:
+            m = re.search(r"(\w+)(<[^(]*>)?\(", e.name)
+            name = (m.group(1) + (m.group(2) or "")) if m else e.name
+            agg[name[:80]][0] += 1
+            agg[name[:80]][1] += e.time_range.end - e.time_range.start
+        span = ev[-1].time_range.end - ev[0].time_range.start
+        print(f"# rank 0: span {span / 1e3:.2f} ms, kernel time sum {sum(v[1] for v in agg.values()) / 1e3:.2f} ms, {len(ev)} device activities")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+            print(f"{v[1]:10.1f} us {v[0]:5d} x  {k}")
 if rank == 0:
     print(json.dumps(res))
 dist.destroy_process_group()
