@@ -13,6 +13,9 @@
 // entry per lane and slot, sorted across the warp, and a candidate enters by a ballot +
 // shuffle insertion only when it beats the current k-th entry lexicographically -- so the
 // result is independent of the scan order and bit-identical to the serial insertion sort.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "topk.cuh"
 
@@ -382,6 +385,118 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ sr
     }
 }
 
+// ---- K3 on a thread-block CLUSTER: eight CTAs (eight SMs) share one tile.  A round of farthest point sampling is
+// a reduction over the whole tile followed by a broadcast of the winner, 4 096 times in a row for a 16 384-point tile
+// at ratio 0.25, so the latency of ONE round is the whole cost.  With one 1 024-thread CTA per tile (above) a round is
+// ~16 distance updates per thread, two block barriers and a dependent global load of the winner's coordinates
+// (2.7 us); here a CTA of 256 threads keeps 8 points per thread in registers (2 048 points per CTA), reduces them to
+// one candidate WITH its coordinates, and the eight candidates meet through distributed shared memory: every CTA
+// reads the eight slots of the cluster (`map_shared_rank`), so all of them know the next reference point after ONE
+// cluster barrier per round (slots are double-buffered by round parity).  Same arithmetic, same tie rule (lowest
+// index), hence the same samples as the single-CTA kernel and the oracle.
+constexpr int FPSC_T = 256, FPSC_PT = 8, FPSC_C = 8;
+constexpr int FPSC_SPAN = FPSC_T * FPSC_C;             // points visited per register slot across the cluster
+
+struct __align__(16) FpsSlot {
+    float v;
+    int i;
+    float x, y, z;
+    int pad[3];
+};
+
+__device__ __forceinline__ bool fps_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__global__ void __cluster_dims__(FPSC_C, 1, 1) __launch_bounds__(FPSC_T)
+    fps_cluster_kernel(const float *__restrict__ src, const int64_t *__restrict__ ptr, const int64_t *__restrict__ out_ptr,
+                       float *__restrict__ dist_ws, int64_t *__restrict__ out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ FpsSlot slot[2];
+    __shared__ FpsSlot red[FPSC_T / 32];
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int b = blockIdx.x / FPSC_C;
+    const int64_t s0 = ptr[b];
+    const int n = static_cast<int>(ptr[b + 1] - s0);
+    const int64_t o0 = out_ptr[b];
+    const int m = static_cast<int>(out_ptr[b + 1] - o0);
+    if (m <= 0 || n <= 0) return;                      // the same for every CTA of the cluster
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int g = rank * FPSC_T + t;                   // 0 .. 2047: this thread's first point
+    float px[FPSC_PT], py[FPSC_PT], pz[FPSC_PT], pd[FPSC_PT];
+#pragma unroll
+    for (int u = 0; u < FPSC_PT; u++) {
+        const int i = g + u * FPSC_SPAN;
+        const bool ok = i < n;
+        px[u] = ok ? src[(s0 + i) * 3 + 0] : 0.f;
+        py[u] = ok ? src[(s0 + i) * 3 + 1] : 0.f;
+        pz[u] = ok ? src[(s0 + i) * 3 + 2] : 0.f;
+        pd[u] = 5e4f;
+    }
+    for (int i = g + FPSC_PT * FPSC_SPAN; i < n; i += FPSC_SPAN) dist_ws[s0 + i] = 5e4f;
+    float lx = src[s0 * 3 + 0], ly = src[s0 * 3 + 1], lz = src[s0 * 3 + 2];
+    if (rank == 0 && t == 0) out[o0] = s0;
+    for (int j = 1; j < m; j++) {
+        float bv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < FPSC_PT; u++) {
+            const int i = g + u * FPSC_SPAN;
+            if (i < n) {
+                const float dx = __fsub_rn(px[u], lx), dy = __fsub_rn(py[u], ly), dz = __fsub_rn(pz[u], lz);
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                const float v = pd[u] < d ? pd[u] : d;
+                pd[u] = v;
+                if (v > bv) { bv = v; bi = i; bx = px[u]; by = py[u]; bz = pz[u]; }      // i ascends with u: ties keep the lower
+            }
+        }
+        for (int i = g + FPSC_PT * FPSC_SPAN; i < n; i += FPSC_SPAN) {               // tiles beyond 16 384 points
+            const float qx = src[(s0 + i) * 3 + 0], qy = src[(s0 + i) * 3 + 1], qz = src[(s0 + i) * 3 + 2];
+            const float dx = __fsub_rn(qx, lx), dy = __fsub_rn(qy, ly), dz = __fsub_rn(qz, lz);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            const float old = dist_ws[s0 + i];
+            const float v = old < d ? old : d;
+            dist_ws[s0 + i] = v;
+            if (v > bv) { bv = v; bi = i; bx = qx; by = qy; bz = qz; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            const float ox = __shfl_xor_sync(FULL, bx, o), oy = __shfl_xor_sync(FULL, by, o), oz = __shfl_xor_sync(FULL, bz, o);
+            if (fps_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bx = ox; by = oy; bz = oz; }
+        }
+        if (lane == 0) { red[warp].v = bv; red[warp].i = bi; red[warp].x = bx; red[warp].y = by; red[warp].z = bz; }
+        __syncthreads();
+        if (warp == 0) {
+            const FpsSlot c = red[lane & (FPSC_T / 32 - 1)];
+            bv = c.v; bi = c.i; bx = c.x; by = c.y; bz = c.z;
+            for (int o = FPSC_T / 64; o; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, bv, o);
+                const int oi = __shfl_xor_sync(FULL, bi, o);
+                const float ox = __shfl_xor_sync(FULL, bx, o), oy = __shfl_xor_sync(FULL, by, o), oz = __shfl_xor_sync(FULL, bz, o);
+                if (fps_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bx = ox; by = oy; bz = oz; }
+            }
+            if (lane == 0) {
+                FpsSlot &d = slot[j & 1];
+                d.v = bv; d.i = bi; d.x = bx; d.y = by; d.z = bz;
+            }
+        }
+        cluster.sync();                                  // every CTA's candidate of this round is in its slot
+        bv = -1.f;
+        bi = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < FPSC_C; r++) {
+            const FpsSlot *p = cluster.map_shared_rank(&slot[j & 1], r);
+            const float4 a = *reinterpret_cast<const float4 *>(p);               // v, i, x, y
+            const float cz = p->z;
+            const int ci = __float_as_int(a.y);
+            if (fps_better(a.x, ci, bv, bi)) { bv = a.x; bi = ci; lx = a.z; ly = a.w; lz = cz; }
+        }
+        if (bi == 0x7fffffff) { bi = 0; lx = src[s0 * 3 + 0]; ly = src[s0 * 3 + 1]; lz = src[s0 * 3 + 2]; }
+        if (rank == 0 && t == 0) out[o0 + j] = s0 + bi;
+    }
+    cluster.sync();                                      // no CTA leaves while its slots may still be read
+}
+
 }  // namespace
 }  // namespace p2w
 
@@ -429,6 +544,14 @@ extern "C" int p2w_fps(const float *src, const int64_t *ptr, const int64_t *out_
                        float *dist_ws, int64_t *out, p2w_stream_t stream) {
     P2W_REQUIRE(num_tiles >= 1, "p2w_fps: num_tiles must be positive");
     if (n == 0) return P2W_OK;
-    P2W_LAUNCH(fps_kernel, num_tiles, FPS_T, 0, as_stream(stream))(src, ptr, out_ptr, dist_ws, out);
+    // Few tiles: a cluster of eight CTAs per tile (B = 8 x 16 384 points, ratio 0.25: 11.3 -> 8.0 ms on B200).  Many
+    // tiles fill the SMs with one CTA each, and eight CTAs per tile would queue in waves (B = 64: 11.3 vs 17.6 ms).
+    // P2W_FPS_CLUSTER=0 / 1 forces one of them (A/B runs; the samples are identical).
+    static const int forced = [] { const char *e = getenv("P2W_FPS_CLUSTER"); return e ? atoi(e) : -1; }();
+    const bool single = forced >= 0 ? forced == 0 : num_tiles * FPSC_C > kNumSMs * 2;
+    if (single)
+        P2W_LAUNCH(fps_kernel, num_tiles, FPS_T, 0, as_stream(stream))(src, ptr, out_ptr, dist_ws, out);
+    else
+        P2W_LAUNCH(fps_cluster_kernel, num_tiles * FPSC_C, FPSC_T, 0, as_stream(stream))(src, ptr, out_ptr, dist_ws, out);
     return check_launch("p2w_fps");
 }
