@@ -103,11 +103,12 @@ def replacement_picks(idx: np.ndarray, voxel_id: int, max_pts: int, seed: int, g
 
 
 def tile(feat5: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=16384, seed=SUBSAMPLE_SEED, weighted=True):
-    """grid() + the > max_pts branch of write_voxels (:55-64, 116-120) -> list of index arrays."""
+    """grid() + the > max_pts branch of write_voxels (:55-64, 116-120) -> list of index arrays.  `feat5` may hold more
+    than five columns (further scalar fields of the file between reflectance and n_z): ALL of them are voxelised (:58)."""
     tiles, grids = [], []
     refl_min = feat5[:, 3].min()
     for gi, size in enumerate(gridsize):
-        ids = O.grid(feat5, np.full(5, size, np.float32))
+        ids = O.grid(feat5, np.full(feat5.shape[1], size, np.float32))
         order = np.argsort(ids, kind="stable")
         sid = ids[order]
         starts = np.concatenate([[0], np.nonzero(sid[1:] != sid[:-1])[0] + 1, [len(sid)]])
@@ -136,7 +137,8 @@ def preprocess(cloud: np.ndarray, gridsize=(2.0, 4.0), min_pts=128, max_pts=1638
     if weighted:
         refl = quantile_normalize_reflectance(refl)
     feat5 = np.concatenate([cloud[:, :3], refl[:, None], n_z[:, None]], 1).astype(np.float32)
-    tiles, grids = tile(feat5, gridsize, min_pts, max_pts, seed, weighted)
+    grid_feat = np.concatenate([feat5[:, :4], cloud[:, 4:], feat5[:, 4:5]], 1).astype(np.float32) if cloud.shape[1] > 4 else feat5
+    tiles, grids = tile(grid_feat, gridsize, min_pts, max_pts, seed, weighted)
     return feat5, tiles, grids
 
 

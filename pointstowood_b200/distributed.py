@@ -282,8 +282,9 @@ class ShardedPlot:
     def __init__(self, chunk: Tensor, comm: Optional[Comm] = None, min_pts: int = 128, max_pts: int = 16384,
                  grid_size=(2.0, 4.0), batch_size: int = 8, seed: int = SUBSAMPLE_SEED, kernels: Optional[_Kernels] = None):
         self.chunk = chunk.contiguous()
-        if self.chunk.dim() != 2 or self.chunk.size(1) < 4 or self.chunk.dtype != torch.float32:
-            raise _lib.P2WError("ShardedPlot: the chunk must be float32 [n, >= 4] (x, y, z, reflectance)")
+        if self.chunk.dim() != 2 or self.chunk.size(1) != 4 or self.chunk.dtype != torch.float32:
+            raise _lib.P2WError("ShardedPlot: the chunk must be float32 [n, 4] (x, y, z, reflectance); further scalar "
+                                "columns would take part in the 5-D voxel grid (Voxelise handles them on one GPU)")
         self.comm = comm or Comm()
         self.min_pts, self.max_pts, self.grid_size, self.batch_size, self.seed = min_pts, max_pts, list(grid_size), batch_size, seed
         self.K = kernels or _Kernels()

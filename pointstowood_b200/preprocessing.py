@@ -14,6 +14,7 @@ oracle oracle/ref_pipeline.py pins the same ones):
   Efraimidis-Spirakis keys -log(u)/w, rows in draw order; without reflectance, `maxpoints` uniform
   draws WITH replacement (torch.randint, :120);
 * tiles are listed 2 m voxels first, then 4 m voxels, each by ascending voxel id (:57-63).
+Files with further scalar columns (rgb, deviation, ...) are voxelised over those columns too, as the reference does.
 Non-finite input: NaN reflectance raises ValueError as the reference does (:20-21); rows with a
 non-finite coordinate join no tile (the reference's per-tile NaN row filter, :123) and get
 n_z = NaN; `Voxelise.finite_rows` lists the rows that were tiled (None: all of them).
@@ -151,7 +152,10 @@ class Voxelise:
     def grid(self, feat: Tensor):
         out = []
         n = feat.size(0)
-        mn, mx = ops._colminmax(feat)
+        if feat.size(1) <= 8:
+            mn, mx = ops._colminmax(feat)
+        else:                                                           # more scalar fields than the kernel's eight columns
+            mn, mx = feat.min(0).values.contiguous(), feat.max(0).values.contiguous()
         ext = torch.stack([mn, mx]).cpu().numpy()                       # one round trip for every grid size
         self._feat_ext = ext
         L = _lib.lib()
@@ -229,10 +233,22 @@ class Voxelise:
         feat = torch.empty((n, 5), device=dev, dtype=torch.float32)
         _lib.check(_lib.lib().p2w_assemble5(cloud.data_ptr(), cloud.stride(0), None if refl is None else refl.data_ptr(),
                                             n_z.data_ptr(), n, feat.data_ptr(), _stream()))
+        # The reference voxelises EVERY column it holds (src/preprocessing.py:58 on self.pos): x, y, z, the normalised
+        # reflectance, whatever further scalar fields the file carried (predict.py:36-53 keeps them) and n_z -- in the
+        # frame's column order, n_z appended last when gpu_ground computed it (:52).  The tiles' rows are packed from
+        # `feat` (x, y, z, reflectance, n_z) either way.
+        n_extra = cloud.size(1) - 4 - (1 if has_nz else 0)
+        if n_extra > 0 or (has_nz and nz_col != cloud.size(1) - 1):
+            cols = [feat[:, :4]] + [cloud[:, c: c + 1] for c in range(4, cloud.size(1))]
+            if not has_nz:
+                cols.append(feat[:, 4:5])
+            grid_feat = torch.cat(cols, dim=1).contiguous()
+        else:
+            grid_feat = feat
         pieces: List[Tensor] = []
         sizes: List[np.ndarray] = []
         grids: List[np.ndarray] = []
-        for gi, (size, order, seg, keys) in enumerate(self.grid(feat)):
+        for gi, (size, order, seg, keys) in enumerate(self.grid(grid_feat)):
             counts = np.diff(seg)
             keep = np.nonzero(counts >= self.minpoints)[0]
             if not len(keep):

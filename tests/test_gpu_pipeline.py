@@ -83,6 +83,25 @@ def test_weighted_thinning_follows_the_sampling_law(plot):
     assert w[kept].mean() > w[~kept].mean()
 
 
+def test_extra_scalar_columns_take_part_in_the_voxel_grid(plot):
+    """src/preprocessing.py:58 voxelises every column the frame holds: a file with two more scalar fields (here a
+    coarse 'deviation' and a colour channel) splits tiles along them exactly as the oracle does."""
+    rng = np.random.default_rng(3)
+    extra = np.stack([rng.integers(0, 3, len(plot)).astype(np.float32) * 2.5, rng.random(len(plot)).astype(np.float32) * 3.0], 1)
+    cloud = np.concatenate([plot, extra], 1)
+    kw = dict(minpoints=128, maxpoints=4096, gridsize=(2.0, 4.0))
+    store = _tile_store(cloud, **kw)
+    feat5, tiles, grids = ref_pipeline.preprocess(cloud, kw["gridsize"], kw["minpoints"], kw["maxpoints"])
+    feat = store.feat.cpu().numpy()
+    grid_feat = np.concatenate([feat[:, :4], cloud[:, 4:], feat[:, 4:5]], 1)          # the GPU's reflectance column (see above)
+    tiles, grids = ref_pipeline.tile(grid_feat, kw["gridsize"], kw["minpoints"], kw["maxpoints"])
+    plain = _tile_store(plot, **kw)
+    assert store.num_tiles == len(tiles) and store.num_tiles != plain.num_tiles
+    members = store.members.cpu().numpy()
+    for t, ref in enumerate(tiles):
+        assert np.array_equal(members[store.ptr[t]:store.ptr[t + 1]], ref), f"tile {t} differs"
+
+
 def test_non_finite_input(plot):
     """NaN reflectance raises like the reference (:20-21); rows with a non-finite coordinate join no tile (:123)."""
     from pointstowood_b200.preprocessing import Voxelise
