@@ -208,6 +208,14 @@ int p2w_knn_interpolate_cat(const void *x, int32_t x_dtype, const float *pos_x, 
                             const void *skip, int32_t skip_dtype, int32_t c_skip, int32_t ld_out,
                             void *out, int32_t out_dtype, p2w_stream_t stream);
 
+/* The first Linear of an FPModule applied BEFORE the interpolation (src/model.py:149-152): knn_interpolate is
+ * linear with weights that sum to one, so relu([interp(x), x_skip] W^T + b) = relu(interp(x Wc^T) + (x_skip Ws^T + b)).
+ * out[q, :] = act(sum_e w_e y[nbr[q,e], :] / sum_e w_e + z[q, :]) with y = x Wc^T over the COARSE rows (y_dtype) and
+ * z = x_skip Ws^T + b over the fine rows (out_dtype; out may alias z); relu != 0 applies max(., 0).  c % 8 == 0. */
+int p2w_knn_interpolate_add(const void *y, int32_t y_dtype, const float *pos_x, const float *pos_y,
+                            const int32_t *nbr, int64_t ny, int32_t k, int32_t c, const void *z, void *out,
+                            int32_t out_dtype, int32_t relu, p2w_stream_t stream);
+
 /* ---- dense-block epilogues (src/model.py:18-85, InvertedResidualBlock in eval mode) ------------
  * What remains between two k=1 convolutions once every BatchNorm that follows a convolution is
  * folded into its weights: y = relu(x*s1 + t1), and if s2 != NULL y = relu(y*s2 + t2), per channel,

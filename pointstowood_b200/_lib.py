@@ -48,6 +48,7 @@ SIGNATURES = {
     "p2w_knn_interpolate_ex": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, c_int32, _P]),
     "p2w_knn_interpolate_cat": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int32, c_int32, c_int32,
                                           _P, c_int32, _P]),
+    "p2w_knn_interpolate_add": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_int32, _P]),
     "p2w_affine_relu": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, _P]),
     "p2w_rowdot": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_float, _P, _P]),
     "p2w_add_relu": (c_int32, [_P, _P, _P, c_int64, c_int32, _P]),

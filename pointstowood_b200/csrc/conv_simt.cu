@@ -251,6 +251,61 @@ __global__ void __launch_bounds__(256) interp_cat_kernel(const TI *__restrict__ 
     }
 }
 
+// out[q, :] = act( knn_interpolate(y)[q, :] + z[q, :] ): the first Linear of an FPModule applied BEFORE the
+// interpolation.  knn_interpolate is linear with weights that sum to one, so
+//     relu([interp(x), x_skip] W^T + b) = relu(interp(x Wc^T) + (x_skip Ws^T + b)),
+// and x Wc^T runs over the COARSE rows (2.3-4x fewer than the fine ones) while the [n_fine, C + C_skip] concatenation
+// is never built.  One warp per fine row, 16-byte channel groups; out may alias z.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) interp_add_kernel(const TI *__restrict__ y, const float *__restrict__ pos_x,
+                                                         const float *__restrict__ pos_y,
+                                                         const int32_t *__restrict__ nbr, int64_t ny, int k, int c,
+                                                         const TO *z, int relu, TO *out) {
+    const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= ny) return;
+    int j = -1;
+    float w = 0.f;
+    if (lane < k) {
+        j = nbr[q * k + lane];
+        if (j >= 0) {
+            const float dx = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 0], pos_y[q * 3 + 0]);
+            const float dy = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 1], pos_y[q * 3 + 1]);
+            const float dz = __fsub_rn(pos_x[static_cast<int64_t>(j) * 3 + 2], pos_y[q * 3 + 2]);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            w = __fdiv_rn(1.0f, fmaxf(d2, 1e-16f));
+        }
+    }
+    float den = 0.f;
+    for (int e = 0; e < k; e++) den = __fadd_rn(den, __shfl_sync(FULL, w, e));
+    const float wn = den > 0.f ? __fdiv_rn(w, den) : 0.f;
+    const int groups = c >> 3;
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+        const int g = g0 + lane;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int e = 0; e < k; e++) {          // warp-uniform trip count: the shuffles stay converged
+            const int je = __shfl_sync(FULL, j, e);
+            const float we = __shfl_sync(FULL, wn, e);
+            if (je >= 0 && g < groups) {
+                float v[8];
+                ld8(y + static_cast<int64_t>(je) * c + g * 8, v);
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] = fmaf(v[u], we, acc[u]);
+            }
+        }
+        if (g < groups) {
+            float zz[8];
+            ld8(z + q * c + g * 8, zz);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float t = acc[u] + zz[u];
+                acc[u] = relu ? fmaxf(t, 0.f) : t;
+            }
+            st8(out + q * c + g * 8, acc);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ segment max (global_max_pool)
 __global__ void __launch_bounds__(128) segment_max_kernel(const float *__restrict__ x, const int64_t *__restrict__ ptr,
                                                           int c, float *__restrict__ out) {
@@ -528,6 +583,30 @@ extern "C" int p2w_knn_interpolate_cat(const void *x, int32_t x_dtype, const flo
     }
 #undef P2W_IC
     return check_launch("p2w_knn_interpolate_cat");
+}
+
+extern "C" int p2w_knn_interpolate_add(const void *y, int32_t y_dtype, const float *pos_x, const float *pos_y,
+                                       const int32_t *nbr, int64_t ny, int32_t k, int32_t c, const void *z, void *out,
+                                       int32_t out_dtype, int32_t relu, p2w_stream_t stream) {
+    P2W_REQUIRE(k >= 1 && k <= 32, "p2w_knn_interpolate_add: k=%d outside [1,32]", k);
+    P2W_REQUIRE(c >= 8 && c % 8 == 0, "p2w_knn_interpolate_add: the channel count must be a multiple of 8");
+    auto okdt = [](int d) { return d == P2W_F32 || d == P2W_BF16; };
+    P2W_REQUIRE(okdt(y_dtype) && okdt(out_dtype), "p2w_knn_interpolate_add: unknown dtype");
+    P2W_REQUIRE(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                "p2w_knn_interpolate_add: rows must be 16-byte aligned");
+    if (ny == 0) return P2W_OK;
+    cudaStream_t st = as_stream(stream);
+    const unsigned blocks = (unsigned)((ny * 32 + 255) / 256);
+    typedef __nv_bfloat16 bf;
+#define P2W_IA(TI, TO)                                                                                                  \
+    P2W_LAUNCH((interp_add_kernel<TI, TO>), blocks, 256, 0, st)(static_cast<const TI *>(y), pos_x, pos_y, nbr, ny, k, c, \
+                                                                static_cast<const TO *>(z), relu, static_cast<TO *>(out))
+    if (y_dtype == P2W_F32 && out_dtype == P2W_F32) P2W_IA(float, float);
+    else if (y_dtype == P2W_F32) P2W_IA(float, bf);
+    else if (out_dtype == P2W_F32) P2W_IA(bf, float);
+    else P2W_IA(bf, bf);
+#undef P2W_IA
+    return check_launch("p2w_knn_interpolate_add");
 }
 
 extern "C" int p2w_segment_max(const float *x, const int64_t *ptr, int32_t num_segments, int32_t c, float *out,

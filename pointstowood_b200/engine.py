@@ -130,15 +130,23 @@ class InferenceEngine:
         self.g2 = _Lin(g[1][0].weight, g[1][0].bias, dt, True)
         gs, gt = _affine(g[1][2])
         self.g_s, self.g_t = f32(gs), f32(gt)
-        # FP modules: the trailing BN affine of each MLP is folded into the consumer of its output
+        # FP modules (src/model.py:142-153).  The trailing BN affine of each MLP is folded into the consumer of its
+        # output, and the FIRST Linear is split over its two inputs: relu([interp(x), x_skip] W^T + b) =
+        # relu(interp(x Wc^T) + (x_skip Ws^T + b)) -- the interpolation is linear and its weights sum to one, so the
+        # coarse part of the GEMM runs over the coarse rows (2.3-4x fewer) and the [n, C + C_skip] concatenation is
+        # never built (p2w_knn_interpolate_add).
         self.fp = []
         pend = None                                                    # (s, t) owed by the previous MLP's output
+        c_coarse = g[1][0].weight.size(0)                              # channels of the interpolated features
         for mod in (net.fp4_module, net.fp3_module, net.fp2_module, net.fp1_module):
             nn_ = mod.NN
-            l1 = _Lin(nn_[0][0].weight, nn_[0][0].bias, dt, True, *(pend if pend else (None, None)))
+            w1, b1 = nn_[0][0].weight, nn_[0][0].bias
+            lc = _Lin(w1[:, :c_coarse], torch.zeros_like(b1), torch.float64, False, *(pend if pend else (None, None)))
+            ls = _Lin(w1[:, c_coarse:], b1.double() + lc.b, dt, False)          # lc.b = Wc t_in: a constant survives the interpolation
             l2 = _Lin(nn_[1][0].weight, nn_[1][0].bias, dt, True)
-            self.fp.append(dict(k=mod.k, l1=l1, l2=l2))
+            self.fp.append(dict(k=mod.k, wc=lc.wt.to(dt).contiguous(), ws=ls.wt, bs=ls.b, l2=l2))
             pend = _affine(nn_[1][2])
+            c_coarse = nn_[1][0].weight.size(0)
         self.head1 = _Lin(net.conv1.weight, net.conv1.bias, dt, True, pend[0], pend[1], *_affine(net.norm))
         self.head2_w = net.conv2.weight.detach().reshape(-1).float().contiguous()       # one output channel: a row dot
         self.head2_b = float(net.conv2.bias.detach().reshape(-1)[0]) if net.conv2.weight.size(0) == 1 else None
@@ -159,6 +167,8 @@ class InferenceEngine:
         if group_ptr is None:
             group_ptr = torch.tensor([0, T], device=pos.device, dtype=torch.int64)
         x = self.stem(pos)                                             # [N0,32] fp32
+        if dt != torch.float32:
+            x = x.to(dt)                                               # one rounding serves SA1's gather and FP1's skip GEMM
         skips = [(x, pos, ptr)]
         refl = reflectance
         for lvl in self.sa:
@@ -194,8 +204,10 @@ class InferenceEngine:
         ptr_c = torch.arange(T + 1, device=pos.device, dtype=torch.int64)
         # ---- FPModules (src/model.py:148-153), coarse -> fine
         for fp, (x_skip, pos_skip, ptr_skip) in zip(self.fp, reversed(skips)):
-            buf = ops.knn_interpolate_cat(x, pos_c, pos_skip, x_skip, fp["k"], ptr_c, ptr_skip, out_dtype=dt)
-            x = fp["l2"](fp["l1"](buf))
+            y = torch.mm(x if x.dtype == dt else x.to(dt), fp["wc"])                          # coarse rows
+            z = torch.addmm(fp["bs"], x_skip if x_skip.dtype == dt else x_skip.to(dt), fp["ws"])    # fine rows
+            h = ops.knn_interpolate_add_(y, pos_c, pos_skip, z, fp["k"], ptr_c, ptr_skip, relu=True)
+            x = fp["l2"](h)
             pos_c, ptr_c = pos_skip, ptr_skip
         x = self.head1(x)
         if self.head2_b is not None and x.size(1) % 8 == 0 and x.size(1) <= 1024:

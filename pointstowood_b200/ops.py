@@ -26,7 +26,7 @@ from . import _lib
 
 __all__ = [
     "batch_to_ptr", "knn", "radius", "fps", "grid_cluster", "voxel_grid", "consecutive_cluster",
-    "knn_interpolate", "knn_interpolate_cat", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
+    "knn_interpolate", "knn_interpolate_cat", "knn_interpolate_add_", "global_max_pool", "scatter_max", "scatter_min", "knn_table", "radius_table",
     "table_to_edge_index", "voxel_sample", "pointnet_conv_max", "sa_prepare", "pack_tiles", "writeback", "spatial_vote",
     "sort_pairs", "affine_relu_", "add_relu_", "rowdot", "pointnet_conv_ws", "CONV_FP32", "CONV_BF16_TC",
 ]
@@ -506,6 +506,23 @@ def knn_interpolate_cat(x: Tensor, pos_x: Tensor, pos_y: Tensor, x_skip: Optiona
                                                   c, _dp(x_skip), _DT[x_skip.dtype] if cs else 0, cs, c + cs, _dp(out),
                                                   _DT[out.dtype], _stream()))
     return out
+
+
+def knn_interpolate_add_(y: Tensor, pos_x: Tensor, pos_y: Tensor, z: Tensor, k: int, ptr_x: Tensor, ptr_y: Tensor,
+                         relu: bool = True) -> Tensor:
+    """z <- act(knn_interpolate(y, pos_x, pos_y, k) + z) in place: an FPModule whose first Linear was applied to the
+    coarse rows (y = x @ Wc^T) and to the skip rows (z = x_skip @ Ws^T + b) separately -- the interpolation is linear
+    and its weights sum to one (src/model.py:149-152).  y: [Nx, C] and z: [Ny, C], float32 or bfloat16."""
+    if y.dtype not in _DT or z.dtype not in _DT:
+        raise _lib.P2WError("knn_interpolate_add_: rows must be float32 or bfloat16")
+    y, z = _req(y, y.dtype, "y", 2), _req(z, z.dtype, "z", 2)
+    pos_x, pos_y = _req(pos_x, torch.float32, "pos_x", 2), _req(pos_y, torch.float32, "pos_y", 2)
+    if y.size(1) != z.size(1) or z.size(0) != pos_y.size(0) or y.size(0) != pos_x.size(0):
+        raise _lib.P2WError("knn_interpolate_add_: inconsistent shapes")
+    nbr = knn_table(pos_x, pos_y, k, ptr_x, ptr_y)
+    _lib.check(_lib.lib().p2w_knn_interpolate_add(_dp(y), _DT[y.dtype], _dp(pos_x), _dp(pos_y), _dp(nbr), pos_y.size(0), k,
+                                                  y.size(1), _dp(z), _dp(z), _DT[z.dtype], 1 if relu else 0, _stream()))
+    return z
 
 
 # --------------------------------------------------------------------------- fused conv and glue

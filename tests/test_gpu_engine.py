@@ -235,3 +235,32 @@ def test_knn_interpolate_cat_equals_interpolate_then_cat(p2w):
     assert got_bf.dtype == torch.bfloat16 and (got_bf.float() - want).abs().max().item() <= 3e-2
     none = ops.knn_interpolate_cat(x, px, py, None, 2, ptr_x, ptr_y)
     assert torch.equal(none, want[:, :64])
+
+
+def test_interpolate_add_is_interpolation_after_the_linear():
+    """p2w_knn_interpolate_add: relu(interp(x Wc^T) + (x_skip Ws^T + b)) equals relu([interp(x), x_skip] W^T + b) -- the
+    identity the engine uses to run an FPModule's first Linear over the coarse rows (src/model.py:149-152)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pointstowood_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    sizes_c, sizes_f = [300, 0, 700], [900, 40, 2100]
+    ptr_c = torch.tensor([0, 300, 300, 1000], device="cuda")
+    ptr_f = torch.tensor([0, 900, 940, 3040], device="cuda")
+    pos_c = torch.rand(1000, 3, device="cuda", generator=g)
+    pos_f = torch.rand(3040, 3, device="cuda", generator=g)
+    pos_f[:50] = pos_c[:50]                                   # coincident points: the 1e-16 clamp of the weights
+    x = torch.randn(1000, 64, device="cuda", generator=g)
+    skip = torch.randn(3040, 24, device="cuda", generator=g)
+    w = torch.randn(48, 88, device="cuda", generator=g) * 0.2
+    b = torch.randn(48, device="cuda", generator=g)
+    want = torch.relu(torch.cat([ops.knn_interpolate(x, pos_c, pos_f, k=2, ptr_x=ptr_c, ptr_y=ptr_f), skip], 1) @ w.t() + b)
+    y = x @ w[:, :64].t()
+    z = skip @ w[:, 64:].t() + b
+    got = ops.knn_interpolate_add_(y, pos_c, pos_f, z.clone(), 2, ptr_c, ptr_f, relu=True)
+    rows = torch.ones(3040, dtype=torch.bool, device="cuda")
+    rows[900:940] = False                                     # tile 1 has no coarse rows: interpolation of nothing is 0 in both
+    assert torch.allclose(got[rows], want[rows], atol=1e-4, rtol=1e-4)         # FP32 GEMMs in another association
+    assert torch.equal(got[~rows], torch.relu(z[~rows]))
+    got16 = ops.knn_interpolate_add_(y.bfloat16(), pos_c, pos_f, z.bfloat16(), 2, ptr_c, ptr_f, relu=True)
+    assert (got16.float() - want).abs().max().item() <= 0.05 * want.abs().max().item()
