@@ -263,4 +263,4 @@ def test_interpolate_add_is_interpolation_after_the_linear():
     assert torch.allclose(got[rows], want[rows], atol=1e-4, rtol=1e-4)         # FP32 GEMMs in another association
     assert torch.equal(got[~rows], torch.relu(z[~rows]))
     got16 = ops.knn_interpolate_add_(y.bfloat16(), pos_c, pos_f, z.bfloat16(), 2, ptr_c, ptr_f, relu=True)
-    assert (got16.float() - want).abs().max().item() <= 0.05 * want.abs().max().item()
+    assert (got16.float() - want)[rows].abs().max().item() <= 0.05 * want[rows].abs().max().item()
