@@ -2,10 +2,13 @@
 (/root/reference/pointstowood/src/preprocessing.py:18-64, 79-127), batch packing
 (src/predicter.py:78-94 + PyG collate) and write-back (src/predicter.py:199-214).
 
-TEST INFRASTRUCTURE (checker + timed CPU arm), numpy / torch-CPU only.  PARITY UNPINNED: the
-reference has no tests for this path and its preprocessing cannot run here at all (it hard-codes
-device='cuda', :43-44,83,86, and imports torch_geometric / torch_scatter); what is restated is
-the arithmetic of the cited lines.  Where the reference is random or order-unstable the same
+TEST INFRASTRUCTURE (checker + timed CPU arm), numpy / torch-CPU only.  PARITY PINNED to reference-executed code
+since round 2: tests/golden/tiling.npz and predicter.npz are written by running the reference's OWN
+src/preprocessing.py (one textual device='cuda' -> 'cpu' substitution at load time) and src/predicter.py over
+oracle/shim (oracle/make_golden_tiling.py, make_golden_predicter.py), and this restatement reproduces them: n_z, the
+normalised reflectance, tile membership and order bit for bit; packing to the ulp of the FP32 mean; vote labels and
+pwood exactly (tests/test_oracle_tiling_golden.py, test_oracle_predicter_golden.py).  The third-party primitives under
+the shim stay unpinned (oracle.py).  Where the reference is random or order-unstable the same
 deterministic choices as the CUDA path are pinned:
   * stable sort for reflectance ranks (C.9);
   * > max_pts tiles: the reference's sampling laws on a counter-based hash instead of torch's generator (C.5):

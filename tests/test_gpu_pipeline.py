@@ -44,6 +44,23 @@ def test_tiling_is_bit_exact(plot):
         assert np.array_equal(members[store.ptr[t]:store.ptr[t + 1]], ref), f"tile {t} differs"
 
 
+def test_tiling_matches_the_reference_run(golden_dir):
+    """The CUDA tiling against tests/golden/tiling.npz, written by EXECUTING the reference's src/preprocessing.py
+    (oracle/make_golden_tiling.py): n_z bit-equal, normalised reflectance within the erfinv ulp, the same tiles with
+    the same members in the same order."""
+    import os
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = np.load(os.path.join(golden_dir, "tiling.npz"))
+    store = _tile_store(g["cloud"], minpoints=128, maxpoints=10 ** 9, gridsize=(2.0, 4.0))
+    feat = store.feat.cpu().numpy()
+    assert np.array_equal(feat[:, 4], g["n_z"])
+    assert np.abs(feat[:, 3] - g["reflectance"]).max() < 2e-6
+    ptr = g["ptr"]
+    assert store.num_tiles == len(ptr) - 1 and np.array_equal(store.ptr, ptr)
+    assert np.array_equal(store.members.cpu().numpy(), g["members"])
+
+
 def test_oversized_tiles_without_reflectance_use_draws_with_replacement(plot):
     """src/preprocessing.py:120: a cloud whose reflectance is all zero thins oversized tiles with max_pts uniform
     draws WITH replacement (torch.randint) -- same tiles as the oracle, duplicates included."""
@@ -189,3 +206,40 @@ def test_predict_cli_file_to_file(tmp_path):
     assert (got["label"].to_numpy() == label.cpu().numpy()).mean() >= 0.999
     assert np.abs(got["pwood"].to_numpy() - pwood.cpu().numpy()).max() <= 1e-3 or \
         (np.abs(got["pwood"].to_numpy() - pwood.cpu().numpy()) <= 1e-3).mean() >= 0.995
+
+
+def test_packing_and_vote_match_the_reference_run(golden_dir):
+    """K7 and the spatial vote against tests/golden/predicter.npz, written by EXECUTING the reference's src/predicter.py
+    (TestingDataset.__getitem__; PointCloudClassifier.collect_predictions with its numba compute_labels)."""
+    import os
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pointstowood_b200 import ops
+    g = np.load(os.path.join(golden_dir, "tiling.npz"))
+    p = np.load(os.path.join(golden_dir, "predicter.npz"))
+    feat5 = np.concatenate([g["cloud"][:, :3], g["reflectance"][:, None], g["n_z"][:, None]], 1).astype(np.float32)
+    tiles = [g["members"][g["ptr"][t]:g["ptr"][t + 1]] for t in p["tiles"]]
+    index = torch.from_numpy(np.concatenate(tiles)).cuda()
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum([len(t) for t in tiles])]).astype(np.int64)).cuda()
+    pos, refl, batch, shift, sf = ops.pack_tiles(torch.from_numpy(feat5).cuda(), index, ptr)
+    o = 0
+    for i, idx in enumerate(tiles):
+        n = len(idx)
+        assert np.abs(shift[i].cpu().numpy() - p[f"shift{i}"]).max() <= 2e-6       # FP64-accumulated mean vs torch's FP32 mean
+        assert np.abs(pos[o:o + n].cpu().numpy() - p[f"pos{i}"]).max() <= 4e-6
+        assert np.array_equal(refl[o:o + n].cpu().numpy(), p[f"refl{i}"])
+        assert abs(float(sf[i]) - float(p[f"sf{i}"])) <= 4e-6
+        o += n
+    rng = np.random.default_rng(7)                         # the rows oracle/make_golden_predicter.py voted on
+    rxyz = g["cloud"][g["members"], :3].astype(np.float64)
+    rprob = np.clip(0.5 + 0.45 * np.sin(3.0 * rxyz[:, 0]) * np.cos(2.0 * rxyz[:, 1]) + 0.1 * rng.normal(size=len(rxyz)), 0.0, 1.0)
+    rows = np.concatenate([rxyz, (rprob >= 0.5)[:, None].astype(np.float64), rprob[:, None]], 1)
+    xyz = torch.from_numpy(rows[:, :3].astype(np.float32)).cuda()
+    prob = torch.from_numpy(rows[:, 4].astype(np.float32)).cuda()
+    pred = torch.from_numpy(rows[:, 3].astype(np.uint8)).cuda()
+    org = torch.from_numpy(g["cloud"][:20000, :3].copy()).cuda()
+    for name, any_wood, k in (("vote", 1.0, 64), ("vote_any", 0.9, 32)):
+        label, pwood = ops.spatial_vote(xyz, prob, pred, org, k, any_wood)
+        # FP32 search and FP32 probabilities vs the reference's float64 KD-tree and float64 rows
+        assert (label.cpu().numpy() == p[f"{name}_label"]).mean() >= 0.999, name
+        assert (np.abs(pwood.cpu().numpy() - p[f"{name}_pwood"]) <= 1e-6).mean() >= 0.995, name
