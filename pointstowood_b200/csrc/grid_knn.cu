@@ -1190,13 +1190,15 @@ int grid_search(const float *x, const float *y, const int64_t *ptr_x, const int6
     const float tau = fmaxf(1.f, 0.45f * static_cast<float>(k));
     P2W_REQUIRE(cell_hint >= 0.f && cell_hint < 1e30f, "%s: bad cell size", what);
     const bool small = !radius && k <= 4;
-    // Kernel choice, measured on B200 (profiles/r2_knn_ab.txt): the per-thread heap wins the RADIUS search at the
-    // bench shapes (SA1: 1.21 -> 0.89 ms) and every search on uniform 16 384-point tiles (1.4-2.1x), but on the
-    // real SA2 / SA3 kNN (sub-sampled surfaces, ~750 sources per tile) its lanes diverge on candidate counts and on
-    // ring-2 walks and the warp-wide kernel stays ahead (0.83 vs 1.12 ms); at k = 64 (the vote) two thirds of the
-    // ~200 candidates enter a 6-level heap and it loses as well.  P2W_KNN_HEAP=1 / P2W_KNN_WARP=1 force one kernel
-    // for every k >= 5 (A/B runs; results are identical).
-    const bool heap = !small && !use_warp_kernel() && ((radius && k <= 32) || force_heap_kernel());
+    // Kernel choice, measured on B200 (profiles/r2_knn_ab.txt).  The per-thread heap wins the RADIUS search at the bench
+    // shapes (SA1: 1.21 -> 0.89 ms) and every k <= 32 search on LARGE tiles (16 384 points, uniform or TLS-like: 1.4-2.1x,
+    // BASELINE.json configs[2]); on the real SA2 / SA3 kNN (sub-sampled surfaces, ~750 sources per tile) its lanes
+    // diverge on candidate counts and ring-2 walks and the warp-wide kernel stays ahead (0.83 vs 1.12 ms); at k = 64 (the
+    // vote) two thirds of the ~200 candidates enter a 6-level heap and it loses as well.  So: the heap for the radius
+    // search, and for kNN up to k = 32 when the tiles average 8 192 sources or more.  P2W_KNN_HEAP=1 / P2W_KNN_WARP=1
+    // force one kernel for every k >= 5 (A/B runs; results are identical).
+    const bool big_tiles = nx >= static_cast<int64_t>(8192) * T;
+    const bool heap = !small && !use_warp_kernel() && ((k <= 32 && (radius || big_tiles)) || force_heap_kernel());
     if (!heap) unordered = false;                       // the other kernels always order (a valid answer to the flag)
     const float *pre_box = nullptr;
     if (T == 1 && cell_hint > 0.f && nx > 65536) {          // one plot-wide tile: the box is everybody's job
