@@ -54,7 +54,9 @@ def search(x, y, px, py, k, radius=None, cell=0.0, unordered=False):
 def line(name, x, y, px, py, k, **kw):
     ms, evals = search(x, y, px, py, k, **kw)
     byt = 12 * (x.size(0) + y.size(0)) + 16 * y.size(0) * k + 16 * px.numel()
-    out = dict(case=name, kernel="warp-per-query (round 1)" if os.environ.get("P2W_KNN_WARP") == "1" else "thread-per-query heap",
+    out = dict(case=name, kernel="warp-per-query (P2W_KNN_WARP=1)" if os.environ.get("P2W_KNN_WARP") == "1" else
+               ("thread-per-query heap (P2W_KNN_HEAP=1)" if os.environ.get("P2W_KNN_HEAP") == "1" else
+                "default dispatch (heap: radius, and kNN up to k = 32 on tiles of >= 8 192 sources; warp kernel otherwise)"),
                nx=x.size(0), ny=y.size(0), tiles=px.numel() - 1, k=k, ms=round(ms, 4), us_per_tile=round(ms * 1e3 / (px.numel() - 1), 2),
                alg_GBs=round(byt / ms / 1e6, 1), frac_hbm=round(byt / ms / 1e6 / 6542.7, 4))
     if evals:
