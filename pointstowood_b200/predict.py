@@ -105,7 +105,53 @@ def predict_file(args, point_cloud_file: str, net=None) -> str:
     return out
 
 
+def predict_file_sharded(args, point_cloud_file: str, net=None):
+    """The same flow with ONE plot sharded over the ranks of a torchrun launch (BASELINE.json configs[3]): every rank
+    reads the file, keeps its contiguous chunk of rows on its GPU, `distributed.classify_plot` tiles / classifies / votes
+    with the exchanges of DESIGN.md section 8, the per-point columns are gathered and rank 0 writes the output -- the
+    file a single GPU writes.  Returns the output path on rank 0, None elsewhere."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import model as M
+    from .distributed import Comm, classify_plot
+    rank, world = dist.get_rank(), dist.get_world_size()
+    stem = OP.splitext(OP.basename(point_cloud_file))[0]
+    out = OP.join(OP.dirname(point_cloud_file), f"{stem}_ours.{args.output_fmt}")
+    pc, headers = load_file(filename=point_cloud_file, additional_headers=True, verbose=False)
+    pc, headers, _ = preprocess_point_cloud_data(pc)
+    if pc.shape[1] != 4:
+        raise Exception("sharded prediction takes x, y, z, reflectance only: the extra scalar columns of this file would "
+                        "take part in the voxel grid (run it on one GPU)")
+    n = len(pc)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    chunk = torch.from_numpy(np.ascontiguousarray(pc.values[lo:hi], dtype=np.float32)).cuda()
+    if net is None:
+        net = M.Net(num_classes=1).cuda()
+        path = args.model if OP.isfile(args.model) else OP.join(args.wdir, "model", args.model)
+        try:
+            M.load_model(path, net, torch.device("cuda"))
+        except (KeyError, FileNotFoundError):
+            raise Exception(f"No model loaded at {path}")
+        net = net.eval().set_precision(args.precision)
+    args.net = net
+    label, pwood, plot = classify_plot(net, chunk, args.min_pts, args.max_pts, args.grid_size, args.batch_size, args.is_wood,
+                                       args.any_wood, return_plot=True)
+    comm = Comm()
+    counts = [(r + 1) * n // world - r * n // world for r in range(world)]
+    cols = [comm.all_gather_v(t, counts, "all-gather: results") for t in (plot.n_z.double(), label.double(), pwood)]
+    if rank != 0:
+        return None
+    pc = pc.copy()
+    for name, col in zip(("n_z", "label", "pwood"), cols):
+        pc[name] = col.cpu().numpy()
+    save_file(out, pc, additional_fields=list(dict.fromkeys(list(headers) + ["n_z", "label", "pwood"])), verbose=False)
+    return out
+
+
 def main(argv=None):
+    """python -m pointstowood_b200.predict ...  classifies every file on one GPU;
+    torchrun --nproc-per-node N -m pointstowood_b200.predict ...  shards every file's plot over N GPUs (same output)."""
     args = build_parser().parse_args(argv)
     import torch
     torch.set_num_threads(os.cpu_count() if args.num_procs == -1 else args.num_procs)
@@ -114,6 +160,21 @@ def main(argv=None):
     for f in args.point_cloud:
         if not OP.isfile(f):
             raise FileNotFoundError(f"Point cloud file not found: {f}")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        own_group = not dist.is_initialized()
+        if own_group:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")) % max(torch.cuda.device_count(), 1))
+            dist.init_process_group(os.environ.get("P2W_DIST_BACKEND", "nccl"))
+        net, outs = None, []
+        for f in args.point_cloud:
+            outs.append(predict_file_sharded(args, f, net))
+            net = args.net
+        if own_group:
+            dist.barrier()
+            dist.destroy_process_group()
+        return outs
     net = None
     outs = []
     for f in args.point_cloud:

@@ -100,3 +100,46 @@ def test_world_size_2_equals_single_gpu(halo):
         assert got[0]["rounds"] > 1            # a 1 cm halo fails the bound: widened, still exact
     else:
         assert got[0]["rounds"] == 1
+
+
+def _predict_worker(rank, world, port, src, ckpt):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0",
+                      P2W_DIST_BACKEND="gloo")
+    from pointstowood_b200 import predict
+    predict.main(["--point-cloud", src, "--model", ckpt, "--is-wood", "0.5", "--max_pts", "4096"])
+
+
+def test_predict_cli_sharded_writes_the_single_gpu_file(tmp_path):
+    """`torchrun -m pointstowood_b200.predict` (two ranks sharing cuda:0 over gloo here): the output file equals the one
+    a single process writes."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import pandas as pd
+    from oracle import ref_model
+    from pointstowood_b200 import io as pio
+    from pointstowood_b200 import predict
+    cloud = _cloud()[:90_000]
+    ckpt = str(tmp_path / "seeded.pth")
+    torch.save({"model_state_dict": ref_model.seeded_state_dict()}, ckpt)
+    outs = {}
+    for mode in ("single", "sharded"):
+        d = tmp_path / mode
+        d.mkdir()
+        src = str(d / "plot.ply")
+        pio.write_ply(src, pd.DataFrame(cloud, columns=["x", "y", "z", "scalar_Reflectance"]))
+        if mode == "single":
+            predict.main(["--point-cloud", src, "--model", ckpt, "--is-wood", "0.5", "--max_pts", "4096"])
+        else:
+            ctx = mp.get_context("spawn")
+            port = _free_port()
+            procs = [ctx.Process(target=_predict_worker, args=(r, 2, port, src, ckpt)) for r in range(2)]
+            for p in procs:
+                p.start()
+            for p in procs:
+                p.join(timeout=600)
+                assert p.exitcode == 0
+        outs[mode] = pio.read_ply(str(d / "plot_ours.ply"))
+    a, b = outs["single"], outs["sharded"]
+    assert list(a.columns) == list(b.columns) == ["x", "y", "z", "reflectance", "n_z", "label", "pwood"]
+    for col in a.columns:
+        assert np.array_equal(a[col].to_numpy(), b[col].to_numpy()), col
