@@ -223,6 +223,16 @@ int p2w_knn_interpolate_add(const void *y, int32_t y_dtype, const float *pos_x, 
 int p2w_affine_relu(const void *x, void *y, int64_t n, int32_t c, const float *s1, const float *t1,
                     const float *s2, const float *t2, int32_t dtype, p2w_stream_t stream);
 
+/* The expand convolution of InvertedResidualBlock with its epilogue chain on tcgen05 (src/model.py:46-85, eval mode, BN folded):
+ * out[n, co] = relu(relu(x[n, :] . w[co, :] + bias[co]) * a[co] + c[co]) (a == c == NULL: the first ReLU only); x [n, k] and
+ * out [n, c_out] BF16 row-major, w [c_out, k] / bias / a / c FP32.  One pass instead of a library GEMM plus p2w_affine_relu over
+ * [n, c_out].  k a multiple of 64 in [64, 512].  ws: p2w_dense_expand_ws_bytes(k, c_out) bytes; flags bit 0: ws still holds the
+ * weights packed by an earlier call. */
+size_t p2w_dense_expand_ws_bytes(int32_t k, int32_t c_out);
+int p2w_dense_expand(const void *x, int64_t n, int32_t k, int32_t c_out, const float *w, const float *bias,
+                     const float *a, const float *c, void *out, void *ws, size_t ws_bytes, int32_t flags,
+                     p2w_stream_t stream);
+
 /* out[r] = dot(x[r, :], w) + bias over [n, c] FP32 / BF16 rows (c % 8 == 0, c <= 1024): the 1-channel head
  * conv2 (src/model.py:243) as one streaming pass instead of a GEMM with one output column. */
 int p2w_rowdot(const void *x, int32_t dtype, int64_t n, int32_t c, const float *w, float bias, float *out,

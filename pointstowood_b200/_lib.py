@@ -50,6 +50,8 @@ SIGNATURES = {
                                           _P, c_int32, _P]),
     "p2w_knn_interpolate_add": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_int32, _P]),
     "p2w_affine_relu": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, c_int32, _P]),
+    "p2w_dense_expand_ws_bytes": (c_size_t, [c_int32, c_int32]),
+    "p2w_dense_expand": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_size_t, c_int32, _P]),
     "p2w_rowdot": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_float, _P, _P]),
     "p2w_add_relu": (c_int32, [_P, _P, _P, c_int64, c_int32, _P]),
     "p2w_segment_max": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),

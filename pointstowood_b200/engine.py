@@ -53,6 +53,7 @@ class _Lin:
             w = torch.cat([w, w.new_zeros(w.size(0), pad_in)], dim=1)
         self.wt = w.t().contiguous().to(dtype)
         self.b = b.to(dtype).contiguous()
+        self.b32 = b.float().contiguous()
         self.relu = relu
 
     def __call__(self, x: Tensor) -> Tensor:
@@ -76,6 +77,12 @@ class _Residual:
 
         a0, c0 = dw(ds0)
         self.a0, self.c0 = f32(a0), f32(c0)
+        # bf16: the expand GEMM, its ReLU and this affine + ReLU in one tcgen05 kernel (csrc/dense_tc.cu)
+        c_in = self.expand.wt.size(0)
+        self.fused_expand = dtype == torch.bfloat16 and ops.DENSE_TC and c_in % 64 == 0 and 64 <= c_in <= 512
+        if self.fused_expand:
+            self.w_expand = self.expand.wt.t().float().contiguous()
+            self.ws_expand, self.ws_packed = None, False
         self.pw0 = _Lin(ds0.pointwise_conv.weight, ds0.pointwise_conv.bias, dtype, True, None, None,
                         *_affine(ds0.pointwise_bn))
         s1, t1 = _affine(blk.conv[1])
@@ -87,8 +94,14 @@ class _Residual:
         self.project = _Lin(blk.project[0].weight, blk.project[0].bias, dtype, False, s4, t4, *_affine(blk.project[1]))
 
     def __call__(self, x: Tensor) -> Tensor:
-        h = self.expand(x)
-        h = self.pw0(ops.affine_relu_(h, self.a0, self.c0))
+        if self.fused_expand and x.is_cuda:
+            if self.ws_expand is None or self.ws_expand.device != x.device:
+                self.ws_expand, self.ws_packed = ops.dense_expand_ws(x.size(1), self.w_expand.size(0), x.device), False
+            h = ops.dense_expand(x, self.w_expand, self.expand.b32, self.a0, self.c0, self.ws_expand, self.ws_packed)
+            self.ws_packed = True
+        else:
+            h = ops.affine_relu_(self.expand(x), self.a0, self.c0)
+        h = self.pw0(h)
         h = self.pw3(ops.affine_relu_(h, self.s1, self.t1, self.a3, self.c3))
         h = self.project(h)
         if h.numel() % 8 == 0 and h.is_contiguous() and x.is_contiguous() and h.dtype == x.dtype:

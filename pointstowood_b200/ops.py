@@ -16,6 +16,7 @@ streams only; every op raises if libp2w.so is missing or the tensors are not on 
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -572,6 +573,36 @@ def pointnet_conv_max(x: Tensor, pos_src: Tensor, pos_tgt: Tensor, nbr: Tensor, 
                                  _dp(pos_src), _dp(pos_tgt), _dp(nbr), x.size(0), n_tgt, nbr.size(1), C, H, Co,
                                  *[_dp(a) for a in args], _dp(out), _DT[out_dtype], mode, _dp(ws), ws.numel(),
                                  1 if packed else 0, _dp(tgt_index), _stream()))
+    return out
+
+
+DENSE_TC = os.environ.get("P2W_DENSE_TC", "1") != "0"        # 0: library GEMM + affine pass (A/B switch)
+
+
+def dense_expand_ws(k: int, c_out: int, device) -> Tensor:
+    return torch.empty(int(_lib.lib().p2w_dense_expand_ws_bytes(k, c_out)), device=device, dtype=torch.uint8)
+
+
+def dense_expand(x: Tensor, w: Tensor, bias: Tensor, a: Optional[Tensor], c: Optional[Tensor], ws: Optional[Tensor] = None,
+                 packed: bool = False) -> Tensor:
+    """relu(relu(x @ w.T + bias) * a + c) for bfloat16 rows x [n, k] and FP32 w [c_out, k] on tcgen05: the expand
+    convolution of InvertedResidualBlock with the depthwise + BatchNorm + ReLU that follows it (src/model.py:46-85) in ONE
+    pass over the [n, c_out] result.  `ws` (dense_expand_ws) with packed=True re-uses the weights laid out by an earlier call."""
+    x = _req(x, torch.bfloat16, "x", 2)
+    w, bias = _req(w, torch.float32, "w", 2), _req(bias, torch.float32, "bias", 1)
+    if w.size(1) != x.size(1) or bias.numel() != w.size(0):
+        raise _lib.P2WError("dense_expand: inconsistent shapes")
+    if (a is None) != (c is None):
+        raise _lib.P2WError("dense_expand: a and c go together")
+    if a is not None:
+        a, c = _req(a, torch.float32, "a", 1), _req(c, torch.float32, "c", 1)
+    if ws is None:
+        if packed:
+            raise _lib.P2WError("dense_expand: packed=True needs the workspace of the packing call")
+        ws = dense_expand_ws(x.size(1), w.size(0), x.device)
+    out = torch.empty((x.size(0), w.size(0)), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().p2w_dense_expand(_dp(x), x.size(0), x.size(1), w.size(0), _dp(w), _dp(bias), _dp(a), _dp(c), _dp(out),
+                                           _dp(ws), ws.numel(), 1 if packed else 0, _stream()))
     return out
 
 

@@ -264,3 +264,29 @@ def test_interpolate_add_is_interpolation_after_the_linear():
     assert torch.equal(got[~rows], torch.relu(z[~rows]))
     got16 = ops.knn_interpolate_add_(y.bfloat16(), pos_c, pos_f, z.bfloat16(), 2, ptr_c, ptr_f, relu=True)
     assert (got16.float() - want)[rows].abs().max().item() <= 0.05 * want[rows].abs().max().item()
+
+
+@pytest.mark.parametrize("n,k,c_out", [(1000, 128, 512), (12345, 256, 1024), (777, 512, 2048), (300, 64, 256), (129, 128, 200),
+                                       (0, 128, 512)])
+def test_dense_expand_matches_gemm_then_affine(p2w, n, k, c_out):
+    """p2w_dense_expand (tcgen05): relu(relu(x W^T + b) * a + c) in one pass equals the library GEMM with its bias + ReLU
+    epilogue followed by p2w_affine_relu, to bf16 rounding of the intermediate (which the fused kernel does not round)."""
+    _, ops = p2w
+    g = torch.Generator(device="cuda").manual_seed(n + k)
+    x = torch.randn(n, k, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(c_out, k, device="cuda", generator=g) / k ** 0.5).bfloat16().float()
+    b = torch.randn(c_out, device="cuda", generator=g) * 0.1
+    a = torch.randn(c_out, device="cuda", generator=g)
+    c = torch.randn(c_out, device="cuda", generator=g) * 0.1
+    ws = ops.dense_expand_ws(k, c_out, x.device)
+    got = ops.dense_expand(x, w, b, a, c, ws)
+    again = ops.dense_expand(x, w, b, a, c, ws, packed=True)             # the packed weights are re-used
+    assert torch.equal(got, again)
+    want = torch.relu(torch.relu(x.double() @ w.double().t() + b.double()) * a.double() + c.double())
+    assert got.shape == (n, c_out) and got.dtype == torch.bfloat16
+    if n:
+        err = (got.double() - want).abs()
+        assert float((err / (1.0 + want.abs())).max()) < 8e-3             # one bf16 rounding of the result
+        plain = ops.dense_expand(x, w, b, None, None)
+        want1 = torch.relu(x.double() @ w.double().t() + b.double())
+        assert float(((plain.double() - want1).abs() / (1.0 + want1)).max()) < 8e-3

@@ -46,6 +46,21 @@ def main():
             print(json.dumps(dict(block=name, gemm=tag, rows=n, k=k, n_out=m, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
                                   hbm_gbs=round(nbytes / ms / 1e6, 1), bound_math_ms=round(flops / PEAK_TF / 1e9, 4),
                                   bound_hbm_ms=round(nbytes / PEAK_GBS / 1e6, 4))), flush=True)
+        # the fused expand (csrc/dense_tc.cu): GEMM + ReLU + affine + ReLU, [n, 4c] written once
+        a = torch.randn(n, c, device="cuda", generator=g).bfloat16()
+        w32 = torch.randn(e, c, device="cuda", generator=g) * 0.05
+        b32, a32, c32 = (torch.randn(e, device="cuda", generator=g) * 0.1 for _ in range(3))
+        ws = ops.dense_expand_ws(c, e, a.device)
+        ops.dense_expand(a, w32, b32, a32, c32, ws)
+
+        def fused():
+            flush.zero_()
+            return ops.dense_expand(a, w32, b32, a32, c32, ws, packed=True)
+        ms = timed(fused) - timed(lambda: flush.zero_())
+        nbytes = 2.0 * n * (c + e)
+        print(json.dumps(dict(block=name, op="fused expand + affine (tcgen05)", rows=n, k=c, n_out=e, ms=round(ms, 4),
+                              tflops=round(2.0 * n * c * e / ms / 1e9, 1), hbm_gbs=round(nbytes / ms / 1e6, 1),
+                              bound_hbm_ms=round(nbytes / PEAK_GBS / 1e6, 4))), flush=True)
         x = torch.randn(n, e, device="cuda", generator=g).bfloat16()
         s1 = torch.rand(e, device="cuda", generator=g) + 0.5
         t1 = torch.randn(e, device="cuda", generator=g) * 0.1
