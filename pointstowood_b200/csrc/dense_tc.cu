@@ -9,15 +9,20 @@
 // costs as much as the GEMM itself (tools/bench_dense.py: 0.22 + 0.31 ms at N = 870 k, C = 128).  Here the [N, 4C] tensor
 // is written once.
 //
-// Same machinery as conv_tc.cu, minus the gather: A = a 128-row activation tile re-laid K-major (canonical no-swizzle layout)
-// by four loader warps with 16-byte loads / stores, B = weights, pre-packed bf16 in the same layout and streamed through a
-// ring of 16 KB slices by 1-D TMA bulk copies (resident when all of them fit).  D[n, co] lands in TMEM with one ROW per lane.
-// The epilogue is the critical role (output-bound GEMM: 1 KB of results per 128 MACs x 512 of a row at C = 128), hence EIGHT
-// epilogue warps, two per TMEM lane quarter, each taking half of the 128 columns in two passes of 32: accumulator -> both
-// stages with the constants read from shared memory (uniform addresses) -> bf16 into the warp's own staging rows -> read
-// back transposed so eight lanes write one row's 64 contiguous bytes (whole sectors; a direct store would scatter 16-byte
-// pieces over 32 lines per instruction and measured 2.6x slower).  Roles per persistent CTA: warps 0-7 epilogue, 8-11 tile
-// loader, 12 MMA issue (one elected lane), 13 weight producer.  Two 128-column accumulators alternate.
+// Same machinery as conv_tc.cu, minus the gather: the contraction runs transposed (D^T[co, n] = sum_k W[co, k] x[n, k]):
+// A = weights, pre-packed bf16 in the canonical no-swizzle K-major layout and streamed through a ring of 16 KB slices by 1-D
+// TMA bulk copies (resident when all of them fit), B = a 128-row activation tile re-laid K-major by four loader warps with
+// 16-byte loads / stores.  D^T lands in TMEM with one CHANNEL per lane, so bias, a, c are three registers of an epilogue
+// thread.  The epilogue is the critical role (output-bound GEMM: 1 KB of results per row for 128 x 512 MACs at C = 128), hence
+// SIXTEEN epilogue warps, four per TMEM lane quarter, each taking 32 of the 128 rows in two passes of 16: accumulator -> both
+// stages -> bf16, exchanged pairwise with the neighbouring lane so 32-bit words go into the warp's own staging block
+// [row][32 channels] -> read back with eight lanes per row, so a store instruction writes 8 rows x 64 contiguous bytes.
+// History of the epilogue on the SA1 block (870 k rows, C = 128; library GEMM 0.22 ms + affine pass 0.31 ms): 2-byte stores
+// from a channel-per-lane thread 0.71 ms; row-per-lane with 16-byte pieces stored straight from registers (32 lines per
+// instruction) and constants by __ldg 0.85 ms, constants prefetched 0.51 ms; constants in shared memory + staged rows 0.32 ms
+// with the LSU data pipe at 89 %; channel-per-lane + staging 0.32 ms (16-bit stores of two lanes into one word conflict);
+// pairwise exchange 0.30 ms; sixteen epilogue warps 0.28 ms.  Roles per persistent CTA: warps 0-15 epilogue, 16-19 tile
+// loader, 20 MMA issue (one elected lane), 21 weight producer.  Two 128-column accumulators alternate.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -30,12 +35,13 @@ constexpr int NT = 128;                        // rows per tile (MMA N)
 constexpr int SLICE_K = 64;                    // k extent of one ring slice: four K = 16 MMAs
 constexpr int SLICE_BYTES = 128 * SLICE_K * 2; // 16 KB: [8 k-chunks][128 rows][8 bf16]
 constexpr int MAX_STAGES = 12;
-constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32, LOAD_WARPS = 4, LOAD_THREADS = LOAD_WARPS * 32;
+constexpr int EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32, LOAD_WARPS = 4, LOAD_THREADS = LOAD_WARPS * 32;
 constexpr int THREADS = EPI_THREADS + LOAD_THREADS + 64;
 constexpr int MAX_TILE_BUFS = 2;
 constexpr int LU = 16;                         // 16-byte loads a loader thread keeps in flight
 constexpr int LBO_B = NT * 16 + 16;            // k-chunk stride of the activation tile, padded against bank conflicts
 constexpr int TMEM_COLS = 2 * NT;
+constexpr int ROWS_PER_WARP = NT / (EPI_WARPS / 4);       // epilogue warps per TMEM lane quarter split the tile's rows
 constexpr int MMA_WARP = EPI_WARPS + LOAD_WARPS, PRODUCER_WARP = MMA_WARP + 1;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -75,19 +81,6 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -105,8 +98,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 constexpr int STAGE_COLS = 32;                              // columns an epilogue warp transposes per pass
-constexpr int STAGE_ROW = STAGE_COLS * 2 + 16;              // bytes per staged row, padded against bank conflicts
-constexpr int STAGE_BYTES = 32 * STAGE_ROW;
+constexpr int STAGE_ROW = STAGE_COLS * 2;                   // bytes per staged row: 64, conflict-free both ways (see the epilogue)
+constexpr int PASS_ROWS = 16;                               // rows an epilogue warp takes through its staging block at a time
+constexpr int STAGE_BYTES = PASS_ROWS * STAGE_ROW;
 struct SmemLayout {
     uint32_t ring, tiles, stage, consts, bars, tmem, total;
 };
@@ -186,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseParams 
         }
         __syncwarp();
     } else if (warp == MMA_WARP) {
-        // ------------------------------------------------ MMA issuer (A = activation tile, B = weight slice)
+        // ------------------------------------------------ MMA issuer (A = weight slice, B = activation tile: D^T[co, n])
         int slot = 0, acc = 0, mbuf = 0;
         uint32_t ph = 0, mph = 0, use0 = 0, use1 = 0;
         const uint64_t a_desc0 = smem_desc(smem_u32(ring), 2048, 128);
@@ -209,10 +203,10 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseParams 
                     if (stream || it == 0) mbar_wait(&ring_full[slot], ph);
                     const uint32_t ad = a_lo0 + static_cast<uint32_t>(slot) * (SLICE_BYTES >> 4);
                     if (elect_one()) {
-                        umma(d_addr, bd, b_hi, ad, a_hi, ID, s ? 1u : 0u);
-                        umma(d_addr, bd + bq, b_hi, ad + 256u, a_hi, ID, 1u);
-                        umma(d_addr, bd + 2u * bq, b_hi, ad + 512u, a_hi, ID, 1u);
-                        umma(d_addr, bd + 3u * bq, b_hi, ad + 768u, a_hi, ID, 1u);
+                        umma(d_addr, ad, a_hi, bd, b_hi, ID, s ? 1u : 0u);
+                        umma(d_addr, ad + 256u, a_hi, bd + bq, b_hi, ID, 1u);
+                        umma(d_addr, ad + 512u, a_hi, bd + 2u * bq, b_hi, ID, 1u);
+                        umma(d_addr, ad + 768u, a_hi, bd + 3u * bq, b_hi, ID, 1u);
                         if (stream) umma_commit(&ring_empty[slot]);
                     }
                     bd += 4u * bq;
@@ -261,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseParams 
             if (++mbuf == TILE_BUFS) { mbuf = 0; mph ^= 1; }
         }
     } else {
-        // ------------------------------------------------ epilogue warps: TMEM lane quarter q, column half h
+        // ------------------------------------------------ epilogue warps: TMEM lane quarter q (channels), row half h
         int acc = 0;
         uint32_t use0 = 0, use1 = 0;
         const int q = warp & 3, h = warp >> 2;
@@ -271,52 +265,50 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseParams 
         const float *sconst = reinterpret_cast<const float *>(smem + L.consts);
         const int nconst = p.NB * 128;
         for (int it = 0; it < my_tiles; it++) {
-            const int64_t row0 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x) * NT + 32 * q;
+            const int64_t t0 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(it) * gridDim.x) * NT;
             for (int blk = 0; blk < p.NB; blk++) {
+                const int cw = blk * 128 + 32 * q;                     // first channel of this warp
+                const float bias = sconst[cw + lane], a = sconst[nconst + cw + lane], c = sconst[2 * nconst + cw + lane];
                 mbar_wait(&acc_full[acc], (acc ? use1 : use0) & 1);
                 tc_fence_after();
-                // 64 columns per warp in two passes of 32: accumulator -> both stages (constants from shared memory, uniform
-                // addresses) -> bf16 into this warp's staging rows -> read back so that eight lanes cover one row's 64
-                // contiguous bytes: full 32-byte sectors leave the SM instead of 16-byte pieces of 32 different lines
+                // 32 rows per warp in two passes of 16: a lane owns ONE channel (its constants are registers); the bf16
+                // results go through the warp's own staging block [row][32 channels] and come back with eight lanes per
+                // row, so a store instruction writes 8 rows x 64 contiguous bytes (whole sectors)
 #pragma unroll 1
-                for (int j = 0; j < 2; j++) {
-                    const int col = 64 * h + STAGE_COLS * j, co0 = blk * 128 + col;
-                    uint32_t r[32];
-                    tmem_ld32(lane_taddr + acc * NT + col, r);
-                    const float4 *kb = reinterpret_cast<const float4 *>(sconst + co0);
-                    const float4 *ka = reinterpret_cast<const float4 *>(sconst + nconst + co0);
-                    const float4 *kc = reinterpret_cast<const float4 *>(sconst + 2 * nconst + co0);
+                for (int j = 0; j < ROWS_PER_WARP / PASS_ROWS; j++) {
+                    const int r0 = ROWS_PER_WARP * h + PASS_ROWS * j;
+                    uint32_t r[PASS_ROWS];
+                    tmem_ld16(lane_taddr + acc * NT + r0, r);
+                    // 2 x 2 exchange with the neighbouring lane: an even lane ends up with rows e, e + 2 of channels (L, L + 1), an
+                    // odd one with rows e + 1, e + 3 of (L - 1, L): 32-bit stores, sixteen lanes per row and two adjacent rows
+                    // per instruction = all 32 banks once (16-bit stores of two lanes into one word cost a second wavefront)
+                    const bool odd = lane & 1;
+                    unsigned char *sw = stage + (odd ? STAGE_ROW : 0) + (lane & ~1) * 2;
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        uint32_t o[4];
+                    for (int e = 0; e < PASS_ROWS; e += 4) {
+                        float v[4];
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            const float4 b4 = kb[2 * g + u];
-                            float v0 = fmaxf(__uint_as_float(r[8 * g + 4 * u + 0]) + b4.x, 0.f);
-                            float v1 = fmaxf(__uint_as_float(r[8 * g + 4 * u + 1]) + b4.y, 0.f);
-                            float v2 = fmaxf(__uint_as_float(r[8 * g + 4 * u + 2]) + b4.z, 0.f);
-                            float v3 = fmaxf(__uint_as_float(r[8 * g + 4 * u + 3]) + b4.w, 0.f);
-                            if (two) {
-                                const float4 a4 = ka[2 * g + u], c4 = kc[2 * g + u];
-                                v0 = fmaxf(fmaf(v0, a4.x, c4.x), 0.f);
-                                v1 = fmaxf(fmaf(v1, a4.y, c4.y), 0.f);
-                                v2 = fmaxf(fmaf(v2, a4.z, c4.z), 0.f);
-                                v3 = fmaxf(fmaf(v3, a4.w, c4.w), 0.f);
-                            }
-                            __nv_bfloat162 t = __floats2bfloat162_rn(v0, v1);
-                            o[2 * u] = *reinterpret_cast<uint32_t *>(&t);
-                            t = __floats2bfloat162_rn(v2, v3);
-                            o[2 * u + 1] = *reinterpret_cast<uint32_t *>(&t);
+                        for (int u = 0; u < 4; u++) {
+                            v[u] = fmaxf(__uint_as_float(r[e + u]) + bias, 0.f);
+                            if (two) v[u] = fmaxf(fmaf(v[u], a, c), 0.f);
                         }
-                        *reinterpret_cast<uint4 *>(stage + lane * STAGE_ROW + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                        __nv_bfloat162 t = __floats2bfloat162_rn(v[0], v[2]);
+                        const uint32_t pa = *reinterpret_cast<uint32_t *>(&t);       // rows e, e + 2
+                        t = __floats2bfloat162_rn(v[1], v[3]);
+                        const uint32_t pb = *reinterpret_cast<uint32_t *>(&t);       // rows e + 1, e + 3
+                        const uint32_t got = __shfl_xor_sync(FULL, odd ? pa : pb, 1);
+                        const uint32_t x = odd ? got : pa, y = odd ? pb : got;       // (channel L&~1, channel L|1)
+                        *reinterpret_cast<uint32_t *>(sw + e * STAGE_ROW) = __byte_perm(x, y, 0x5410);
+                        *reinterpret_cast<uint32_t *>(sw + (e + 2) * STAGE_ROW) = __byte_perm(x, y, 0x7632);
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int rr = i * 8 + (lane >> 2), c = lane & 3;
-                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + rr * STAGE_ROW + c * 16);
-                        if (row0 + rr < p.n && co0 + c * 8 < p.Co)                  // Co % 8 == 0: a group of 8 is all in or all out
-                            *reinterpret_cast<uint4 *>(p.out + (row0 + rr) * p.Co + co0 + c * 8) = v;
+                    for (int i = 0; i < PASS_ROWS / 8; i++) {
+                        const int rr = i * 8 + (lane >> 2), c8 = (lane & 3) * 8;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + rr * STAGE_ROW + c8 * 2);
+                        const int64_t row = t0 + r0 + rr;
+                        if (row < p.n && cw + c8 < p.Co)                             // Co % 8 == 0: a group of 8 is all in or all out
+                            *reinterpret_cast<uint4 *>(p.out + row * p.Co + cw + c8) = v;
                     }
                     __syncwarp();
                 }
@@ -398,13 +390,14 @@ extern "C" int p2w_dense_expand(const void *x, int64_t n, int32_t k, int32_t c_o
         P2W_LAUNCH(dense_padvec_kernel, (t.NB * 128 + 255) / 256, 256, 0, st)(c, c_out, t.NB * 128, 0.f, cp);
     }
     const int per_tile = t.NB * (k / SLICE_K);
-    // two activation tiles (the next one loads while this one multiplies) when a useful ring still fits beside them
-    int tile_bufs = MAX_TILE_BUFS, stages = 0;
-    for (; tile_bufs >= 1; tile_bufs--) {
-        const unsigned fixed = smem_layout(k, t.NB, 0, tile_bufs).total;
+    // Two activation tiles (the next one loads while this one multiplies) whenever a ring of three slices still fits beside
+    // them: trading the second tile for a deeper ring measured slower (K = 256: 0.35 ms against 0.29 ms)
+    int tile_bufs = 0, stages = 0;
+    for (int tb = MAX_TILE_BUFS; tb >= 1 && !tile_bufs; tb--) {
+        const unsigned fixed = smem_layout(k, t.NB, 0, tb).total;
         if (fixed + 3u * SLICE_BYTES > 227u * 1024u) continue;
+        tile_bufs = tb;
         stages = static_cast<int>((227u * 1024u - fixed) / SLICE_BYTES);
-        break;
     }
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     P2W_REQUIRE(tile_bufs >= 1 && stages >= 3, "p2w_dense_expand: k=%d leaves no room for the weight ring", k);
