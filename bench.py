@@ -108,6 +108,11 @@ class ClockSampler:
         if self.proc:
             time.sleep(0.25)
             self.proc.terminate()
+            try:                                  # gone before the next timed region starts (it holds driver locks while it queries)
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+                self.proc.wait()
             self.thread.join(timeout=2)
 
     def summary(self):

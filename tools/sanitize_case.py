@@ -1,7 +1,8 @@
 """Small invocations of the hand-written kernels for compute-sanitizer (memcheck / racecheck / synccheck):
 conv_tc_kernel at the three SA widths, the brute-force sweep, the warp-per-query and heap cell-list kernels, the
-radix sort + unique pass, pack / write-back and the vote.  Results are checked against the oracle / the FP32 kernel so
+radix sort + unique pass, pack / write-back, the vote and the fused expand GEMM (dense_tc_kernel).  Results are checked against the oracle / the FP32 kernel so
 that a sanitizer-clean run is also a correct one.  Usage: compute-sanitizer --tool memcheck python tools/sanitize_case.py
+[dense]  ("dense": only the fused expand case).
 (P2W_KNN_HEAP=1 in the environment sends every k >= 5 search through the heap kernel, P2W_KNN_WARP=1 through the warp kernel.)"""
 import os
 import sys
@@ -15,6 +16,25 @@ from pointstowood_b200 import ops  # noqa: E402
 
 rng = np.random.default_rng(0)
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def dense_case():
+    """dense_tc_kernel: resident (K = 128) and streamed (K = 256, 512) weight rings, ragged last tile, c_out not a multiple of 128"""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for n, k, co in ((1000, 128, 512), (700, 256, 1024), (300, 512, 2048), (129, 64, 200)):
+        xs = torch.randn(n, k, device="cuda", generator=g).bfloat16()
+        w = (torch.randn(co, k, device="cuda", generator=g) / k ** 0.5).bfloat16().float()
+        b, a, c = (torch.randn(co, device="cuda", generator=g) * 0.3 for _ in range(3))
+        got = ops.dense_expand(xs, w, b, a, c).double()
+        want = torch.relu(torch.relu(xs.double() @ w.double().t() + b.double()) * a.double() + c.double())
+        assert float(((got - want).abs() / (1.0 + want.abs())).max()) < 8e-3, (n, k, co)
+    torch.cuda.synchronize()
+
+
+if sys.argv[1:] == ["dense"]:
+    dense_case()
+    print("sanitize_case ok (dense)")
+    sys.exit(0)
 # ---- neighbour searches (sweep_kernel, grid_query_kernel, grid_query_heap_kernel, grid_query_small_kernel)
 sizes = [1500, 0, 700, 2300]
 x = rng.random((sum(sizes), 3)).astype(np.float32)
@@ -60,5 +80,6 @@ pos, refl, b, shift, sf = ops.pack_tiles(cloud, None, dev(ptr))
 prob, pred, xyz = ops.writeback(torch.randn(len(x), device="cuda"), pos, dev(ptr), shift, 0.5, want_xyz=True)
 label, pwood = ops.spatial_vote(xyz, prob, pred, cloud[:, :3].contiguous(), 64, 1.0)
 assert bool(((pwood >= 0) & (pwood <= 1)).all())
+dense_case()
 torch.cuda.synchronize()
 print("sanitize_case ok")
