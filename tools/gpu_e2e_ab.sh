@@ -1,5 +1,9 @@
 #!/bin/bash
-for v in 1 0 1 0; do
-P2W_DENSE_TC=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('dense_tc=$v', round(d['ms_per_step'],2), 'e2e ms', round(1e9/d['e2e']['value'],2))"
-done
-nvidia-smi --query-gpu=pcie.link.gen.current,pcie.link.width.current --format=csv
+# host-to-host step time: default run, without the CPU leg, with the fused expand off
+mkdir -p gpurun_out
+timeout 600 python bench.py > gpurun_out/f_bench1.json 2> gpurun_out/f_bench1.err; grep "host-to-host" gpurun_out/f_bench1.err
+python -c "
+import json; d=json.load(open('gpurun_out/f_bench1.json')); print(d['ms_per_step'], d['e2e'], d['roofline']['frac'], d['cpu_baseline']['value'])"
+timeout 300 python bench.py --no-cpu-baseline 2>&1 >/dev/null | grep "host-to-host"
+P2W_DENSE_TC=0 timeout 300 python bench.py --no-cpu-baseline 2>&1 >/dev/null | grep "host-to-host"
+timeout 300 python bench.py --no-cpu-baseline --steps 8 2>&1 >/dev/null | grep "host-to-host"
